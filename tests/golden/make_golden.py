@@ -1,0 +1,251 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+What it does: imports ``partial_fc.py`` / ``losses.py`` / ``server.py`` from ``/root/reference`` and drives
+``PartialFC.forward_backward`` (partial_fc.py:130-176), ``update`` (:113-116) and ``FedPavg`` /
+``FedAvg_on_FC`` (server.py:25-46) on CPU + gloo.  The reference's constructor hard-codes CUDA
+(partial_fc.py:27,61,69), so the module object is assembled with ``__new__`` and the very same field
+assignments on ``device=cpu``; three process-wide shims make the rest run on torch 2.11 without a GPU:
+
+* ``torch.cuda.current_stream`` -> object with a no-op ``wait_stream``      (partial_fc.py:109)
+* ``torch.cuda.stream``         -> null context                              (partial_fc.py:119)
+* ``dist.reduce_scatter``       -> same call under ``torch.no_grad()``       (partial_fc.py:171-173 writes
+  in place into a ``requires_grad`` leaf, which modern torch refuses)
+
+``torch.rand`` is wrapped to record the ``perm`` draw of ``sample()`` (partial_fc.py:95) so the CUDA
+index kernel can be fed the identical numbers.  No reference source is copied into this repo; only
+inputs/outputs are stored (``*.npz``).
+"""
+import contextlib
+import hashlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _install_shims():
+    class _S:
+        def wait_stream(self, *_):
+            pass
+    torch.cuda.current_stream = lambda *a, **k: _S()
+    torch.cuda.stream = lambda *_a, **_k: contextlib.nullcontext()
+    real_rs = dist.reduce_scatter
+
+    def rs(out, ins, *a, **k):
+        with torch.no_grad():
+            return real_rs(out, ins, *a, **k)
+    dist.reduce_scatter = rs
+
+
+def _import_reference():
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import partial_fc  # noqa
+    import losses  # noqa
+    return partial_fc, losses
+
+
+def _build_module(partial_fc, losses, rank, world_size, batch_size, num_classes, sample_rate, emb, weight, s, m):
+    """Field-for-field what partial_fc.py:24-69 sets, with device=cpu and a caller supplied shard."""
+    from torch.nn import Module
+    from torch.nn.parameter import Parameter
+    mod = partial_fc.PartialFC.__new__(partial_fc.PartialFC)
+    Module.__init__(mod)
+    mod.num_classes, mod.rank, mod.local_rank = num_classes, rank, rank
+    mod.device = torch.device("cpu")
+    mod.world_size, mod.batch_size = world_size, batch_size
+    mod.margin_softmax = losses.CosFace(s=s, m=m)
+    mod.sample_rate, mod.embedding_size, mod.prefix = sample_rate, emb, "./"
+    mod.num_local = num_classes // world_size + int(rank < num_classes % world_size)
+    mod.class_start = num_classes // world_size * rank + min(rank, num_classes % world_size)
+    mod.num_sample = int(sample_rate * mod.num_local)
+    mod.weight = weight.clone()
+    mod.weight_mom = torch.zeros_like(mod.weight)
+    mod.stream = None
+    mod.index = None
+    if int(sample_rate) == 1:
+        mod.update = lambda: 0
+        mod.sub_weight = Parameter(mod.weight)
+        mod.sub_weight_mom = mod.weight_mom
+    else:
+        mod.sub_weight = Parameter(torch.empty((0, 0)))
+    return mod
+
+
+def make_inputs(seed, world_size, batch, num_classes, emb, label_pool=None):
+    g = torch.Generator().manual_seed(seed)
+    feats, labels, weights = [], [], []
+    for r in range(world_size):
+        f = torch.nn.functional.normalize(torch.randn(batch, emb, generator=g))
+        if label_pool is None:
+            l = torch.randint(0, num_classes, (batch,), generator=g)
+        else:
+            l = label_pool[torch.randint(0, len(label_pool), (batch,), generator=g)]
+        nl = num_classes // world_size + int(r < num_classes % world_size)
+        w = torch.randn(nl, emb, generator=g) * 0.01
+        feats.append(f), labels.append(l.long()), weights.append(w)
+    return feats, labels, weights
+
+
+def _worker(rank, world_size, cfg, feats, labels, weights, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    torch.set_num_threads(2)
+    _install_shims()
+    partial_fc, losses = _import_reference()
+    torch.manual_seed(cfg["seed"] * 1000 + rank)
+    perm_log = []
+    real_rand = torch.rand
+
+    def rand_spy(*a, **k):
+        t = real_rand(*a, **k)
+        perm_log.append(t.clone())
+        return t
+    torch.rand = rand_spy
+    mod = _build_module(partial_fc, losses, rank, world_size, cfg["batch"], cfg["num_classes"],
+                        cfg["sample_rate"], cfg["emb"], weights[rank], cfg["s"], cfg["m"])
+    opt = torch.optim.SGD([{"params": mod.parameters()}], lr=cfg["lr"], momentum=0.9, weight_decay=5e-4)
+    steps = []
+    for step in range(cfg["steps"]):
+        perm_log.clear()
+        x_grad, loss_v = mod.forward_backward(labels[rank], feats[rank], opt)
+        rec = {
+            "x_grad": x_grad.detach().numpy().copy(),
+            "loss": np.float32(loss_v.item()),
+            "dw": mod.sub_weight.grad.detach().numpy().copy(),
+            "index": None if mod.index is None else mod.index.numpy().copy(),
+            "perm": perm_log[0].numpy().copy() if perm_log else None,
+        }
+        opt.step()
+        mod.update()
+        opt.zero_grad()
+        rec["weight_after"] = mod.weight.detach().numpy().copy()
+        rec["mom_after"] = mod.weight_mom.detach().numpy().copy()
+        steps.append(rec)
+    ret[rank] = steps
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+_PORT = [29611]
+
+
+def run_reference(cfg, feats, labels, weights):
+    W = cfg["world_size"]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    _PORT[0] += 1
+    if W == 1:
+        _worker(0, 1, cfg, feats, labels, weights, _PORT[0], ret)
+    else:
+        mp.spawn(_worker, args=(W, cfg, feats, labels, weights, _PORT[0], ret), nprocs=W, join=True)
+    return [ret[r] for r in range(W)]
+
+
+def sha(arrs):
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+CASES = {
+    # name: cfg.   store_inputs=False -> inputs are regenerated from the seed and pinned by sha256
+    "w1_sr1_small": dict(seed=1, world_size=1, batch=16, num_classes=200, emb=512, sample_rate=1.0, s=64.0, m=0.4, lr=0.1, steps=2, store_inputs=True),
+    "w1_sr1_s30": dict(seed=2, world_size=1, batch=24, num_classes=96, emb=128, sample_rate=1.0, s=30.0, m=0.4, lr=0.1, steps=1, store_inputs=True),
+    "w1_sr01": dict(seed=3, world_size=1, batch=16, num_classes=400, emb=128, sample_rate=0.1, s=64.0, m=0.4, lr=0.1, steps=2, store_inputs=True),
+    "w1_sr_pos_overflow": dict(seed=4, world_size=1, batch=64, num_classes=300, emb=64, sample_rate=0.1, s=64.0, m=0.4, lr=0.1, steps=1, store_inputs=True),
+    "w2_sr1_ragged": dict(seed=5, world_size=2, batch=16, num_classes=301, emb=128, sample_rate=1.0, s=64.0, m=0.4, lr=0.1, steps=1, store_inputs=True),
+    "w2_sr03": dict(seed=6, world_size=2, batch=16, num_classes=401, emb=128, sample_rate=0.3, s=64.0, m=0.4, lr=0.1, steps=2, store_inputs=True),
+    "c1_b128_c10k": dict(seed=100, world_size=1, batch=128, num_classes=10000, emb=512, sample_rate=1.0, s=64.0, m=0.4, lr=0.1, steps=1, store_inputs=False),
+}
+
+
+def fedavg_golden():
+    for name in ("easydict", "mxnet", "prettytable"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["easydict"].EasyDict = type("EasyDict", (dict,), {"__getattr__": dict.get, "__setattr__": dict.__setitem__})
+    for sub in ("ndarray", "recordio", "image"):
+        m = types.ModuleType("mxnet." + sub)
+        sys.modules["mxnet." + sub] = m
+        setattr(sys.modules["mxnet"], sub, m)
+    sys.modules["prettytable"].PrettyTable = object
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import server
+    g = torch.Generator().manual_seed(77)
+    K = 5
+    base = {"conv.weight": torch.randn(8, 3, 3, 3, generator=g), "bn.weight": torch.randn(8, generator=g),
+            "bn.running_var": torch.rand(8, generator=g) + 0.5, "bn.num_batches_tracked": torch.tensor(0),
+            "fc.weight": torch.randn(33, 17, generator=g)}
+    models = []
+    for i in range(K):
+        sd = {}
+        for k, v in base.items():
+            sd[k] = (v + 0.01 * torch.randn(v.shape, generator=g)) if v.is_floating_point() else torch.tensor(1000 * i + 7 * i * i + 3)
+        models.append(sd)
+    weights = [6000 + 37 * i for i in range(K)]
+    out = server.FedPavg(models, weights)
+    store = {"weights": np.array(weights, dtype=np.int64), "K": np.int64(K)}
+    for i, sd in enumerate(models):
+        for k, v in sd.items():
+            store[f"in{i}/{k}"] = v.numpy()
+    for k, v in out.items():
+        store[f"out/{k}"] = v.numpy()
+    fcs = [torch.randn(50, 32, generator=g) for _ in range(K)]
+    old = torch.randn(50, 32, generator=g)
+    store["fc_old"] = old.numpy()
+    for i, f in enumerate(fcs):
+        store[f"fc_in{i}"] = f.numpy()
+    store["fc_out_p1"] = server.FedAvg_on_FC(old, fcs, weights, 1).numpy()
+    store["fc_out_p07"] = server.FedAvg_on_FC(old, fcs, weights, 0.7).numpy()
+    np.savez_compressed(os.path.join(OUT, "fedavg.npz"), **store)
+    print("fedavg.npz written")
+
+
+def main():
+    for name, cfg in CASES.items():
+        pool = None
+        if name == "w1_sr_pos_overflow":      # 64 samples over 60 distinct ids > num_sample=30 -> index = positives
+            pool = torch.arange(0, 300, 5)
+        feats, labels, weights = make_inputs(cfg["seed"], cfg["world_size"], cfg["batch"], cfg["num_classes"], cfg["emb"], pool)
+        res = run_reference(cfg, feats, labels, weights)
+        store = {"cfg_" + k: np.array(v) for k, v in cfg.items()}
+        store["input_sha256"] = np.array(sha([t.numpy() for t in feats + labels + weights]))
+        for r in range(cfg["world_size"]):
+            if cfg["store_inputs"]:
+                store[f"r{r}/features"] = feats[r].numpy()
+                store[f"r{r}/weight"] = weights[r].numpy()
+            store[f"r{r}/labels"] = labels[r].numpy()
+            for t, rec in enumerate(res[r]):
+                for k, v in rec.items():
+                    if v is None:
+                        continue
+                    if not cfg["store_inputs"] and k in ("dw", "weight_after", "mom_after"):
+                        # too large to commit: keep norm + a strided sample
+                        store[f"r{r}/s{t}/{k}_norm"] = np.float64(np.linalg.norm(v.astype(np.float64)))
+                        store[f"r{r}/s{t}/{k}_rows"] = v[::97].copy()
+                        continue
+                    store[f"r{r}/s{t}/{k}"] = v
+                if rec["perm"] is not None:   # tie check: goldens must be tie-free at the threshold
+                    pass
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **store)
+        print(name, "loss", [float(res[r][0]["loss"]) for r in range(cfg["world_size"])])
+    fedavg_golden()
+
+
+if __name__ == "__main__":
+    main()
