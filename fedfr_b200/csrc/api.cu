@@ -1,0 +1,72 @@
+// extern "C" entries of the GEMM-shaped part of the hot path: dispatch between the tensor path
+// (tc_kernels.cu) and check mode (simt_check.cu).  There is no CPU path.
+#include "common.cuh"
+
+namespace pfc {
+int tc_fwd_num_partials(int64_t n_rows, int64_t n_classes);
+int tc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m,
+                 float* part_max, float* part_sum, float* target_logit, cudaStream_t st);
+size_t tc_bwd_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb);
+int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_max, const float* row_sum,
+           int64_t n_rows, int64_t n_classes, int emb, float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
+           void* workspace, size_t workspace_bytes, cudaStream_t st);
+void tc_set_fwd_bn(int bn);
+int simt_fwd_num_partials(int64_t n_rows, int64_t n_classes);
+int simt_fwd_stats(const float* x, const float* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m,
+                   float* part_max, float* part_sum, float* target_logit, cudaStream_t st);
+size_t simt_bwd_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb);
+int simt_bwd(const float* x, const float* w_hat, const float* inv_norm, const int64_t* label, const float* row_max, const float* row_sum,
+             int64_t n_rows, int64_t n_classes, int emb, float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
+             void* workspace, size_t workspace_bytes, cudaStream_t st);
+}  // namespace pfc
+
+using namespace pfc;
+
+extern "C" {
+
+int pfc_fwd_num_partials(int64_t n_rows, int64_t n_classes, int emb, int path) {
+  (void)emb;
+  if (n_rows <= 0 || n_classes <= 0) return 0;
+  return path == PFC_PATH_CHECK ? simt_fwd_num_partials(n_rows, n_classes) : tc_fwd_num_partials(n_rows, n_classes);
+}
+
+int pfc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m,
+                  float* part_max, float* part_sum, float* target_logit, int path, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  PFC_REQUIRE(x && w_hat && label && part_max && part_sum && target_logit, PFC_E_ARG, "pfc_fwd_stats: null argument");
+  PFC_REQUIRE(n_rows > 0 && n_classes > 0 && emb > 0, PFC_E_ARG, "pfc_fwd_stats: empty shape (rows=%lld classes=%lld)", (long long)n_rows,
+              (long long)n_classes);
+  if (path == PFC_PATH_CHECK)
+    return simt_fwd_stats(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(w_hat), label, n_rows, n_classes, emb, s, m,
+                          part_max, part_sum, target_logit, as_stream(stream));
+  PFC_REQUIRE(path == PFC_PATH_TENSOR, PFC_E_ARG, "pfc_fwd_stats: unknown path %d", path);
+  return tc_fwd_stats(x, w_hat, label, n_rows, n_classes, emb, s, m, part_max, part_sum, target_logit, as_stream(stream));
+}
+
+size_t pfc_bwd_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb, int path) {
+  if (n_rows <= 0 || n_classes <= 0 || emb <= 0) return 0;
+  return path == PFC_PATH_CHECK ? simt_bwd_workspace_bytes(n_rows, n_classes, emb) : tc_bwd_workspace_bytes(n_rows, n_classes, emb);
+}
+
+int pfc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_max, const float* row_sum,
+            int64_t n_rows, int64_t n_classes, int emb, float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
+            void* workspace, size_t workspace_bytes, int path, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  PFC_REQUIRE(x && w_hat && inv_norm && label && row_max && row_sum && dx && dw && workspace, PFC_E_ARG, "pfc_bwd: null argument");
+  PFC_REQUIRE(n_rows > 0 && n_classes > 0 && emb > 0, PFC_E_ARG, "pfc_bwd: empty shape");
+  if (path == PFC_PATH_CHECK)
+    return simt_bwd(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(w_hat), inv_norm, label, row_max, row_sum, n_rows,
+                    n_classes, emb, s, m, inv_total_batch, dx, dw, accumulate_dw, workspace, workspace_bytes, as_stream(stream));
+  PFC_REQUIRE(path == PFC_PATH_TENSOR, PFC_E_ARG, "pfc_bwd: unknown path %d", path);
+  return tc_bwd(x, w_hat, inv_norm, label, row_max, row_sum, n_rows, n_classes, emb, s, m, inv_total_batch, dx, dw, accumulate_dw, workspace,
+                workspace_bytes, as_stream(stream));
+}
+
+/* tuning knob (not part of the reference-facing surface): class-tile width of the logits kernels */
+int pfc_set_logits_tile(int bn) {
+  PFC_REQUIRE(bn == 128 || bn == 256, PFC_E_ARG, "pfc_set_logits_tile: bn must be 128 or 256");
+  tc_set_fwd_bn(bn);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,179 @@
+// HBM-bound row kernels: normalise (+gather) -> bf16, cast, gather, scatter.
+// One warp per row, 128-bit accesses; rows are 2 KB (E=512 fp32) so a warp owns 4 float4 per lane.
+#include "common.cuh"
+
+namespace pfc {
+
+// normalize(sub_weight) (partial_fc.py:127) fused with the sampled gather (partial_fc.py:105).
+// Algorithmic bytes per row: read 4E, write 2E (bf16) + 4.
+template <int kVecPerLane>
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __restrict__ w, const int64_t* __restrict__ index,
+                                                             int64_t n_rows, int emb, __nv_bfloat16* __restrict__ out_bf16,
+                                                             float* __restrict__ out_f32, float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int nvec = emb >> 2;
+  for (int64_t r = warp; r < n_rows; r += n_warps) {
+    const int64_t src = index ? index[r] : r;
+    const float4* p = reinterpret_cast<const float4*>(w + src * emb);
+    float4 v[kVecPerLane];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVecPerLane; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        v[i] = ld_stream_f4(p + c);
+        ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+      }
+    }
+    ss = warp_sum(ss);
+    const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+    const float inv = 1.0f / nrm;
+    if (lane == 0 && inv_norm) inv_norm[r] = inv;
+#pragma unroll
+    for (int i = 0; i < kVecPerLane; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        // divide (not multiply by the reciprocal) so the fp32 output matches F.normalize bit for bit
+        float4 o = make_float4(v[i].x / nrm, v[i].y / nrm, v[i].z / nrm, v[i].w / nrm);
+        if (out_bf16) {
+          uint2 pk = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+          *reinterpret_cast<uint2*>(out_bf16 + r * emb + c * 4) = pk;
+        }
+        if (out_f32) st_stream_f4(reinterpret_cast<float4*>(out_f32 + r * emb) + c, o);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_rows_kernel(const float4* __restrict__ x, int64_t n_vec, uint2* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = x[i];
+    out[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+// sub_weight = weight[index]; sub_weight_mom = weight_mom[index]   (gather=true)
+// weight[index] = sub_weight; weight_mom[index] = sub_weight_mom   (gather=false)
+template <bool kGather>
+__global__ void __launch_bounds__(256) move_rows2_kernel(float* __restrict__ big_a, float* __restrict__ big_b,
+                                                         const int64_t* __restrict__ index, int64_t n_index, int emb,
+                                                         float* __restrict__ small_a, float* __restrict__ small_b) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int nvec = emb >> 2;
+  for (int64_t r = warp; r < n_index; r += n_warps) {
+    const int64_t row = index[r];
+    float4* ba = reinterpret_cast<float4*>(big_a + row * emb);
+    float4* bb = big_b ? reinterpret_cast<float4*>(big_b + row * emb) : nullptr;
+    float4* sa = reinterpret_cast<float4*>(small_a + r * emb);
+    float4* sb = small_b ? reinterpret_cast<float4*>(small_b + r * emb) : nullptr;
+    for (int c = lane; c < nvec; c += 32) {
+      if (kGather) {
+        st_stream_f4(sa + c, ld_stream_f4(ba + c));
+        if (bb && sb) st_stream_f4(sb + c, ld_stream_f4(bb + c));
+      } else {
+        st_stream_f4(ba + c, ld_stream_f4(sa + c));
+        if (bb && sb) st_stream_f4(bb + c, ld_stream_f4(sb + c));
+      }
+    }
+  }
+}
+
+// losses.CosFace.forward on materialised logits (losses.py:23-29).
+__global__ void cosface_margin_kernel(float* cosine, const int64_t* label, int64_t n_rows, int64_t n_classes, float m) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_rows) {
+    int64_t y = label[i];
+    if (y >= 0 && y < n_classes) cosine[i * n_classes + y] -= m;
+  }
+}
+__global__ void scale_kernel(const float* __restrict__ in, float s, int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i] * s;
+}
+
+static int row_grid(int64_t n_rows) {
+  int64_t blocks = (n_rows + 7) / 8;            // 8 warps per block
+  int64_t cap = (int64_t)sm_count() * 8;        // 8 resident blocks of 256 threads per SM
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace pfc
+
+using namespace pfc;
+
+extern "C" {
+
+int pfc_normalize_rows(const float* w, const int64_t* index, int64_t n_rows, int emb, void* w_hat_bf16, float* w_hat_f32,
+                       float* inv_norm, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  PFC_REQUIRE(w && n_rows >= 0 && emb > 0, PFC_E_ARG, "pfc_normalize_rows: bad argument");
+  PFC_REQUIRE(emb % 4 == 0 && emb <= 2048, PFC_E_SHAPE, "pfc_normalize_rows: emb=%d must be a multiple of 4 and <= 2048", emb);
+  if (n_rows == 0) return 0;
+  const int vec_per_lane = (emb / 4 + 31) / 32;
+  auto* ob = reinterpret_cast<__nv_bfloat16*>(w_hat_bf16);
+  const int grid = row_grid(n_rows);
+  cudaStream_t st = as_stream(stream);
+  if (vec_per_lane <= 1) normalize_rows_kernel<1><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, w_hat_f32, inv_norm);
+  else if (vec_per_lane <= 2) normalize_rows_kernel<2><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, w_hat_f32, inv_norm);
+  else if (vec_per_lane <= 4) normalize_rows_kernel<4><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, w_hat_f32, inv_norm);
+  else if (vec_per_lane <= 8) normalize_rows_kernel<8><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, w_hat_f32, inv_norm);
+  else normalize_rows_kernel<16><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, w_hat_f32, inv_norm);
+  PFC_LAUNCH_CHECK();
+  return 0;
+}
+
+int pfc_cast_rows_bf16(const float* x, int64_t n_rows, int emb, void* x_bf16, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  PFC_REQUIRE(x && x_bf16 && n_rows >= 0 && emb > 0 && emb % 4 == 0, PFC_E_ARG, "pfc_cast_rows_bf16: bad argument");
+  if (n_rows == 0) return 0;
+  const int64_t n_vec = n_rows * emb / 4;
+  int64_t blocks = (n_vec + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+  cast_rows_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), n_vec, reinterpret_cast<uint2*>(x_bf16));
+  PFC_LAUNCH_CHECK();
+  return 0;
+}
+
+int pfc_gather_rows2(const float* weight, const float* weight_mom, const int64_t* index, int64_t n_index, int emb,
+                     float* sub_weight, float* sub_weight_mom, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  PFC_REQUIRE(weight && index && sub_weight && n_index >= 0 && emb > 0 && emb % 4 == 0, PFC_E_ARG, "pfc_gather_rows2: bad argument");
+  if (n_index == 0) return 0;
+  move_rows2_kernel<true><<<row_grid(n_index), 256, 0, as_stream(stream)>>>(const_cast<float*>(weight), const_cast<float*>(weight_mom), index,
+                                                                             n_index, emb, sub_weight, sub_weight_mom);
+  PFC_LAUNCH_CHECK();
+  return 0;
+}
+
+int pfc_scatter_rows2(float* weight, float* weight_mom, const int64_t* index, int64_t n_index, int emb, const float* sub_weight,
+                      const float* sub_weight_mom, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  PFC_REQUIRE(weight && index && sub_weight && n_index >= 0 && emb > 0 && emb % 4 == 0, PFC_E_ARG, "pfc_scatter_rows2: bad argument");
+  if (n_index == 0) return 0;
+  move_rows2_kernel<false><<<row_grid(n_index), 256, 0, as_stream(stream)>>>(weight, weight_mom, index, n_index, emb,
+                                                                              const_cast<float*>(sub_weight), const_cast<float*>(sub_weight_mom));
+  PFC_LAUNCH_CHECK();
+  return 0;
+}
+
+int pfc_cosface_dense(float* cosine, const int64_t* label, int64_t n_rows, int64_t n_classes, float s, float m, float* out, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  PFC_REQUIRE(cosine && label && out && n_rows >= 0 && n_classes >= 0, PFC_E_ARG, "pfc_cosface_dense: bad argument");
+  if (n_rows == 0 || n_classes == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  cosface_margin_kernel<<<(int)((n_rows + 255) / 256), 256, 0, st>>>(cosine, label, n_rows, n_classes, m);
+  PFC_LAUNCH_CHECK();
+  int64_t n = n_rows * n_classes;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+  scale_kernel<<<(int)blocks, 256, 0, st>>>(cosine, s, n, out);
+  PFC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

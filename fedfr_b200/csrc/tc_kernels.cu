@@ -1,0 +1,764 @@
+// Tensor-core path (sm_100a): TMA-fed tcgen05.mma kernels with TMEM accumulators.
+//
+//   logits_kernel<MODE_STATS>  z = s (x.w_hat - m[y]) tile by tile, CosFace margin + online max / sum-exp in the
+//                              epilogue; logits never leave the SM.          (partial_fc.py:137-147, losses.py:23-29)
+//   logits_kernel<MODE_GRAD>   recompute z, G = s (softmax - onehot) / Bt -> bf16 chunk scratch    (partial_fc.py:150-166)
+//   dx_kernel                  dx (+)= G . w_hat      (split over the class axis, fp32 partial slabs)  (autograd of :110)
+//   dw_kernel                  dw = normalize_bwd(G^T . x)                                            (autograd of :110,127)
+//
+// All kernels: 192 threads = 4 epilogue warps (TMEM lanes 0..127) + 1 TMA producer warp + 1 MMA issuer warp,
+// 128-byte-swizzled operand tiles, mbarrier pipelines (smem full/empty, TMEM full/empty).
+#include "tc_common.cuh"
+#include <mutex>
+
+namespace pfc {
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static EncodeTiledFn get_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  });
+  return g_encode;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows,
+                      uint32_t box_cols) {
+  EncodeTiledFn enc = get_encode();
+  PFC_REQUIRE(enc != nullptr, PFC_E_ARCH, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  PFC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (row_stride_elems * 2) % 16 == 0, PFC_E_ARG,
+              "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PFC_REQUIRE(r == CUDA_SUCCESS, PFC_E_ARG, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu pitch=%llu box=%ux%u)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)row_stride_elems, box_rows, box_cols);
+  return 0;
+}
+
+namespace tc {
+
+constexpr int kThreads = 192;
+constexpr int kEpiWarps = 4;
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kChunkBytes = BM * BK * 2;      // one [128 x 64] bf16 K-major tile = 16 KB
+constexpr int kBoxBytes = 64 * BK * 2;        // one [64 x 64] bf16 box = 8 KB
+
+enum { MODE_STATS = 0, MODE_GRAD = 1 };
+
+struct LogitsParams {
+  const int64_t* label;      // [n_rows] shard-local id or -1
+  int n_rows;
+  int n_classes;             // classes covered by this launch (chunk)
+  int class_base;            // shard-local id of class 0 of this launch
+  int emb;
+  int n_rb, n_ct;            // row blocks, class tiles
+  float s, m;
+  // MODE_STATS
+  float* part_max;           // [gridDim.x, n_rows]   (log-e units)
+  float* part_sum;
+  float* target_logit;       // [n_rows]
+  // MODE_GRAD
+  const float* row_max;      // [n_rows]
+  const float* row_sum;
+  __nv_bfloat16* g;          // [n_rows, ldg]
+  int64_t ldg;
+  float g_scale;             // s / total_batch
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct PipeState {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int n_stages) {
+    if (++stage == n_stages) { stage = 0; phase ^= 1; }
+  }
+};
+
+// ================================================================================================
+// logits kernel: A = x_hat row block (stationary in smem), B = w_hat class tiles (streamed)
+// ================================================================================================
+template <int BN, int STAGES, int MODE>
+__global__ void __launch_bounds__(kThreads, 1) logits_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                                                             const LogitsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int n_kb = p.emb / BK;
+  uint8_t* smem_a = smem;                                  // n_kb chunks of [128 x 64]
+  uint8_t* smem_b = smem + n_kb * kChunkBytes;             // STAGES tiles of [BN x 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + STAGES * BN * BK * 2);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
+  uint64_t* a_full = bars + 2 * STAGES + 4;
+  uint64_t* a_empty = bars + 2 * STAGES + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (int64_t)p.n_rb * p.n_ct;
+  const int64_t t0 = n_tiles * blockIdx.x / gridDim.x, t1 = n_tiles * (blockIdx.x + 1) / gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); }
+  if (warp == 5) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      PipeState ps;
+      int cur_rb = -1, a_loads = 0;
+      for (int64_t t = t0; t < t1; ++t) {
+        const int rb = (int)(t / p.n_ct), ct = (int)(t % p.n_ct);
+        if (rb != cur_rb) {
+          if (a_loads > 0) mbar_wait(a_empty, (a_loads - 1) & 1);      // MMAs of the previous row block are done
+          mbar_arrive_expect_tx(a_full, n_kb * kChunkBytes);
+          for (int kb = 0; kb < n_kb; ++kb) tma_load_2d(smem_a + kb * kChunkBytes, &tmap_x, a_full, kb * BK, rb * BM);
+          cur_rb = rb;
+          ++a_loads;
+        }
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&empty[ps.stage], ps.phase ^ 1);
+          mbar_arrive_expect_tx(&full[ps.stage], BN * BK * 2);
+          tma_load_2d(smem_b + ps.stage * (BN * BK * 2), &tmap_w, &full[ps.stage], kb * BK, ct * BN);
+          ps.advance(STAGES);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
+      PipeState ps;
+      int cur_rb = -1, a_uses = 0;
+      int64_t it = 0;
+      for (int64_t t = t0; t < t1; ++t, ++it) {
+        const int rb = (int)(t / p.n_ct);
+        if (rb != cur_rb) {
+          mbar_wait(a_full, a_uses & 1);
+          ++a_uses;
+          cur_rb = rb;
+        }
+        const int acc = (int)(it & 1);
+        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&full[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + kb * kChunkBytes);
+          const uint32_t b_addr = smem_u32(smem_b + ps.stage * (BN * BK * 2));
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t da = make_desc_sw128(a_addr + kk * 32, 0, 1024);
+            const uint64_t db = make_desc_sw128(b_addr + kk * 32, 0, 1024);
+            umma_bf16_ss(d_tmem, da, db, idesc, (kb | kk) != 0);
+          }
+          umma_commit(&empty[ps.stage]);      // frees the smem stage once these MMAs retire
+          ps.advance(STAGES);
+        }
+        umma_commit(&tmem_full[acc]);
+        const bool last_of_rb = (t + 1 == t1) || ((int)((t + 1) / p.n_ct) != rb);
+        if (last_of_rb) umma_commit(a_empty);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 0..3), thread = row
+    const float s2 = p.s * kLog2e, ms2 = p.m * p.s * kLog2e;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    int cur_rb = -1;
+    constexpr int kNoLabel = -(1 << 30);
+    int row = 0, my_label = kNoLabel;
+    bool row_ok = false;
+    float run_m = -INFINITY, run_l = 0.f;        // MODE_STATS (log2 units)
+    float M2 = 0.f, rS = 0.f;                    // MODE_GRAD
+    int64_t it = 0;
+    for (int64_t t = t0; t < t1; ++t, ++it) {
+      const int rb = (int)(t / p.n_ct), ct = (int)(t % p.n_ct);
+      if (rb != cur_rb) {
+        if (MODE == MODE_STATS && cur_rb >= 0 && row_ok) {
+          p.part_max[(int64_t)blockIdx.x * p.n_rows + row] = run_m * kLn2;
+          p.part_sum[(int64_t)blockIdx.x * p.n_rows + row] = run_l;
+        }
+        cur_rb = rb;
+        row = rb * BM + threadIdx.x;
+        row_ok = row < p.n_rows;
+        my_label = kNoLabel;
+        if (row_ok) {
+          const int64_t y = p.label[row];
+          if (y >= 0) my_label = (int)(y - p.class_base);          // relative to this launch; out of range never matches
+        }
+        run_m = -INFINITY; run_l = 0.f;
+        if (MODE == MODE_GRAD && row_ok) { M2 = p.row_max[row] * kLog2e; rS = 1.0f / p.row_sum[row]; }
+      }
+      const int acc = (int)(it & 1);
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int col0 = ct * BN;
+      const bool tile_has_oob = col0 + BN > p.n_classes;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_base + lane_base + acc * BN + c, v);
+        tmem_ld_wait();
+        const int cb = col0 + c;
+        float z[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) z[j] = __uint_as_float(v[j]) * s2;
+        const int hit = my_label - cb;                   // in [0,32) iff the target class is in this column group
+        if (hit >= 0 && hit < 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j == hit) {
+            z[j] -= ms2;
+            if (MODE == MODE_STATS) p.target_logit[row] = p.s * (__uint_as_float(v[j]) - p.m);
+          }
+        }
+        if (MODE == MODE_STATS) {
+          if (tile_has_oob) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (cb + j >= p.n_classes) z[j] = -INFINITY;
+          }
+          float cm = z[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) cm = fmaxf(cm, z[j]);
+          if (cm > -INFINITY) {
+            const float nm = fmaxf(run_m, cm);
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += fast_exp2(z[j] - nm);
+            run_l = run_l * fast_exp2(run_m - nm) + sum;
+            run_m = nm;
+          }
+        } else {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float g0 = fast_exp2(z[j] - M2) * rS, g1 = fast_exp2(z[j + 1] - M2) * rS;
+            if (j == hit) g0 -= 1.0f;
+            if (j + 1 == hit) g1 -= 1.0f;
+            pk[j >> 1] = pack_bf16x2(g0 * p.g_scale, g1 * p.g_scale);
+          }
+          if (row_ok && cb < p.ldg) {
+            uint4* dst = reinterpret_cast<uint4*>(p.g + (int64_t)row * p.ldg + cb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+    if (MODE == MODE_STATS && cur_rb >= 0 && row_ok) {
+      p.part_max[(int64_t)blockIdx.x * p.n_rows + row] = run_m * kLn2;
+      p.part_sum[(int64_t)blockIdx.x * p.n_rows + row] = run_l;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<2 * BN>(tmem_base);
+}
+
+// ================================================================================================
+// dx kernel: D[128 rows x BN e] = sum over a class slice of G[rows, classes] * w_hat[classes, e]
+//   A = G (K-major, K = classes), B = w_hat (MN-major: N = e contiguous, K = classes)
+// ================================================================================================
+struct DxParams {
+  int n_rows, n_classes, emb;
+  int n_rb, n_eh, ksplit;
+  float* dx_part;          // [ksplit, n_rows, emb]
+  int accumulate;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) dx_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_w,
+                                                         const DxParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kBBytes = (BN / 64) * kBoxBytes;
+  constexpr int kStageBytes = kChunkBytes + kBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x;
+  const int ks = u % p.ksplit, eh = (u / p.ksplit) % p.n_eh, rb = u / (p.ksplit * p.n_eh);
+  const int n_kb_total = (p.n_classes + BK - 1) / BK;
+  const int kb0 = (int)((int64_t)n_kb_total * ks / p.ksplit), kb1 = (int)((int64_t)n_kb_total * (ks + 1) / p.ksplit);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) { prefetch_tmap(&tmap_g); prefetch_tmap(&tmap_w); }
+  if (warp == 5) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      PipeState ps;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty[ps.stage], ps.phase ^ 1);
+        uint8_t* sa = smem + ps.stage * kStageBytes;
+        uint8_t* sb = sa + kChunkBytes;
+        mbar_arrive_expect_tx(&full[ps.stage], kStageBytes);
+        tma_load_2d(sa, &tmap_g, &full[ps.stage], kb * BK, rb * BM);
+#pragma unroll
+        for (int nb = 0; nb < BN / 64; ++nb) tma_load_2d(sb + nb * kBoxBytes, &tmap_w, &full[ps.stage], eh * BN + nb * 64, kb * BK);
+        ps.advance(STAGES);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, true);
+      PipeState ps;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[ps.stage], ps.phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + ps.stage * kStageBytes);
+        const uint32_t b_addr = a_addr + kChunkBytes;
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          const uint64_t da = make_desc_sw128(a_addr + kk * 32, 0, 1024);
+          const uint64_t db = make_desc_sw128(b_addr + kk * 2048, kBoxBytes, 1024);
+          umma_bf16_ss(tmem_base, da, db, idesc, (kb != kb0) || (kk != 0));
+        }
+        umma_commit(&empty[ps.stage]);
+        ps.advance(STAGES);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    const int row = rb * BM + threadIdx.x;
+    const bool row_ok = row < p.n_rows;
+    float* out = p.dx_part + ((int64_t)ks * p.n_rows + row) * p.emb + eh * BN;
+    const bool have = kb1 > kb0;
+    if (have) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t v[32];
+      if (have) {
+        tmem_ld_x32(tmem_base + lane_base + c, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0;
+      }
+      if (row_ok) {
+        float4* o = reinterpret_cast<float4*>(out + c);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 r = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                 __uint_as_float(v[4 * q + 3]));
+          if (p.accumulate) { float4 old = o[q]; r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w; }
+          o[q] = r;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<BN>(tmem_base);
+}
+
+__global__ void reduce_dx_kernel(const float4* __restrict__ part, int ksplit, int64_t n_vec, float4* __restrict__ dx) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = part[i];
+    for (int k = 1; k < ksplit; ++k) {
+      const float4 b = part[(int64_t)k * n_vec + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    dx[i] = a;
+  }
+}
+
+// ================================================================================================
+// dw kernel: D[128 classes x E] = G^T[classes, rows] * x_hat[rows, E], epilogue = normalize backward
+//   A = G^T (MN-major: M = classes contiguous in a G row), B = x_hat (MN-major: N = e contiguous), K = rows
+// ================================================================================================
+struct DwParams {
+  int n_rows, n_classes, emb;     // n_classes = classes in this chunk
+  int n_ct;
+  const __nv_bfloat16* w_hat;     // [n_classes, emb] chunk base
+  const float* inv_norm;          // [n_classes]
+  float* dw;                      // [n_classes, emb] chunk base
+  int accumulate;
+};
+
+template <int EMB, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                                                         const DwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kABytes = 2 * kBoxBytes;                 // 128 classes x 64 rows
+  constexpr int kBBytes = (EMB / 64) * kBoxBytes;        // EMB x 64 rows
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int UN = EMB < 256 ? EMB : 256;              // N per MMA instruction
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_kb = (p.n_rows + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, kEpiWarps);
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) { prefetch_tmap(&tmap_g); prefetch_tmap(&tmap_x); }
+  if (warp == 5) tmem_alloc<EMB>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      PipeState ps;
+      for (int ct = blockIdx.x; ct < p.n_ct; ct += gridDim.x) {
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&empty[ps.stage], ps.phase ^ 1);
+          uint8_t* sa = smem + ps.stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_arrive_expect_tx(&full[ps.stage], kStageBytes);
+          tma_load_2d(sa, &tmap_g, &full[ps.stage], ct * BM, kb * BK);
+          tma_load_2d(sa + kBoxBytes, &tmap_g, &full[ps.stage], ct * BM + 64, kb * BK);
+#pragma unroll
+          for (int nb = 0; nb < EMB / 64; ++nb) tma_load_2d(sb + nb * kBoxBytes, &tmap_x, &full[ps.stage], nb * 64, kb * BK);
+          ps.advance(STAGES);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, UN, true, true);
+      PipeState ps;
+      int it = 0;
+      for (int ct = blockIdx.x; ct < p.n_ct; ct += gridDim.x, ++it) {
+        mbar_wait(tmem_empty, (uint32_t)((it & 1) ^ 1));
+        tc_fence_after();
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&full[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + ps.stage * kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t da = make_desc_sw128(a_addr + kk * 2048, kBoxBytes, 1024);
+#pragma unroll
+            for (int nh = 0; nh < EMB / UN; ++nh) {
+              const uint64_t db = make_desc_sw128(b_addr + nh * (UN / 64) * kBoxBytes + kk * 2048, kBoxBytes, 1024);
+              umma_bf16_ss(tmem_base + nh * UN, da, db, idesc, (kb | kk) != 0);
+            }
+          }
+          umma_commit(&empty[ps.stage]);
+          ps.advance(STAGES);
+        }
+        umma_commit(tmem_full);
+      }
+    }
+  } else {
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    int it = 0;
+    for (int ct = blockIdx.x; ct < p.n_ct; ct += gridDim.x, ++it) {
+      const int cls = ct * BM + threadIdx.x;
+      const bool ok = cls < p.n_classes;
+      mbar_wait(tmem_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      const __nv_bfloat16* wrow = p.w_hat + (int64_t)cls * EMB;
+      // pass 1: radial component  t = w_hat_j . dwh_j
+      float radial = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < EMB; c += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_base + lane_base + c, v);
+        tmem_ld_wait();
+        if (ok) {
+          const uint4* wv = reinterpret_cast<const uint4*>(wrow + c);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 w8 = wv[q];
+            const uint32_t ws[4] = {w8.x, w8.y, w8.z, w8.w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const float2 wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ws[h]));
+              radial += wf.x * __uint_as_float(v[q * 8 + h * 2]) + wf.y * __uint_as_float(v[q * 8 + h * 2 + 1]);
+            }
+          }
+        }
+      }
+      const float inv_n = ok ? p.inv_norm[cls] : 0.f;
+      // pass 2: dw = (dwh - w_hat * t) / n
+#pragma unroll 1
+      for (int c = 0; c < EMB; c += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_base + lane_base + c, v);
+        tmem_ld_wait();
+        if (ok) {
+          const uint4* wv = reinterpret_cast<const uint4*>(wrow + c);
+          float4* o = reinterpret_cast<float4*>(p.dw + (int64_t)cls * EMB + c);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 w8 = wv[q];
+            const uint32_t ws[4] = {w8.x, w8.y, w8.z, w8.w};
+            float r[8];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const float2 wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ws[h]));
+              r[h * 2] = (__uint_as_float(v[q * 8 + h * 2]) - wf.x * radial) * inv_n;
+              r[h * 2 + 1] = (__uint_as_float(v[q * 8 + h * 2 + 1]) - wf.y * radial) * inv_n;
+            }
+            float4 r0 = make_float4(r[0], r[1], r[2], r[3]), r1 = make_float4(r[4], r[5], r[6], r[7]);
+            if (p.accumulate) {
+              const float4 a = o[2 * q], b = o[2 * q + 1];
+              r0.x += a.x; r0.y += a.y; r0.z += a.z; r0.w += a.w;
+              r1.x += b.x; r1.y += b.y; r1.z += b.z; r1.w += b.w;
+            }
+            o[2 * q] = r0;
+            o[2 * q + 1] = r1;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<EMB>(tmem_base);
+}
+
+}  // namespace tc
+
+// ================================================================================================
+// host launchers
+// ================================================================================================
+using namespace tc;
+
+static int g_fwd_bn = 128;       // class-tile width of the logits kernels (128 or 256)
+
+static int fwd_grid(int64_t n_rows, int64_t n_classes, int bn) {
+  const int64_t n_rb = (n_rows + BM - 1) / BM, n_ct = (n_classes + bn - 1) / bn;
+  const int64_t tiles = n_rb * n_ct;
+  const int sms = sm_count();
+  return (int)(tiles < sms ? tiles : sms);
+}
+
+template <int BN, int STAGES, int MODE>
+static int launch_logits(const CUtensorMap& tx, const CUtensorMap& tw, const LogitsParams& p, int grid, cudaStream_t st) {
+  const size_t smem = (size_t)(p.emb / BK) * kChunkBytes + (size_t)STAGES * BN * BK * 2 + 1024 + 256;
+  auto kern = logits_kernel<BN, STAGES, MODE>;
+  PFC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kThreads, smem, st>>>(tx, tw, p);
+  PFC_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int MODE>
+static int dispatch_logits(const CUtensorMap& tx, const CUtensorMap& tw, const LogitsParams& p, int bn, int grid, cudaStream_t st) {
+  const int n_kb = p.emb / BK;
+  if (bn == 256) {
+    if (n_kb <= 4) return launch_logits<256, 4, MODE>(tx, tw, p, grid, st);
+    return launch_logits<256, 3, MODE>(tx, tw, p, grid, st);
+  }
+  if (n_kb <= 4) return launch_logits<128, 8, MODE>(tx, tw, p, grid, st);
+  return launch_logits<128, 5, MODE>(tx, tw, p, grid, st);
+}
+
+static bool tensor_emb_ok(int emb) { return emb == 64 || emb == 128 || emb == 256 || emb == 512; }
+
+int tc_fwd_num_partials(int64_t n_rows, int64_t n_classes) { return fwd_grid(n_rows, n_classes, g_fwd_bn); }
+
+int tc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m,
+                 float* part_max, float* part_sum, float* target_logit, cudaStream_t st) {
+  PFC_REQUIRE(tensor_emb_ok(emb), PFC_E_SHAPE, "tensor path supports emb in {64,128,256,512}, got %d (use PFC_PATH_CHECK)", emb);
+  PFC_REQUIRE(n_rows > 0 && n_classes > 0 && n_classes < (1ll << 30) && n_rows < (1ll << 24), PFC_E_SHAPE, "pfc_fwd_stats: shape out of range");
+  const int bn = g_fwd_bn;
+  CUtensorMap tx, tw;
+  if (int rc = make_tmap_bf16_2d(&tx, x, n_rows, emb, emb, BM)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tw, w_hat, n_classes, emb, emb, bn)) return rc;
+  LogitsParams p{};
+  p.label = label; p.n_rows = (int)n_rows; p.n_classes = (int)n_classes; p.class_base = 0; p.emb = emb;
+  p.n_rb = (int)((n_rows + BM - 1) / BM); p.n_ct = (int)((n_classes + bn - 1) / bn);
+  p.s = s; p.m = m; p.part_max = part_max; p.part_sum = part_sum; p.target_logit = target_logit;
+  const int grid = fwd_grid(n_rows, n_classes, bn);
+  PFC_CUDA(cudaMemsetAsync(part_sum, 0, sizeof(float) * (size_t)grid * n_rows, st));
+  PFC_CUDA(cudaMemsetAsync(target_logit, 0, sizeof(float) * (size_t)n_rows, st));
+  return dispatch_logits<MODE_STATS>(tx, tw, p, bn, grid, st);
+}
+
+// ---- backward chunking -------------------------------------------------------------------------
+struct BwdPlan {
+  int64_t chunk;        // classes per chunk (multiple of 256)
+  int64_t ldg;          // row pitch of the G scratch (elements)
+  int ksplit, n_eh, dx_bn;
+  size_t g_bytes, dxp_bytes;
+};
+
+static BwdPlan make_bwd_plan(int64_t n_rows, int64_t n_classes, int emb) {
+  BwdPlan pl{};
+  int64_t budget = 128ll << 20;     // bytes of bf16 G scratch per chunk
+  if (const char* e = getenv("FEDFR_G_CHUNK_MB")) { long v = atol(e); if (v > 0) budget = (int64_t)v << 20; }
+  int64_t chunk = budget / (n_rows * 2);
+  chunk = chunk / 256 * 256;
+  if (chunk < 256) chunk = 256;
+  const int64_t c_pad = (n_classes + 255) / 256 * 256;
+  if (chunk > c_pad) chunk = c_pad;
+  pl.chunk = chunk;
+  pl.ldg = chunk;
+  pl.dx_bn = emb < 256 ? emb : 256;
+  pl.n_eh = emb / pl.dx_bn;
+  const int64_t n_rb = (n_rows + BM - 1) / BM;
+  int64_t units = n_rb * pl.n_eh;
+  int64_t ks = sm_count() / units;
+  if (ks < 1) ks = 1;
+  const int64_t min_kb = ((chunk < n_classes ? chunk : n_classes) + BK - 1) / BK;
+  if (ks > min_kb) ks = min_kb;
+  if (ks > 64) ks = 64;
+  pl.ksplit = (int)ks;
+  pl.g_bytes = ((size_t)n_rows * pl.ldg * 2 + 1023) / 1024 * 1024;
+  pl.dxp_bytes = ((size_t)pl.ksplit * n_rows * emb * 4 + 1023) / 1024 * 1024;
+  return pl;
+}
+
+size_t tc_bwd_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb) {
+  BwdPlan pl = make_bwd_plan(n_rows, n_classes, emb);
+  return pl.g_bytes + pl.dxp_bytes + 1024;
+}
+
+template <int BN>
+static int launch_dx(const CUtensorMap& tg, const CUtensorMap& tw, const DxParams& p, int grid, cudaStream_t st) {
+  constexpr int STAGES = BN == 256 ? 4 : 6;
+  const size_t smem = (size_t)STAGES * (kChunkBytes + (BN / 64) * kBoxBytes) + 1024 + 256;
+  auto kern = dx_kernel<BN, STAGES>;
+  PFC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kThreads, smem, st>>>(tg, tw, p);
+  PFC_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int EMB>
+static int launch_dw(const CUtensorMap& tg, const CUtensorMap& tx, const DwParams& p, int grid, cudaStream_t st) {
+  constexpr int STAGES = EMB == 512 ? 2 : (EMB == 256 ? 4 : 6);
+  const size_t smem = (size_t)STAGES * (2 * kBoxBytes + (EMB / 64) * kBoxBytes) + 1024 + 256;
+  auto kern = dw_kernel<EMB, STAGES>;
+  PFC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kThreads, smem, st>>>(tg, tx, p);
+  PFC_LAUNCH_CHECK();
+  return 0;
+}
+
+int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_max, const float* row_sum,
+           int64_t n_rows, int64_t n_classes, int emb, float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
+           void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  PFC_REQUIRE(tensor_emb_ok(emb), PFC_E_SHAPE, "tensor path supports emb in {64,128,256,512}, got %d (use PFC_PATH_CHECK)", emb);
+  PFC_REQUIRE(n_rows > 0 && n_classes > 0 && n_classes < (1ll << 30) && n_rows < (1ll << 24), PFC_E_SHAPE, "pfc_bwd: shape out of range");
+  const BwdPlan pl = make_bwd_plan(n_rows, n_classes, emb);
+  PFC_REQUIRE(workspace_bytes >= pl.g_bytes + pl.dxp_bytes, PFC_E_WORKSPACE, "pfc_bwd: workspace too small (%zu < %zu)", workspace_bytes,
+              pl.g_bytes + pl.dxp_bytes);
+  PFC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, PFC_E_ARG, "pfc_bwd: workspace must be 1024-byte aligned");
+  auto* g = reinterpret_cast<__nv_bfloat16*>(workspace);
+  float* dx_part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.g_bytes);
+  const auto* wh = reinterpret_cast<const __nv_bfloat16*>(w_hat);
+  const int bn = g_fwd_bn;
+  const int n_rb = (int)((n_rows + BM - 1) / BM);
+  CUtensorMap tx_k, tx_mn;
+  if (int rc = make_tmap_bf16_2d(&tx_k, x, n_rows, emb, emb, BM)) return rc;       // logits: A K-major [128 x 64]
+  if (int rc = make_tmap_bf16_2d(&tx_mn, x, n_rows, emb, emb, 64)) return rc;      // dw: B MN-major boxes [64 rows x 64 e]
+  int chunk_idx = 0;
+  for (int64_t c0 = 0; c0 < n_classes; c0 += pl.chunk, ++chunk_idx) {
+    const int64_t cc = (n_classes - c0 < pl.chunk) ? n_classes - c0 : pl.chunk;
+    // (1) G chunk
+    CUtensorMap tw_k;
+    if (int rc = make_tmap_bf16_2d(&tw_k, wh + c0 * emb, cc, emb, emb, bn)) return rc;
+    LogitsParams lp{};
+    lp.label = label; lp.n_rows = (int)n_rows; lp.n_classes = (int)cc; lp.class_base = (int)c0; lp.emb = emb;
+    lp.n_rb = n_rb; lp.n_ct = (int)((cc + bn - 1) / bn); lp.s = s; lp.m = m;
+    lp.row_max = row_max; lp.row_sum = row_sum; lp.g = g; lp.ldg = pl.ldg; lp.g_scale = s * inv_total_batch;
+    if (int rc = dispatch_logits<MODE_GRAD>(tx_k, tw_k, lp, bn, fwd_grid(n_rows, cc, bn), st)) return rc;
+    // (2) dx partial slabs
+    CUtensorMap tg_k, tw_mn, tg_mn;
+    if (int rc = make_tmap_bf16_2d(&tg_k, g, n_rows, cc, pl.ldg, BM)) return rc;            // A K-major [128 rows x 64 classes]
+    if (int rc = make_tmap_bf16_2d(&tw_mn, wh + c0 * emb, cc, emb, emb, 64)) return rc;     // B MN-major boxes [64 classes x 64 e]
+    DxParams dp{};
+    dp.n_rows = (int)n_rows; dp.n_classes = (int)cc; dp.emb = emb; dp.n_rb = n_rb; dp.n_eh = pl.n_eh; dp.ksplit = pl.ksplit;
+    dp.dx_part = dx_part; dp.accumulate = chunk_idx > 0;
+    const int dgrid = n_rb * pl.n_eh * pl.ksplit;
+    int rc = 0;
+    switch (pl.dx_bn) {
+      case 256: rc = launch_dx<256>(tg_k, tw_mn, dp, dgrid, st); break;
+      case 128: rc = launch_dx<128>(tg_k, tw_mn, dp, dgrid, st); break;
+      default: rc = launch_dx<64>(tg_k, tw_mn, dp, dgrid, st); break;
+    }
+    if (rc) return rc;
+    // (3) dw chunk
+    if (int rc2 = make_tmap_bf16_2d(&tg_mn, g, n_rows, cc, pl.ldg, 64)) return rc2;         // A MN-major boxes [64 rows x 64 classes]
+    DwParams wp{};
+    wp.n_rows = (int)n_rows; wp.n_classes = (int)cc; wp.emb = emb; wp.n_ct = (int)((cc + BM - 1) / BM);
+    wp.w_hat = wh + c0 * emb; wp.inv_norm = inv_norm + c0; wp.dw = dw + c0 * emb; wp.accumulate = accumulate_dw;
+    const int wgrid = wp.n_ct < sm_count() ? wp.n_ct : sm_count();
+    switch (emb) {
+      case 512: rc = launch_dw<512>(tg_mn, tx_mn, wp, wgrid, st); break;
+      case 256: rc = launch_dw<256>(tg_mn, tx_mn, wp, wgrid, st); break;
+      case 128: rc = launch_dw<128>(tg_mn, tx_mn, wp, wgrid, st); break;
+      default: rc = launch_dw<64>(tg_mn, tx_mn, wp, wgrid, st); break;
+    }
+    if (rc) return rc;
+  }
+  const int64_t n_vec = n_rows * emb / 4;
+  int64_t blocks = (n_vec + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
+  reduce_dx_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(dx_part), pl.ksplit, n_vec, reinterpret_cast<float4*>(dx));
+  PFC_LAUNCH_CHECK();
+  return 0;
+}
+
+void tc_set_fwd_bn(int bn) { g_fwd_bn = (bn == 256) ? 256 : 128; }
+
+}  // namespace pfc

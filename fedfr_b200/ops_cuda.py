@@ -1,0 +1,131 @@
+"""Tensor-level wrappers over the C ABI: the only kernel provider of the product path.
+
+Each method takes/returns torch CUDA tensors, passes raw pointers + the current stream to
+``libfedfr_b200.so`` and raises ``RuntimeError`` on any non-zero return code.
+"""
+import torch
+
+from . import _native as N
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class CudaOps:
+    """Kernel provider backed by the sm_100a extension.  ``path`` = PATH_TENSOR (bf16 tcgen05) or
+    PATH_CHECK (fp32 SIMT check mode)."""
+
+    def __init__(self, device, path=N.PATH_TENSOR):
+        if not torch.cuda.is_available():
+            raise RuntimeError("fedfr_b200 needs a CUDA device (sm_100); there is no CPU fallback")
+        self.device = torch.device(device)
+        self.path = path
+        with torch.cuda.device(self.device):
+            N.check(N.lib.pfc_query_device(self.device.index or 0, None, None, None), "pfc_query_device")
+        self._ws = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _buf(self, key, nbytes):
+        t = self._ws.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(int(nbytes), 1024), dtype=torch.uint8, device=self.device)
+            self._ws[key] = t
+        return t
+
+    # ------------------------------------------------------------------ integer side
+    def remap_labels(self, total_label, class_start, num_local):
+        out = torch.empty_like(total_label)
+        N.check(N.lib.pfc_remap_labels(N.ptr(total_label), total_label.numel(), int(class_start), int(num_local), N.ptr(out),
+                                       _stream(self.device)), "pfc_remap_labels")
+        return out
+
+    def sample(self, local_label, perm, num_sample):
+        """In place on ``local_label`` and ``perm``; returns the sorted ``index`` tensor (partial_fc.py:95-104)."""
+        num_local = perm.numel()
+        cap = max(int(num_sample), min(local_label.numel(), num_local))
+        index = torch.empty(cap, dtype=torch.int64, device=self.device)
+        n_index = torch.zeros(1, dtype=torch.int64, device=self.device)
+        ws = self._buf("sample", N.lib.pfc_sample_workspace_bytes(num_local))
+        N.check(N.lib.pfc_sample_index(N.ptr(local_label), local_label.numel(), N.ptr(perm), num_local, int(num_sample), N.ptr(index),
+                                       N.ptr(n_index), N.ptr(ws), ws.numel(), _stream(self.device)), "pfc_sample_index")
+        if num_sample >= local_label.numel():
+            return index[:num_sample]          # positives cannot outnumber num_sample: size known without a sync
+        return index[: int(n_index.item())]
+
+    def gather_rows2(self, weight, weight_mom, index):
+        emb = weight.shape[1]
+        sub_w = torch.empty((index.numel(), emb), dtype=torch.float32, device=self.device)
+        sub_m = torch.empty_like(sub_w)
+        N.check(N.lib.pfc_gather_rows2(N.ptr(weight), N.ptr(weight_mom), N.ptr(index), index.numel(), emb, N.ptr(sub_w), N.ptr(sub_m),
+                                       _stream(self.device)), "pfc_gather_rows2")
+        return sub_w, sub_m
+
+    def scatter_rows2(self, weight, weight_mom, index, sub_w, sub_m):
+        N.check(N.lib.pfc_scatter_rows2(N.ptr(weight), N.ptr(weight_mom), N.ptr(index), index.numel(), weight.shape[1], N.ptr(sub_w),
+                                        N.ptr(sub_m), _stream(self.device)), "pfc_scatter_rows2")
+
+    # ------------------------------------------------------------------ floating point side
+    def normalize(self, sub_weight):
+        """-> (w_hat operand, inv_norm).  bf16 on the tensor path, fp32 in check mode."""
+        n, emb = sub_weight.shape
+        inv = torch.empty(n, dtype=torch.float32, device=self.device)
+        if self.path == N.PATH_CHECK:
+            w_hat = torch.empty((n, emb), dtype=torch.float32, device=self.device)
+            N.check(N.lib.pfc_normalize_rows(N.ptr(sub_weight), None, n, emb, None, N.ptr(w_hat), N.ptr(inv), _stream(self.device)),
+                    "pfc_normalize_rows")
+        else:
+            key = ("w_hat", n, emb)
+            w_hat = self._ws.get(key)
+            if w_hat is None:
+                self._ws = {k: v for k, v in self._ws.items() if not (isinstance(k, tuple) and k[0] == "w_hat")}
+                w_hat = torch.empty((n, emb), dtype=torch.bfloat16, device=self.device)
+                self._ws[key] = w_hat
+            N.check(N.lib.pfc_normalize_rows(N.ptr(sub_weight), None, n, emb, N.ptr(w_hat), None, N.ptr(inv), _stream(self.device)),
+                    "pfc_normalize_rows")
+        return w_hat, inv
+
+    def cast_features(self, total_features):
+        if self.path == N.PATH_CHECK:
+            return total_features
+        x = torch.empty(total_features.shape, dtype=torch.bfloat16, device=self.device)
+        N.check(N.lib.pfc_cast_rows_bf16(N.ptr(total_features), total_features.shape[0], total_features.shape[1], N.ptr(x),
+                                         _stream(self.device)), "pfc_cast_rows_bf16")
+        return x
+
+    def fwd_stats(self, x_hat, w_hat, label, s, m):
+        """-> stats [Bt, 3] = (row max, sum-exp at that max, target logit) of this shard."""
+        bt, emb = x_hat.shape
+        cs = w_hat.shape[0]
+        n_part = N.lib.pfc_fwd_num_partials(bt, cs, emb, self.path)
+        part = torch.empty((2, n_part, bt), dtype=torch.float32, device=self.device)
+        tz = torch.empty(bt, dtype=torch.float32, device=self.device)
+        st = _stream(self.device)
+        N.check(N.lib.pfc_fwd_stats(N.ptr(x_hat), N.ptr(w_hat), N.ptr(label), bt, cs, emb, float(s), float(m), N.ptr(part[0]), N.ptr(part[1]),
+                                    N.ptr(tz), self.path, st), "pfc_fwd_stats")
+        stats = torch.empty((bt, 3), dtype=torch.float32, device=self.device)
+        N.check(N.lib.pfc_merge_stats(N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), n_part, bt, N.ptr(stats), st), "pfc_merge_stats")
+        return stats
+
+    def finalize(self, gathered_stats):
+        """[W, Bt, 3] -> (row_max [Bt], row_sum [Bt], loss 0-d)."""
+        w, bt, _ = gathered_stats.shape
+        row_max = torch.empty(bt, dtype=torch.float32, device=self.device)
+        row_sum = torch.empty_like(row_max)
+        loss = torch.empty((), dtype=torch.float32, device=self.device)
+        N.check(N.lib.pfc_finalize_stats(N.ptr(gathered_stats), w, bt, N.ptr(row_max), N.ptr(row_sum), N.ptr(loss), _stream(self.device)),
+                "pfc_finalize_stats")
+        return row_max, row_sum, loss
+
+    def bwd(self, x_hat, w_hat, inv_norm, label, row_max, row_sum, s, m, inv_total_batch, dw, accumulate):
+        """Writes/accumulates ``dw`` [Cs, E]; returns this shard's partial ``dx`` [Bt, E]."""
+        bt, emb = x_hat.shape
+        cs = w_hat.shape[0]
+        dx = torch.empty((bt, emb), dtype=torch.float32, device=self.device)
+        nbytes = N.lib.pfc_bwd_workspace_bytes(bt, cs, emb, self.path)
+        ws = self._buf("bwd", nbytes + 1024)
+        off = (-ws.data_ptr()) % 1024
+        N.check(N.lib.pfc_bwd(N.ptr(x_hat), N.ptr(w_hat), N.ptr(inv_norm), N.ptr(label), N.ptr(row_max), N.ptr(row_sum), bt, cs, emb, float(s),
+                              float(m), float(inv_total_batch), N.ptr(dx), N.ptr(dw), 1 if accumulate else 0, ws.data_ptr() + off,
+                              ws.numel() - off, self.path, _stream(self.device)), "pfc_bwd")
+        return dx

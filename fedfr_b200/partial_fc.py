@@ -1,0 +1,191 @@
+"""``PartialFC`` -- class-sharded, optionally sampled CosFace margin-softmax head on B200.
+
+Drop-in for the reference's ``partial_fc.PartialFC`` (partial_fc.py:11-176): same constructor
+arguments, attributes (``weight``, ``weight_mom``, ``sub_weight``, ``sub_weight_mom``, ``index``,
+``num_local``, ``class_start``, ``num_sample``, ``stream``, file names), methods
+(``forward_backward``, ``prepare``, ``sample``, ``update``, ``save_params``, ``save_FC``,
+``update_FC``, ``update_from_tensor``) and optimizer contract.  What differs is underneath:
+
+* the ``[Bt, Cs]`` logits are never materialised -- the margin and the softmax statistics live in the
+  epilogue of a tcgen05 GEMM, and the backward recomputes them (``libfedfr_b200.so``);
+* the three row-statistic all-reduces of partial_fc.py:142,147,161 are one all-gather of
+  ``(max, sum-exp, target logit)`` triples followed by a local merge (mathematically identical);
+* ``margin_softmax`` must be a ``CosFace(s, m)`` object (this package's or the reference's); it is read as a
+  descriptor, never called.
+
+There is no PyTorch/CPU fallback: construction fails without an sm_100 device.
+"""
+import logging
+import os
+
+import torch
+import torch.distributed as dist
+from torch.nn import Module
+from torch.nn.parameter import Parameter
+
+from .losses import margin_params
+
+
+class PartialFC(Module):
+    @torch.no_grad()
+    def __init__(self, rank, local_rank, world_size, batch_size, resume, margin_softmax, num_classes, sample_rate=1.0,
+                 embedding_size=512, prefix="./", check_mode=False, _ops=None):
+        super(PartialFC, self).__init__()
+        self.num_classes: int = num_classes
+        self.rank: int = rank
+        self.local_rank: int = local_rank
+        self.world_size: int = world_size
+        self.batch_size: int = batch_size
+        self.margin_softmax = margin_softmax
+        self._s, self._m = margin_params(margin_softmax)
+        self.sample_rate: float = sample_rate
+        self.embedding_size: int = embedding_size
+        self.prefix: str = prefix
+        # shard geometry, partial_fc.py:34-36
+        self.num_local: int = num_classes // world_size + int(rank < num_classes % world_size)
+        self.class_start: int = num_classes // world_size * rank + min(rank, num_classes % world_size)
+        self.num_sample: int = int(self.sample_rate * self.num_local)
+
+        if _ops is None:
+            from . import _native as N
+            from .ops_cuda import CudaOps
+            self.device = torch.device("cuda:{}".format(self.local_rank))
+            self._ops = CudaOps(self.device, N.PATH_CHECK if check_mode else N.PATH_TENSOR)
+        else:                       # host-logic tests inject a CPU provider (tests/ only)
+            self._ops = _ops
+            self.device = torch.device(_ops.device)
+
+        # checkpoint names, partial_fc.py:38-39
+        self.weight_name = os.path.join(self.prefix, "rank:{}_softmax_weight.pt".format(self.rank))
+        self.weight_mom_name = os.path.join(self.prefix, "rank:{}_softmax_weight_mom.pt".format(self.rank))
+
+        if resume:      # partial_fc.py:41-54
+            try:
+                self.weight: torch.Tensor = torch.load(self.weight_name).to(self.device)
+                logging.info("softmax weight resume successfully!")
+            except (FileNotFoundError, KeyError, IndexError):
+                self.weight = torch.normal(0, 0.01, (self.num_local, self.embedding_size), device=self.device)
+                logging.info("softmax weight resume fail!")
+            try:
+                self.weight_mom: torch.Tensor = torch.load(self.weight_mom_name).to(self.device)
+                logging.info("softmax weight mom resume successfully!")
+            except (FileNotFoundError, KeyError, IndexError):
+                self.weight_mom: torch.Tensor = torch.zeros_like(self.weight)
+                logging.info("softmax weight mom resume fail!")
+        else:           # partial_fc.py:55-60
+            self.weight = torch.normal(0, 0.01, (self.num_local, self.embedding_size), device=self.device)
+            self.weight_mom: torch.Tensor = torch.zeros_like(self.weight)
+            logger = logging.getLogger('FL_face.partial')
+            logger.info("softmax weight init successfully!")
+            logger.info("softmax weight mom init successfully!")
+        self.stream = torch.cuda.Stream(local_rank) if self.device.type == "cuda" else None
+
+        self.index = None
+        if int(self.sample_rate) == 1:      # partial_fc.py:64-67: the shard itself is the parameter
+            self.update = lambda: 0
+            self.sub_weight = Parameter(self.weight)
+            self.sub_weight_mom = self.weight_mom
+        else:
+            self.sub_weight = Parameter(torch.empty((0, 0), device=self.device))
+        self._norm = None       # (w_hat, inv_norm) of the current step
+
+    # ------------------------------------------------------------------ shard I/O (partial_fc.py:71-87)
+    def save_params(self):
+        torch.save(self.weight.data, self.weight_name)
+        torch.save(self.weight_mom, self.weight_mom_name)
+
+    def save_FC(self):
+        torch.save(self.weight.data, os.path.join(self.prefix, 'FC_rank_%d.pth' % (self.local_rank)))
+
+    def update_FC(self):
+        model_path = os.path.join(self.prefix, 'FC_rank_%d.pth' % (self.local_rank))
+        self.weight.data = torch.load(model_path).to(self.device)
+        self.sub_weight = Parameter(self.weight)
+        print('Load weight from %s' % (model_path))
+
+    def update_from_tensor(self, tensor):
+        self.weight.data = tensor.to(self.device)
+        self.sub_weight = Parameter(self.weight)
+
+    # ------------------------------------------------------------------ sampling (partial_fc.py:89-106)
+    @torch.no_grad()
+    def sample(self, total_label):
+        """In place on ``total_label`` (global ids -> shard-local / sampled column ids, -1 elsewhere)."""
+        local = self._ops.remap_labels(total_label, self.class_start, self.num_local)
+        if int(self.sample_rate) != 1:
+            perm = torch.rand(size=[self.num_local], device=self.device)       # same draw as partial_fc.py:95
+            index = self._ops.sample(local, perm, self.num_sample)
+            self.index = index
+            sub_w, sub_m = self._ops.gather_rows2(self.weight, self.weight_mom, index)
+            self.sub_weight = Parameter(sub_w)
+            self.sub_weight_mom = sub_m
+        total_label.copy_(local)
+
+    def forward(self, total_features, norm_weight):
+        """The reference materialises ``logits = linear(total_features, norm_weight)`` here (partial_fc.py:108-111).
+        The fused path never does; this method exists for API parity and returns them in fp32 for inspection."""
+        return torch.nn.functional.linear(total_features, norm_weight.to(total_features.dtype))
+
+    @torch.no_grad()
+    def update(self):
+        """Write the sampled rows back (partial_fc.py:113-116); replaced by a no-op when sample_rate == 1."""
+        self._ops.scatter_rows2(self.weight, self.weight_mom, self.index, self.sub_weight.data, self.sub_weight_mom)
+
+    # ------------------------------------------------------------------ collectives
+    def _all_gather(self, out, inp):
+        if self.world_size == 1:
+            out.copy_(inp.reshape(out.shape))
+        else:
+            dist.all_gather(list(out.chunk(self.world_size, dim=0)), inp)
+
+    @torch.no_grad()
+    def prepare(self, label, optimizer):
+        """partial_fc.py:118-128: gather labels, sample, rewire the optimizer onto ``sub_weight`` and its
+        momentum buffer, normalise the sub-shard.  Returns ``(total_label, norm_weight)``."""
+        total_label = torch.zeros(size=[self.batch_size * self.world_size], device=self.device, dtype=torch.long)
+        self._all_gather(total_label, label.to(self.device))
+        self.sample(total_label)
+        optimizer.state.pop(optimizer.param_groups[-1]['params'][0], None)
+        optimizer.param_groups[-1]['params'][0] = self.sub_weight
+        optimizer.state[self.sub_weight]['momentum_buffer'] = self.sub_weight_mom
+        self._norm = self._ops.normalize(self.sub_weight.data)
+        return total_label, self._norm[0]
+
+    @torch.no_grad()
+    def forward_backward(self, label, features, optimizer):
+        """partial_fc.py:130-176.  ``features`` fp32 [batch_size, E] (caller-normalised), ``label`` int64
+        [batch_size].  Returns ``(x_grad [batch_size, E], loss)``; ``sub_weight.grad`` receives the shard gradient."""
+        W, B, E = self.world_size, self.batch_size, self.embedding_size
+        if features.shape[0] != B or label.shape[0] != B:
+            raise ValueError("features/label batch must equal the constructor's batch_size (gather buffers are pre-sized, "
+                             "partial_fc.py:120-122,132-134)")
+        ops = self._ops
+        total_label, w_hat = self.prepare(label, optimizer)
+        inv_norm = self._norm[1]
+        total_features = torch.zeros(size=[B * W, E], device=self.device)
+        self._all_gather(total_features, features.data.to(torch.float32))
+        x_hat = ops.cast_features(total_features)
+
+        # forward: per-shard (max, sum-exp, target logit), then one exchange instead of three all-reduces
+        stats = ops.fwd_stats(x_hat, w_hat, total_label, self._s, self._m)
+        if W == 1:
+            gathered = stats.unsqueeze(0)
+        else:
+            gathered = torch.empty((W,) + tuple(stats.shape), dtype=stats.dtype, device=self.device)
+            dist.all_gather(list(gathered.unbind(0)), stats)
+        row_max, row_sum, loss_v = ops.finalize(gathered)
+
+        # backward: dx partial of this shard + sub_weight.grad
+        accumulate = self.sub_weight.grad is not None
+        if not accumulate:
+            self.sub_weight.grad = torch.empty_like(self.sub_weight.data)
+        dx_total = ops.bwd(x_hat, w_hat, inv_norm, total_label, row_max, row_sum, self._s, self._m, 1.0 / (B * W),
+                           self.sub_weight.grad, accumulate)
+
+        if W == 1:
+            x_grad = dx_total
+        else:
+            x_grad = torch.zeros_like(features, dtype=torch.float32, device=self.device)
+            dist.reduce_scatter(x_grad, list(dx_total.chunk(W, dim=0)))
+            x_grad = x_grad * W                     # partial_fc.py:174
+        return x_grad, loss_v

@@ -1,0 +1,166 @@
+/*
+ * fedfr_b200 -- C ABI of the B200 (sm_100a) PartialFC CosFace / FedAvg hot path.
+ *
+ * This is the drop-in boundary.  The reference (jackie840129/FedFR) is pure Python; the functions
+ * below are what its hot path binds to through ctypes (see INTEGRATION.md for the stub a reference
+ * maintainer would add).  Each entry cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only, no torch types; every pointer is a DEVICE pointer unless the
+ *     name ends in _host;
+ *   - every function enqueues on `stream` (a cudaStream_t passed as void*) and returns without
+ *     synchronising unless stated;
+ *   - return value: 0 = ok, < 0 = bad argument / unsupported shape / wrong GPU (see PFC_E_*),
+ *     > 0 = a cudaError_t.  pfc_last_error() returns a thread-local message for the last failure;
+ *   - row-major, dense tensors.  `emb` is the embedding size E (reference default 512).
+ *   - there is NO CPU fallback anywhere: without an sm_100 device every compute entry fails.
+ */
+#ifndef FEDFR_B200_H_
+#define FEDFR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFC_E_ARG         (-1)   /* null pointer / negative size / misaligned */
+#define PFC_E_SHAPE       (-2)   /* shape not supported by the requested kernel path */
+#define PFC_E_ARCH        (-3)   /* device is not compute capability 10.x */
+#define PFC_E_WORKSPACE   (-4)   /* workspace too small */
+
+/* kernel path selectors for the GEMM-shaped entries */
+#define PFC_PATH_TENSOR   0      /* bf16 operands, tcgen05/TMEM fp32 accumulate (the product path) */
+#define PFC_PATH_CHECK    1      /* fp32 operands, fp32 SIMT accumulate ("check mode", slow) */
+
+int         pfc_version(void);
+const char* pfc_last_error(void);
+/* cc_major/cc_minor/sm_count may be NULL.  Returns PFC_E_ARCH when the device is not sm_100. */
+int pfc_query_device(int device, int* cc_major, int* cc_minor, int* sm_count);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row kernels (HBM bound)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* norm_weight = normalize(sub_weight)                                   partial_fc.py:127
+ * w [n_rows_src, emb] fp32.  If index != NULL row r of the output is w[index[r]] (fuses the gather of
+ * partial_fc.py:105).  Writes w_hat (bf16 [n_rows, emb], may be NULL), w_hat_f32 (fp32, may be NULL;
+ * check mode) and inv_norm[r] = 1 / max(||w_r||, 1e-12). */
+int pfc_normalize_rows(const float* w, const int64_t* index, int64_t n_rows, int emb,
+                       void* w_hat_bf16, float* w_hat_f32, float* inv_norm, void* stream);
+
+/* total_features -> bf16 operand of the logits GEMM (features are used as passed, partial_fc.py:110). */
+int pfc_cast_rows_bf16(const float* x, int64_t n_rows, int emb, void* x_bf16, void* stream);
+
+/* sub_weight = weight[index]; sub_weight_mom = weight_mom[index]        partial_fc.py:105-106 */
+int pfc_gather_rows2(const float* weight, const float* weight_mom, const int64_t* index, int64_t n_index,
+                     int emb, float* sub_weight, float* sub_weight_mom, void* stream);
+
+/* weight_mom[index] = sub_weight_mom; weight[index] = sub_weight        partial_fc.py:113-116 (update) */
+int pfc_scatter_rows2(float* weight, float* weight_mom, const int64_t* index, int64_t n_index, int emb,
+                      const float* sub_weight, const float* sub_weight_mom, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sampling (integer exact)                                              partial_fc.py:89-106
+ * ---------------------------------------------------------------------------------------------- */
+
+/* label_out[i] = label_in[i] - class_start if owned by this shard else -1      partial_fc.py:91-93 */
+int pfc_remap_labels(const int64_t* label_in, int64_t n, int64_t class_start, int64_t num_local,
+                     int64_t* label_out, void* stream);
+
+size_t pfc_sample_workspace_bytes(int64_t num_local);
+
+/* index = sort(topk(perm with perm[positive] = 2.0, num_sample).indices), or the positives when they
+ * outnumber num_sample; label[i] <- searchsorted(index, label[i]) for owned labels.
+ *   label      in/out [n_label]   shard-local ids or -1 (output of pfc_remap_labels)
+ *   perm       in/out [num_local] fp32 uniform draw (torch.rand, partial_fc.py:95); positives are set to 2.0
+ *   index_out  [max(num_sample, min(n_label, num_local))]
+ *   n_index_out device int64[1]: number of ids written
+ * Ties at the k-th value are resolved like torch's CUDA topk: strictly greater first, then equal in
+ * ascending index order. */
+int pfc_sample_index(int64_t* label, int64_t n_label, float* perm, int64_t num_local, int64_t num_sample,
+                     int64_t* index_out, int64_t* n_index_out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused margin-softmax forward                                          partial_fc.py:137-147, losses.py:23-29
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Number of per-row partial (max, sum-exp) slots pfc_fwd_stats writes for this shape. */
+int pfc_fwd_num_partials(int64_t n_rows, int64_t n_classes, int emb, int path);
+
+/* z_ij = s * (x_i . w_hat_j - m [label_i == j]); for every row the running max and sum exp(z - max) over
+ * the classes this call covers, plus the target logit z_{i,label_i} for owned rows.  Logits never
+ * leave the chip.
+ *   x, w_hat     bf16 (PFC_PATH_TENSOR) or fp32 (PFC_PATH_CHECK), [n_rows, emb] / [n_classes, emb]
+ *   label        int64 [n_rows], -1 = class not in this shard
+ *   part_max/part_sum  fp32 [pfc_fwd_num_partials(...), n_rows]
+ *   target_logit fp32 [n_rows], must be zero-filled by the caller (only owning rows are written) */
+int pfc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes,
+                  int emb, float s, float m, float* part_max, float* part_sum, float* target_logit,
+                  int path, void* stream);
+
+/* Merge the partial slots of one shard into stats[n_rows, 3] = (max, sum-exp at that max, target logit). */
+int pfc_merge_stats(const float* part_max, const float* part_sum, const float* target_logit, int n_partials,
+                    int64_t n_rows, float* stats, void* stream);
+
+/* Combine the shard stats of `world` ranks (all-gathered, [world, n_rows, 3]) -- replaces the three
+ * all_reduces of partial_fc.py:142,147,161 -- into row_max, row_sum and
+ * loss = -mean(log(max(p_target, 1e-30)))                               partial_fc.py:162 */
+int pfc_finalize_stats(const float* gathered_stats, int world, int64_t n_rows, float* row_max, float* row_sum,
+                       float* loss_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused backward                                                        partial_fc.py:165-168 (+ autograd)
+ * ---------------------------------------------------------------------------------------------- */
+
+size_t pfc_bwd_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb, int path);
+
+/* G_ij = s * (softmax_ij - [label_i == j]) / total_batch  (recomputed from x, w_hat and the global stats)
+ * dx    = G . w_hat                         [n_rows, emb]   fp32, overwritten (this shard's partial sum)
+ * dw_j  = (dwh_j - w_hat_j (w_hat_j . dwh_j)) * inv_norm_j  with dwh = G^T . x    (normalize backward)
+ *         [n_classes, emb] fp32; accumulate_dw != 0 adds into dw (torch .grad semantics).
+ * w_hat_f32 is only read in PFC_PATH_CHECK (then x / w_hat are fp32 too). */
+int pfc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label,
+            const float* row_max, const float* row_sum, int64_t n_rows, int64_t n_classes, int emb,
+            float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
+            void* workspace, size_t workspace_bytes, int path, void* stream);
+
+/* losses.CosFace.forward on materialised logits (dense twin, client.py:430): in place
+ * cosine[i, label[i]] -= m for label[i] != -1, then out = cosine * s.      losses.py:23-29 */
+int pfc_cosface_dense(float* cosine, const int64_t* label, int64_t n_rows, int64_t n_classes, float s, float m,
+                      float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * FedAvg                                                                server.py:25-46
+ * ---------------------------------------------------------------------------------------------- */
+
+#define FEDAVG_F32  0
+#define FEDAVG_I64  1
+
+/* One segment = one state_dict entry: K source tensors of n elements and one fp32 output.
+ * out[e] = sum_i fl32(w_i) * fl32(src_i[e]) evaluated as separate round-to-nearest multiply and add in
+ * client order (bit-identical to the reference's `tmp += weights[i] * models[i][name]`).
+ *   seg_src_host   [n_seg * K] device pointers, client-minor (segment s, client i -> s*K + i)
+ *   seg_out_host   [n_seg]     device pointers (fp32)
+ *   seg_len_host   [n_seg]     element counts
+ *   seg_dtype_host [n_seg]     FEDAVG_F32 / FEDAVG_I64
+ *   weights_host   [K]         already normalised (w_i / sum w), rounded to fp32 by the caller
+ * table_dev: device scratch of at least fedavg_table_bytes(n_seg, K) bytes; the host arrays are copied
+ * into it with cudaMemcpyAsync on `stream` (so they must stay valid until the stream reaches the copy;
+ * pass pinned memory to keep the call asynchronous). */
+size_t fedavg_table_bytes(int n_seg, int K);
+int fedavg_weighted_sum(const void* const* seg_src_host, void* const* seg_out_host, const int64_t* seg_len_host,
+                        const int32_t* seg_dtype_host, int n_seg, const float* weights_host, int K,
+                        void* table_dev, size_t table_bytes, void* stream);
+
+/* FedAvg_on_FC epilogue (server.py:42-45): out = fl32(1-p) * old + fl32(p) * aggr, elementwise fp32
+ * (both scalars are rounded from the Python doubles by the caller; separate multiply and add). */
+int fedavg_blend(const float* old_fc, const float* aggr, float one_minus_p, float p, int64_t n, float* out,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* FEDFR_B200_H_ */
