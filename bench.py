@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- PartialFC CosFace fwd+bwd throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                     # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1     # the reference algorithm on host cores
+    torchrun ... bench.py --gpus N ...                                 # class-sharded, one rank per GPU
+
+A "step" is one ``PartialFC.forward_backward`` (prepare -> return: weight normalisation, logits GEMM +
+CosFace + softmax statistics, loss, backward to the feature gradient and the centre-shard gradient, all
+collectives) on a batch of 512 synthetic 512-d embeddings per GPU against 1M classes sharded over the N
+GPUs (BASELINE.json configs[2]).  ``optimizer.step()`` / ``update()`` are outside the step.
+
+Prints ONE JSON line (rank 0).  value = whole-job samples/s with inputs resident in HBM; e2e = the same
+through the public API with pinned HOST inputs and a device->host read of the result inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (batch per GPU, classes (global), emb, sample_rate)
+    "c3": (512, 1_000_000, 512, 1.0),
+    "c2": (512, 100_000, 512, 1.0),
+    "c4": (512, 2_000_000, 512, 0.1),
+}
+METRIC = "PartialFC CosFace fwd+bwd samples/s"
+S, M = 64.0, 0.4
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d["bf16_tflops"], "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_step_time(B, C_sample, E, steps, warmup, threads):
+    """Reference algorithm (oracle port of partial_fc.py:130-176 + losses.py:23-29) on the host cores."""
+    import torch
+    from oracle import partial_fc_oracle as O
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(100)
+    x = torch.nn.functional.normalize(torch.randn(B, E, generator=g))
+    y = torch.randint(0, C_sample, (B,), generator=g)
+    w = torch.randn(C_sample, E, generator=g) * 0.01
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.forward_backward([x], [y], [w], C_sample, S, M)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path for the same metric/config (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    B, C, E, sr = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    C_sample = 32768                 # bounded sample: ~0.3 s of host work per step
+    t = oracle_step_time(B, C_sample, E, args.steps, args.warmup, threads)
+    scale = (C * (sr if sr < 1 else 1.0)) / C_sample
+    ms_full = t * scale * 1e3
+    val = B * args.gpus / (ms_full / 1e3) if args.gpus == 1 else B / (ms_full / 1e3)
+    cpu = {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+           "sample": f"oracle port of PartialFC.forward_backward, B={B}, {C_sample} of {C} classes per step, time scaled x{scale:.2f} (cost is linear in classes)"}
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_full, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: PartialFC CosFace fwd+bwd, B={B}/GPU, {C} classes, E={E}, sample_rate={sr}, s={S}, m={M}"},
+            "cpu_baseline": cpu, "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as G
+    G.build()
+    import fedfr_b200
+    from fedfr_b200 import _native as N
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, C, E, sr = WORKLOADS[args.workload]
+    if args.logits_tile:
+        N.check(N.lib.pfc_set_logits_tile(args.logits_tile), "pfc_set_logits_tile")
+    torch.manual_seed(100 + rank)
+    head = fedfr_b200.PartialFC(rank, local_rank, world, B, False, fedfr_b200.CosFace(s=S, m=M), C, sample_rate=sr, embedding_size=E, prefix="/tmp")
+    opt = torch.optim.SGD([{"params": head.parameters()}], lr=0.1, momentum=0.9, weight_decay=5e-4)
+    feats = torch.nn.functional.normalize(torch.randn(B, E, device=dev))
+    label = torch.randint(0, C, (B,), device=dev)
+    feats_h = feats.cpu().pin_memory()
+    label_h = label.cpu().pin_memory()
+
+    def step_resident():
+        head.sub_weight.grad = None                      # what optimizer.zero_grad(set_to_none=True) leaves behind
+        return head.forward_backward(label, feats, opt)
+
+    def step_e2e():
+        head.sub_weight.grad = None
+        f = feats_h.to(dev, non_blocking=True)
+        l = label_h.to(dev, non_blocking=True)
+        xg, loss = head.forward_backward(l, f, opt)
+        return xg.cpu(), float(loss)                     # D2H of the result, synchronises
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = N.lib.pfc_launch_count()
+    ms_total = timed(step_resident, args.steps)
+    launches = N.lib.pfc_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+
+    # per-phase device times (events on the launch stream inside the library) for the roofline of the dominant kernel
+    import ctypes as CT
+    N.lib.pfc_profile_enable(1)
+    prof_steps = min(args.steps, 5)
+    for _ in range(prof_steps):
+        step_resident()
+    torch.cuda.synchronize()
+    ms = (CT.c_float * 5)()
+    cnt = (CT.c_int * 5)()
+    N.lib.pfc_profile_collect(ms, cnt)
+    N.lib.pfc_profile_enable(0)
+    names = ["normalize_rows", "logits_stats(fwd)", "logits_grad(bwd)", "dx", "dw"]
+    phase_ms = {n: ms[i] / prof_steps for i, n in enumerate(names)}
+    phase_launches = {n: cnt[i] // prof_steps for i, n in enumerate(names)}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    Bt = B * world
+    Cs = head.num_sample if sr < 1 else head.num_local
+    gemm_flops = 2.0 * Bt * Cs * E                       # one GEMM of the three (6*Bt*Cs*E per step)
+    gemm_phases = ["logits_stats(fwd)", "logits_grad(bwd)", "dx", "dw"]
+    dom = max(gemm_phases, key=lambda n: phase_ms[n])
+    dom_launches = max(phase_launches[dom], 1)
+    dom_ms = phase_ms[dom]
+    achieved = gemm_flops / (dom_ms * 1e-3) / 1e12
+    roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+            "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside the step loop); burst {peaks['tflops']}",
+            "flops_per_launch": gemm_flops / dom_launches, "ms_per_launch": dom_ms / dom_launches, "launches_per_step": dom_launches,
+            "phase_ms_per_step": phase_ms,
+            "step_tflops": 6.0 * Bt * Cs * E / (ms_step * 1e-3) / 1e12 / 1.0,
+            "step_frac_of_burst_peak_per_gpu": 6.0 * Bt * Cs * E / (ms_step * 1e-3) / 1e12 / peaks["tflops"],
+            "normalize_gbs": Cs * E * 6.0 / (phase_ms["normalize_rows"] * 1e-3) / 1e9 if phase_ms["normalize_rows"] > 0 else None}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        C_sample = 65536
+        t = oracle_step_time(B, C_sample, E, 3, 1, threads)
+        scale = Cs / C_sample
+        cpu = {"value": B / (t * scale), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"oracle port, B={B}, {C_sample} of {Cs} classes, 3 steps after 1 warm-up, time scaled x{scale:.2f}"}
+
+    line = {"metric": METRIC, "value": Bt / (ms_step * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: class-sharded PartialFC CosFace fwd+bwd, B={B}/GPU, {C} classes over {world} GPU(s), E={E}, "
+                                   f"sample_rate={sr}, s={S}, m={M}",
+                       "l2": "inputs larger than L2 (weight shard fp32+bf16 streamed every step)", "parallelism": f"class-shard x{world}"},
+            "e2e": {"value": Bt / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": B * E * 4 + B * 8, "d2h_bytes_per_step": B * E * 4 + 4,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--logits-tile", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -51,7 +51,13 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)
     _fn.restype = _res
     _fn.argtypes = _args
-# tuning knob, not part of the reference-facing header
+# developer hooks (profiling / launch accounting / tuning), not part of the reference-facing header
+lib.pfc_launch_count.restype = C.c_longlong
+lib.pfc_launch_count.argtypes = []
+lib.pfc_profile_enable.restype = _i32
+lib.pfc_profile_enable.argtypes = [_i32]
+lib.pfc_profile_collect.restype = _i32
+lib.pfc_profile_collect.argtypes = [C.POINTER(C.c_float), C.POINTER(_i32)]
 lib.pfc_set_logits_tile.restype = _i32
 lib.pfc_set_logits_tile.argtypes = [_i32]
 

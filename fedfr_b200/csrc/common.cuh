@@ -10,6 +10,12 @@
 namespace pfc {
 
 void set_error(const char* fmt, ...);
+extern long long g_launch_count;      // kernels launched by this library (bench.py reports it)
+
+// optional per-phase device timing (bench.py roofline): phases are bracketed by events on the launch stream
+enum { PH_NORMALIZE = 0, PH_FWD = 1, PH_GRAD = 2, PH_DX = 3, PH_DW = 4, PH_COUNT = 5 };
+void prof_begin(int phase, cudaStream_t st);
+void prof_end(int phase, cudaStream_t st);
 
 #define PFC_REQUIRE(cond, code, ...)                \
   do {                                              \
@@ -30,6 +36,7 @@ void set_error(const char* fmt, ...);
 
 #define PFC_LAUNCH_CHECK()                                                             \
   do {                                                                                 \
+    ::pfc::g_launch_count++;                                                           \
     cudaError_t e__ = cudaGetLastError();                                              \
     if (e__ != cudaSuccess) {                                                          \
       ::pfc::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \

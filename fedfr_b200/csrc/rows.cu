@@ -118,12 +118,14 @@ int pfc_normalize_rows(const float* w, const int64_t* index, int64_t n_rows, int
   auto* ob = reinterpret_cast<__nv_bfloat16*>(w_hat_bf16);
   const int grid = row_grid(n_rows);
   cudaStream_t st = as_stream(stream);
+  prof_begin(PH_NORMALIZE, st);
   if (vec_per_lane <= 1) normalize_rows_kernel<1><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, w_hat_f32, inv_norm);
   else if (vec_per_lane <= 2) normalize_rows_kernel<2><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, w_hat_f32, inv_norm);
   else if (vec_per_lane <= 4) normalize_rows_kernel<4><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, w_hat_f32, inv_norm);
   else if (vec_per_lane <= 8) normalize_rows_kernel<8><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, w_hat_f32, inv_norm);
   else normalize_rows_kernel<16><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, w_hat_f32, inv_norm);
   PFC_LAUNCH_CHECK();
+  prof_end(PH_NORMALIZE, st);
   return 0;
 }
 

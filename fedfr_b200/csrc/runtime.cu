@@ -5,6 +5,23 @@
 namespace pfc {
 
 static thread_local char g_err[512] = "";
+long long g_launch_count = 0;
+
+// ---- per-phase profiling (off by default) ----
+static int g_prof_on = 0;
+struct ProfSpan { cudaEvent_t a, b; int phase; };
+static ProfSpan g_spans[4096];
+static int g_n_spans = 0;
+static cudaEvent_t g_open[PH_COUNT];
+void prof_begin(int phase, cudaStream_t st) {
+  if (!g_prof_on || g_n_spans >= 4096) return;
+  cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); g_open[phase] = e;
+}
+void prof_end(int phase, cudaStream_t st) {
+  if (!g_prof_on || g_n_spans >= 4096) return;
+  cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
+  g_spans[g_n_spans++] = ProfSpan{g_open[phase], e, phase};
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -51,6 +68,25 @@ int sm_count() {
 extern "C" {
 
 int pfc_version(void) { return 100; }
+
+long long pfc_launch_count(void) { return pfc::g_launch_count; }
+
+/* profiling: enable(1)/disable(0); collect() synchronises, sums the spans per phase (ms) and their counts, and resets */
+int pfc_profile_enable(int on) { pfc::g_prof_on = on; return 0; }
+int pfc_profile_collect(float* ms_out /*[5]*/, int* count_out /*[5]*/) {
+  for (int i = 0; i < pfc::PH_COUNT; ++i) { ms_out[i] = 0.f; count_out[i] = 0; }
+  for (int i = 0; i < pfc::g_n_spans; ++i) {
+    float ms = 0.f;
+    cudaEventSynchronize(pfc::g_spans[i].b);
+    cudaEventElapsedTime(&ms, pfc::g_spans[i].a, pfc::g_spans[i].b);
+    ms_out[pfc::g_spans[i].phase] += ms;
+    count_out[pfc::g_spans[i].phase] += 1;
+    cudaEventDestroy(pfc::g_spans[i].a);
+    cudaEventDestroy(pfc::g_spans[i].b);
+  }
+  pfc::g_n_spans = 0;
+  return 0;
+}
 
 const char* pfc_last_error(void) { return pfc::g_err; }
 

@@ -630,7 +630,10 @@ int tc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t
   const int grid = fwd_grid(n_rows, n_classes, bn);
   PFC_CUDA(cudaMemsetAsync(part_sum, 0, sizeof(float) * (size_t)grid * n_rows, st));
   PFC_CUDA(cudaMemsetAsync(target_logit, 0, sizeof(float) * (size_t)n_rows, st));
-  return dispatch_logits<MODE_STATS>(tx, tw, p, bn, grid, st);
+  prof_begin(PH_FWD, st);
+  int rc = dispatch_logits<MODE_STATS>(tx, tw, p, bn, grid, st);
+  prof_end(PH_FWD, st);
+  return rc;
 }
 
 // ---- backward chunking -------------------------------------------------------------------------
@@ -721,7 +724,9 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
     lp.label = label; lp.n_rows = (int)n_rows; lp.n_classes = (int)cc; lp.class_base = (int)c0; lp.emb = emb;
     lp.n_rb = n_rb; lp.n_ct = (int)((cc + bn - 1) / bn); lp.s = s; lp.m = m;
     lp.row_max = row_max; lp.row_sum = row_sum; lp.g = g; lp.ldg = pl.ldg; lp.g_scale = s * inv_total_batch;
+    prof_begin(PH_GRAD, st);
     if (int rc = dispatch_logits<MODE_GRAD>(tx_k, tw_k, lp, bn, fwd_grid(n_rows, cc, bn), st)) return rc;
+    prof_end(PH_GRAD, st);
     // (2) dx partial slabs
     CUtensorMap tg_k, tw_mn, tg_mn;
     if (int rc = make_tmap_bf16_2d(&tg_k, g, n_rows, cc, pl.ldg, BM)) return rc;            // A K-major [128 rows x 64 classes]
@@ -731,18 +736,21 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
     dp.dx_part = dx_part; dp.accumulate = chunk_idx > 0;
     const int dgrid = n_rb * pl.n_eh * pl.ksplit;
     int rc = 0;
+    prof_begin(PH_DX, st);
     switch (pl.dx_bn) {
       case 256: rc = launch_dx<256>(tg_k, tw_mn, dp, dgrid, st); break;
       case 128: rc = launch_dx<128>(tg_k, tw_mn, dp, dgrid, st); break;
       default: rc = launch_dx<64>(tg_k, tw_mn, dp, dgrid, st); break;
     }
     if (rc) return rc;
+    prof_end(PH_DX, st);
     // (3) dw chunk
     if (int rc2 = make_tmap_bf16_2d(&tg_mn, g, n_rows, cc, pl.ldg, 64)) return rc2;         // A MN-major boxes [64 rows x 64 classes]
     DwParams wp{};
     wp.n_rows = (int)n_rows; wp.n_classes = (int)cc; wp.emb = emb; wp.n_ct = (int)((cc + BM - 1) / BM);
     wp.w_hat = wh + c0 * emb; wp.inv_norm = inv_norm + c0; wp.dw = dw + c0 * emb; wp.accumulate = accumulate_dw;
     const int wgrid = wp.n_ct < sm_count() ? wp.n_ct : sm_count();
+    prof_begin(PH_DW, st);
     switch (emb) {
       case 512: rc = launch_dw<512>(tg_mn, tx_mn, wp, wgrid, st); break;
       case 256: rc = launch_dw<256>(tg_mn, tx_mn, wp, wgrid, st); break;
@@ -750,6 +758,7 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
       default: rc = launch_dw<64>(tg_mn, tx_mn, wp, wgrid, st); break;
     }
     if (rc) return rc;
+    prof_end(PH_DW, st);
   }
   const int64_t n_vec = n_rows * emb / 4;
   int64_t blocks = (n_vec + 255) / 256;

@@ -1,0 +1,69 @@
+"""The C-ABI library loads, exports every symbol include/fedfr_b200.h declares, and fails loudly without a GPU."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def native():
+    import __graft_entry__ as g
+    g.build()
+    from fedfr_b200 import _native
+    return _native
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fedfr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:pfc|fedavg)_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(native):
+    syms = _declared_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(native.lib, s), f"{s} declared in include/fedfr_b200.h but not exported"
+        assert s in native.SIGNATURES, f"{s} has no ctypes signature in fedfr_b200/_native.py"
+    assert native.lib.pfc_version() >= 100
+
+
+def test_pure_host_entries(native):
+    assert native.lib.fedavg_table_bytes(475, 40) > 475 * 40 * 8
+    assert native.lib.pfc_sample_workspace_bytes(250000) > 1024
+    assert native.lib.pfc_fwd_num_partials(0, 0, 512, 0) == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_gpu_fails_loudly(native):
+    rc = native.lib.pfc_query_device(0, None, None, None)
+    assert rc != 0
+    with pytest.raises(RuntimeError):
+        native.check(rc, "pfc_query_device")
+    import fedfr_b200
+    with pytest.raises(RuntimeError):
+        fedfr_b200.PartialFC(0, 0, 1, 4, False, fedfr_b200.CosFace(), 10)
+    with pytest.raises(RuntimeError):
+        fedfr_b200.FedPavg([{"a": torch.zeros(4)}], [1.0])
+
+
+def test_unsupported_margin_is_an_error():
+    from fedfr_b200.losses import margin_params, CosFace
+    assert margin_params(CosFace(s=30.0, m=0.4)) == (30.0, pytest.approx(0.4))
+
+    class ArcFace:
+        s, m = 64.0, 0.5
+    with pytest.raises(NotImplementedError):
+        margin_params(ArcFace())
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under fedfr_b200/ may import, load or execute it."""
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle[/\\.]_?(build|ref)|liboracle|oracle_c", re.M)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "fedfr_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert not pat.search(open(os.path.join(dirpath, f)).read()), f
