@@ -30,21 +30,32 @@ static EncodeTiledFn get_encode() {
   return g_encode;
 }
 
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows,
-                      uint32_t box_cols) {
+static int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, uint32_t esz, uint64_t rows, uint64_t cols,
+                        uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols) {
   EncodeTiledFn enc = get_encode();
   PFC_REQUIRE(enc != nullptr, PFC_E_ARCH, "cuTensorMapEncodeTiled is not available from the CUDA driver");
-  PFC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (row_stride_elems * 2) % 16 == 0, PFC_E_ARG,
+  PFC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (row_stride_elems * esz) % 16 == 0, PFC_E_ARG,
               "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+  PFC_REQUIRE(box_cols * esz == 128 && box_rows <= 256, PFC_E_ARG, "TMA box must be 128 bytes wide and at most 256 rows");
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint64_t strides[1] = {row_stride_elems * esz};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PFC_REQUIRE(r == CUDA_SUCCESS, PFC_E_ARG, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu pitch=%llu box=%ux%u)", (int)r,
               (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)row_stride_elems, box_rows, box_cols);
   return 0;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows,
+                      uint32_t box_cols) {
+  return make_tmap_2d(out, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, cols, row_stride_elems, box_rows, box_cols);
+}
+
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows,
+                     uint32_t box_cols) {
+  return make_tmap_2d(out, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, cols, row_stride_elems, box_rows, box_cols);
 }
 
 namespace tc {
@@ -415,18 +426,21 @@ __global__ void reduce_dx_kernel(const float4* __restrict__ part, int ksplit, in
 // ================================================================================================
 // dw kernel: D[128 classes x E] = G^T[classes, rows] * x_hat[rows, E], epilogue = normalize backward
 //   A = G^T (MN-major: M = classes contiguous in a G row), B = x_hat (MN-major: N = e contiguous), K = rows
+//   Epilogue (thread = class row, full E in TMEM):
+//     pass 1  t_j  = w_hat_j . dwh_j                      (w_hat tile staged by per-warp TMA loads, swizzled smem)
+//     pass 2  dw_j = (dwh_j - w_hat_j t_j) * inv_norm_j   -> swizzled smem staging -> per-warp TMA store / reduce-add
+//   All epilogue traffic is warp-local (own mbarriers, own bulk groups): no CTA-wide barriers.
 // ================================================================================================
 struct DwParams {
   int n_rows, n_classes, emb;     // n_classes = classes in this chunk
   int n_ct;
-  const __nv_bfloat16* w_hat;     // [n_classes, emb] chunk base
   const float* inv_norm;          // [n_classes]
-  float* dw;                      // [n_classes, emb] chunk base
   int accumulate;
 };
 
 template <int EMB, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                                                         const __grid_constant__ CUtensorMap tmap_wh, const __grid_constant__ CUtensorMap tmap_dw,
                                                          const DwParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -434,12 +448,17 @@ __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__
   constexpr int kBBytes = (EMB / 64) * kBoxBytes;        // EMB x 64 rows
   constexpr int kStageBytes = kABytes + kBBytes;
   constexpr int UN = EMB < 256 ? EMB : 256;              // N per MMA instruction
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  constexpr int kWBox = 32 * 128;                        // per-warp w_hat chunk: 32 classes x 64 e bf16 = 4 KB
+  constexpr int kOBox = 32 * 128;                        // per-warp out staging: 32 classes x 32 e fp32 = 4 KB
+  uint8_t* smem_w = smem + STAGES * kStageBytes;         // [4 warps][2] w_hat chunks
+  uint8_t* smem_o = smem_w + 4 * 2 * kWBox;              // [4 warps][2] staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + 4 * 2 * kOBox);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+  uint64_t* wfull = bars + 2 * STAGES + 2;               // [4 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kb = (p.n_rows + BK - 1) / BK;
@@ -448,9 +467,10 @@ __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, kEpiWarps);
+    for (int i = 0; i < 8; ++i) mbar_init(&wfull[i], 1);
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) { prefetch_tmap(&tmap_g); prefetch_tmap(&tmap_x); }
+  if (warp == 4 && lane == 0) { prefetch_tmap(&tmap_g); prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_wh); prefetch_tmap(&tmap_dw); }
   if (warp == 5) tmem_alloc<EMB>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -503,64 +523,79 @@ __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__
       }
     }
   } else {
+    // ------------------------------------------------------------------ epilogue: warp w owns classes [32w, 32w+32) of the tile
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    uint8_t* wbuf = smem_w + warp * 2 * kWBox;
+    uint8_t* obuf = smem_o + warp * 2 * kOBox;
+    uint64_t* wbar = wfull + warp * 2;
+    constexpr int NKC = EMB / 64;                         // w_hat chunks per pass
+    uint32_t wn = 0;                                      // w_hat chunk counter of this warp (slot = wn & 1, parity = (wn >> 1) & 1)
+    uint32_t on = 0;                                      // staging step counter
     int it = 0;
     for (int ct = blockIdx.x; ct < p.n_ct; ct += gridDim.x, ++it) {
-      const int cls = ct * BM + threadIdx.x;
+      const int cls0 = ct * BM + warp * 32;
+      const int cls = cls0 + lane;
       const bool ok = cls < p.n_classes;
+      const float inv_n = ok ? p.inv_norm[cls] : 0.f;
+      if (lane == 0) {                                    // prefetch the first w_hat chunk while the MMAs finish
+        mbar_arrive_expect_tx(&wbar[wn & 1], kWBox);
+        tma_load_2d(wbuf + (wn & 1) * kWBox, &tmap_wh, &wbar[wn & 1], 0, cls0);
+      }
       mbar_wait(tmem_full, (uint32_t)(it & 1));
       tc_fence_after();
-      const __nv_bfloat16* wrow = p.w_hat + (int64_t)cls * EMB;
-      // pass 1: radial component  t = w_hat_j . dwh_j
       float radial = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < EMB; c += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(tmem_base + lane_base + c, v);
-        tmem_ld_wait();
-        if (ok) {
-          const uint4* wv = reinterpret_cast<const uint4*>(wrow + c);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 w8 = wv[q];
-            const uint32_t ws[4] = {w8.x, w8.y, w8.z, w8.w};
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              const float2 wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ws[h]));
-              radial += wf.x * __uint_as_float(v[q * 8 + h * 2]) + wf.y * __uint_as_float(v[q * 8 + h * 2 + 1]);
-            }
-          }
+      for (int i = 0; i < 2 * NKC; ++i) {
+        const int kc = i % NKC;
+        const bool pass2 = i >= NKC;
+        __syncwarp();                                     // everyone is done with the slot the next load overwrites
+        if (lane == 0 && i + 1 < 2 * NKC) {
+          const uint32_t nx = wn + 1;
+          mbar_arrive_expect_tx(&wbar[nx & 1], kWBox);
+          tma_load_2d(wbuf + (nx & 1) * kWBox, &tmap_wh, &wbar[nx & 1], ((i + 1) % NKC) * 64, cls0);
         }
-      }
-      const float inv_n = ok ? p.inv_norm[cls] : 0.f;
-      // pass 2: dw = (dwh - w_hat * t) / n
-#pragma unroll 1
-      for (int c = 0; c < EMB; c += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(tmem_base + lane_base + c, v);
-        tmem_ld_wait();
-        if (ok) {
-          const uint4* wv = reinterpret_cast<const uint4*>(wrow + c);
-          float4* o = reinterpret_cast<float4*>(p.dw + (int64_t)cls * EMB + c);
+        mbar_wait(&wbar[wn & 1], (wn >> 1) & 1);
+        const uint8_t* wrow = wbuf + (wn & 1) * kWBox;
+        ++wn;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                     // two groups of 32 e per 64-wide chunk
+          uint32_t v[32];
+          tmem_ld_x32(tmem_base + lane_base + kc * 64 + h * 32, v);
+          float wf[32];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 w8 = wv[q];
-            const uint32_t ws[4] = {w8.x, w8.y, w8.z, w8.w};
-            float r[8];
+            const uint4 w8 = *reinterpret_cast<const uint4*>(wrow + sw128_off(lane, h * 4 + q));
+            // bf16 -> fp32 is a 16-bit shift
+            wf[q * 8 + 0] = __uint_as_float(w8.x << 16); wf[q * 8 + 1] = __uint_as_float(w8.x & 0xffff0000u);
+            wf[q * 8 + 2] = __uint_as_float(w8.y << 16); wf[q * 8 + 3] = __uint_as_float(w8.y & 0xffff0000u);
+            wf[q * 8 + 4] = __uint_as_float(w8.z << 16); wf[q * 8 + 5] = __uint_as_float(w8.z & 0xffff0000u);
+            wf[q * 8 + 6] = __uint_as_float(w8.w << 16); wf[q * 8 + 7] = __uint_as_float(w8.w & 0xffff0000u);
+          }
+          tmem_ld_wait();
+          if (!pass2) {
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              const float2 wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ws[h]));
-              r[h * 2] = (__uint_as_float(v[q * 8 + h * 2]) - wf.x * radial) * inv_n;
-              r[h * 2 + 1] = (__uint_as_float(v[q * 8 + h * 2 + 1]) - wf.y * radial) * inv_n;
+            for (int j = 0; j < 32; ++j) radial = fmaf(wf[j], __uint_as_float(v[j]), radial);
+          } else {
+            uint8_t* orow = obuf + (on & 1) * kOBox;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 r;
+              r.x = (__uint_as_float(v[4 * q + 0]) - wf[4 * q + 0] * radial) * inv_n;
+              r.y = (__uint_as_float(v[4 * q + 1]) - wf[4 * q + 1] * radial) * inv_n;
+              r.z = (__uint_as_float(v[4 * q + 2]) - wf[4 * q + 2] * radial) * inv_n;
+              r.w = (__uint_as_float(v[4 * q + 3]) - wf[4 * q + 3] * radial) * inv_n;
+              *reinterpret_cast<float4*>(orow + sw128_off(lane, q)) = r;
             }
-            float4 r0 = make_float4(r[0], r[1], r[2], r[3]), r1 = make_float4(r[4], r[5], r[6], r[7]);
-            if (p.accumulate) {
-              const float4 a = o[2 * q], b = o[2 * q + 1];
-              r0.x += a.x; r0.y += a.y; r0.z += a.z; r0.w += a.w;
-              r1.x += b.x; r1.y += b.y; r1.z += b.z; r1.w += b.w;
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (p.accumulate) tma_reduce_add_2d(&tmap_dw, orow, kc * 64 + h * 32, cls0);
+              else tma_store_2d(&tmap_dw, orow, kc * 64 + h * 32, cls0);
+              tma_store_commit();
+              tma_store_wait_read<1>();                   // the other staging buffer is free again
             }
-            o[2 * q] = r0;
-            o[2 * q + 1] = r1;
+            ++on;
+            __syncwarp();
           }
         }
       }
@@ -568,6 +603,7 @@ __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty);
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -646,7 +682,7 @@ struct BwdPlan {
 
 static BwdPlan make_bwd_plan(int64_t n_rows, int64_t n_classes, int emb) {
   BwdPlan pl{};
-  int64_t budget = 128ll << 20;     // bytes of bf16 G scratch per chunk
+  int64_t budget = 256ll << 20;     // bytes of bf16 G scratch per chunk (fewer, larger launches measured faster)
   if (const char* e = getenv("FEDFR_G_CHUNK_MB")) { long v = atol(e); if (v > 0) budget = (int64_t)v << 20; }
   int64_t chunk = budget / (n_rows * 2);
   chunk = chunk / 256 * 256;
@@ -687,12 +723,13 @@ static int launch_dx(const CUtensorMap& tg, const CUtensorMap& tw, const DxParam
 }
 
 template <int EMB>
-static int launch_dw(const CUtensorMap& tg, const CUtensorMap& tx, const DwParams& p, int grid, cudaStream_t st) {
+static int launch_dw(const CUtensorMap& tg, const CUtensorMap& tx, const CUtensorMap& twh, const CUtensorMap& tdw, const DwParams& p, int grid,
+                     cudaStream_t st) {
   constexpr int STAGES = EMB == 512 ? 2 : (EMB == 256 ? 4 : 6);
-  const size_t smem = (size_t)STAGES * (2 * kBoxBytes + (EMB / 64) * kBoxBytes) + 1024 + 256;
+  const size_t smem = (size_t)STAGES * (2 * kBoxBytes + (EMB / 64) * kBoxBytes) + 8 * 4096 * 2 + 1024 + 256;
   auto kern = dw_kernel<EMB, STAGES>;
   PFC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kThreads, smem, st>>>(tg, tx, p);
+  kern<<<grid, kThreads, smem, st>>>(tg, tx, twh, tdw, p);
   PFC_LAUNCH_CHECK();
   return 0;
 }
@@ -748,14 +785,17 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
     if (int rc2 = make_tmap_bf16_2d(&tg_mn, g, n_rows, cc, pl.ldg, 64)) return rc2;         // A MN-major boxes [64 rows x 64 classes]
     DwParams wp{};
     wp.n_rows = (int)n_rows; wp.n_classes = (int)cc; wp.emb = emb; wp.n_ct = (int)((cc + BM - 1) / BM);
-    wp.w_hat = wh + c0 * emb; wp.inv_norm = inv_norm + c0; wp.dw = dw + c0 * emb; wp.accumulate = accumulate_dw;
+    wp.inv_norm = inv_norm + c0; wp.accumulate = accumulate_dw;
+    CUtensorMap twh_e, tdw_e;
+    if (int rc3 = make_tmap_bf16_2d(&twh_e, wh + c0 * emb, cc, emb, emb, 32)) return rc3;      // epilogue: per-warp [32 classes x 64 e]
+    if (int rc3 = make_tmap_f32_2d(&tdw_e, dw + c0 * emb, cc, emb, emb, 32)) return rc3;       // epilogue: per-warp [32 classes x 32 e] fp32
     const int wgrid = wp.n_ct < sm_count() ? wp.n_ct : sm_count();
     prof_begin(PH_DW, st);
     switch (emb) {
-      case 512: rc = launch_dw<512>(tg_mn, tx_mn, wp, wgrid, st); break;
-      case 256: rc = launch_dw<256>(tg_mn, tx_mn, wp, wgrid, st); break;
-      case 128: rc = launch_dw<128>(tg_mn, tx_mn, wp, wgrid, st); break;
-      default: rc = launch_dw<64>(tg_mn, tx_mn, wp, wgrid, st); break;
+      case 512: rc = launch_dw<512>(tg_mn, tx_mn, twh_e, tdw_e, wp, wgrid, st); break;
+      case 256: rc = launch_dw<256>(tg_mn, tx_mn, twh_e, tdw_e, wp, wgrid, st); break;
+      case 128: rc = launch_dw<128>(tg_mn, tx_mn, twh_e, tdw_e, wp, wgrid, st); break;
+      default: rc = launch_dw<64>(tg_mn, tx_mn, twh_e, tdw_e, wp, wgrid, st); break;
     }
     if (rc) return rc;
     prof_end(PH_DW, st);
