@@ -8,21 +8,28 @@
 
 namespace pfc {
 
-__global__ void merge_stats_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
-                                   const float* __restrict__ target_logit, int n_part, int64_t n_rows, float* __restrict__ stats) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per row: lanes stride over the partial slots
+__global__ void __launch_bounds__(256) merge_stats_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
+                                                          const float* __restrict__ target_logit, int n_part, int64_t n_rows,
+                                                          float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n_rows) return;
   float M = -INFINITY;
-  for (int p = 0; p < n_part; ++p)
+  for (int p = lane; p < n_part; p += 32)
     if (part_sum[(int64_t)p * n_rows + r] > 0.f) M = fmaxf(M, part_max[(int64_t)p * n_rows + r]);
+  M = warp_max(M);
   float S = 0.f;
-  for (int p = 0; p < n_part; ++p) {
+  for (int p = lane; p < n_part; p += 32) {
     const float l = part_sum[(int64_t)p * n_rows + r];
     if (l > 0.f) S += l * expf(part_max[(int64_t)p * n_rows + r] - M);
   }
-  stats[r * 3 + 0] = M;
-  stats[r * 3 + 1] = S;
-  stats[r * 3 + 2] = target_logit[r];
+  S = warp_sum(S);
+  if (lane == 0) {
+    stats[r * 3 + 0] = M;
+    stats[r * 3 + 1] = S;
+    stats[r * 3 + 2] = target_logit[r];
+  }
 }
 
 // single block: rows strided over threads, block reduction for the loss
@@ -68,7 +75,7 @@ int pfc_merge_stats(const float* part_max, const float* part_sum, const float* t
   if (int rc = require_sm100()) return rc;
   PFC_REQUIRE(part_max && part_sum && target_logit && stats && n_partials > 0 && n_rows >= 0, PFC_E_ARG, "pfc_merge_stats: bad argument");
   if (n_rows == 0) return 0;
-  merge_stats_kernel<<<(int)((n_rows + 127) / 128), 128, 0, as_stream(stream)>>>(part_max, part_sum, target_logit, n_partials, n_rows, stats);
+  merge_stats_kernel<<<(int)((n_rows + 7) / 8), 256, 0, as_stream(stream)>>>(part_max, part_sum, target_logit, n_partials, n_rows, stats);
   PFC_LAUNCH_CHECK();
   return 0;
 }

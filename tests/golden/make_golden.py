@@ -163,13 +163,13 @@ def sha(arrs):
 
 CASES = {
     # name: cfg.   store_inputs=False -> inputs are regenerated from the seed and pinned by sha256
-    "w1_sr1_small": dict(seed=1, world_size=1, batch=16, num_classes=200, emb=512, sample_rate=1.0, s=64.0, m=0.4, lr=0.1, steps=2, store_inputs=True),
-    "w1_sr1_s30": dict(seed=2, world_size=1, batch=24, num_classes=96, emb=128, sample_rate=1.0, s=30.0, m=0.4, lr=0.1, steps=1, store_inputs=True),
-    "w1_sr01": dict(seed=3, world_size=1, batch=16, num_classes=400, emb=128, sample_rate=0.1, s=64.0, m=0.4, lr=0.1, steps=2, store_inputs=True),
-    "w1_sr_pos_overflow": dict(seed=4, world_size=1, batch=64, num_classes=300, emb=64, sample_rate=0.1, s=64.0, m=0.4, lr=0.1, steps=1, store_inputs=True),
-    "w2_sr1_ragged": dict(seed=5, world_size=2, batch=16, num_classes=301, emb=128, sample_rate=1.0, s=64.0, m=0.4, lr=0.1, steps=1, store_inputs=True),
-    "w2_sr03": dict(seed=6, world_size=2, batch=16, num_classes=401, emb=128, sample_rate=0.3, s=64.0, m=0.4, lr=0.1, steps=2, store_inputs=True),
-    "c1_b128_c10k": dict(seed=100, world_size=1, batch=128, num_classes=10000, emb=512, sample_rate=1.0, s=64.0, m=0.4, lr=0.1, steps=1, store_inputs=False),
+    "w1_sr1_small": dict(seed=1, world_size=1, batch=16, num_classes=200, emb=512, sample_rate=1.0, s=64.0, m=0.4, lr=0.002, steps=2, store_inputs=True),
+    "w1_sr1_s30": dict(seed=2, world_size=1, batch=24, num_classes=96, emb=128, sample_rate=1.0, s=30.0, m=0.4, lr=0.002, steps=1, store_inputs=True),
+    "w1_sr01": dict(seed=3, world_size=1, batch=16, num_classes=400, emb=128, sample_rate=0.1, s=64.0, m=0.4, lr=0.002, steps=2, store_inputs=True),
+    "w1_sr_pos_overflow": dict(seed=4, world_size=1, batch=64, num_classes=300, emb=64, sample_rate=0.1, s=64.0, m=0.4, lr=0.002, steps=1, store_inputs=True),
+    "w2_sr1_ragged": dict(seed=5, world_size=2, batch=16, num_classes=301, emb=128, sample_rate=1.0, s=64.0, m=0.4, lr=0.002, steps=1, store_inputs=True),
+    "w2_sr03": dict(seed=6, world_size=2, batch=16, num_classes=401, emb=128, sample_rate=0.3, s=64.0, m=0.4, lr=0.002, steps=2, store_inputs=True),
+    "c1_b128_c10k": dict(seed=100, world_size=1, batch=128, num_classes=10000, emb=512, sample_rate=1.0, s=64.0, m=0.4, lr=0.002, steps=1, store_inputs=False),
 }
 
 

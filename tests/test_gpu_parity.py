@@ -32,9 +32,10 @@ def pkg():
 
 
 def rel(a, b):
+    """Relative L2 error with an absolute floor (1e-7 rms) so vanishing gradients do not divide by ~0."""
     a = torch.as_tensor(a, dtype=torch.float64).cpu()
     b = torch.as_tensor(b, dtype=torch.float64).cpu()
-    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+    return float((a - b).norm() / (b.norm() + 1e-7 * b.numel() ** 0.5))
 
 
 def _make_head(pkg, cfg, weight, check_mode, rank=0, world=1):
@@ -72,7 +73,7 @@ def test_golden_single_rank(pkg, name, check_mode, monkeypatch):
         opt.step()
         head.update()
         opt.zero_grad()
-        # lr=0.1 amplifies the gradient error into the weights: compare the update, not the weights
+        # compare the update (lr * momentum buffer), not the weights it is added to
         w_ref, w0 = case.get(0, step, "weight_after"), (case.weights[0].numpy() if step == 0 else prev_w)
         assert rel(head.weight.cpu().numpy() - w0, w_ref - w0) < 2 * tol
         prev_w = w_ref
@@ -89,7 +90,7 @@ def test_c1_config_vs_golden(pkg, check_mode):
     case = Case("c1_b128_c10k")
     head = _make_head(pkg, case.cfg, case.weights[0], check_mode)
     dev = head.device
-    opt = torch.optim.SGD([{"params": head.parameters()}], lr=0.1, momentum=0.9, weight_decay=5e-4)
+    opt = torch.optim.SGD([{"params": head.parameters()}], lr=case.cfg["lr"], momentum=0.9, weight_decay=5e-4)
     x_grad, loss = head.forward_backward(case.labels[0].to(dev), case.features[0].to(dev), opt)
     tol = TOL[check_mode]
     assert abs(float(loss) - float(case.get(0, 0, "loss"))) <= tol * float(case.get(0, 0, "loss"))
