@@ -163,6 +163,10 @@ def run_ours(args):
     B, C, E, sr = WORKLOADS[args.workload]
     if args.logits_tile:
         N.check(N.lib.pfc_set_logits_tile(args.logits_tile), "pfc_set_logits_tile")
+    if args.radial_mode != 2:
+        N.lib.pfc_set_radial_mode(args.radial_mode)
+    if args.dx_cluster or args.dw_cluster:
+        N.lib.pfc_set_clusters(args.dx_cluster, args.dw_cluster)
     torch.manual_seed(100 + rank)
     head = fedfr_b200.PartialFC(rank, local_rank, world, B, False, fedfr_b200.CosFace(s=S, m=M), C, sample_rate=sr, embedding_size=E, prefix="/tmp")
     opt = torch.optim.SGD([{"params": head.parameters()}], lr=0.1, momentum=0.9, weight_decay=5e-4)
@@ -287,6 +291,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--logits-tile", type=int, default=0)
+    ap.add_argument("--radial-mode", type=int, default=2)
+    ap.add_argument("--dx-cluster", type=int, default=0)
+    ap.add_argument("--dw-cluster", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

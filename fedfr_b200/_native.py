@@ -58,6 +58,8 @@ lib.pfc_profile_enable.restype = _i32
 lib.pfc_profile_enable.argtypes = [_i32]
 lib.pfc_profile_collect.restype = _i32
 lib.pfc_profile_collect.argtypes = [C.POINTER(C.c_float), C.POINTER(_i32)]
+lib.pfc_set_clusters.restype = _i32
+lib.pfc_set_clusters.argtypes = [_i32, _i32]
 lib.pfc_set_logits_tile.restype = _i32
 lib.pfc_set_logits_tile.argtypes = [_i32]
 

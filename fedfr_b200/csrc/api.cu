@@ -11,6 +11,9 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
            int64_t n_rows, int64_t n_classes, int emb, float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
            void* workspace, size_t workspace_bytes, cudaStream_t st);
 void tc_set_fwd_bn(int bn);
+void tc_set_clusters(int dx_cs, int dw_cs);
+void tc_set_debug(long long* p);
+void tc_set_radial_mode(int m);
 int simt_fwd_num_partials(int64_t n_rows, int64_t n_classes);
 int simt_fwd_stats(const float* x, const float* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m,
                    float* part_max, float* part_sum, float* target_logit, cudaStream_t st);
@@ -66,6 +69,21 @@ int pfc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64
 int pfc_set_logits_tile(int bn) {
   PFC_REQUIRE(bn == 128 || bn == 256, PFC_E_ARG, "pfc_set_logits_tile: bn must be 128 or 256");
   tc_set_fwd_bn(bn);
+  return 0;
+}
+
+int pfc_set_radial_mode(int m) {   /* timing experiment only: anything but 2 gives wrong dw */
+  tc_set_radial_mode(m);
+  return 0;
+}
+
+int pfc_set_debug_buffer(void* dev_ptr) {
+  tc_set_debug(reinterpret_cast<long long*>(dev_ptr));
+  return 0;
+}
+
+int pfc_set_clusters(int dx_cluster, int dw_cluster) {
+  tc_set_clusters(dx_cluster, dw_cluster);
   return 0;
 }
 

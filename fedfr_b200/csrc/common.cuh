@@ -29,6 +29,7 @@ void prof_end(int phase, cudaStream_t st);
   do {                                                                                 \
     cudaError_t e__ = (call);                                                          \
     if (e__ != cudaSuccess) {                                                          \
+      (void)cudaGetLastError();                                                        \
       ::pfc::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
       return (int)e__;                                                                 \
     }                                                                                  \

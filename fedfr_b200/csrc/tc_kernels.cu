@@ -60,8 +60,10 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 
 namespace tc {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;          // dx / dw kernels: 4 epilogue warps + TMA warp + MMA warp
 constexpr int kEpiWarps = 4;
+constexpr int kLogitsEpiWarps = 8;     // logits kernels: two warps per TMEM lane quadrant, each takes half of the tile's columns
+constexpr int kLogitsThreads = (kLogitsEpiWarps + 2) * 32;
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kChunkBytes = BM * BK * 2;      // one [128 x 64] bf16 K-major tile = 16 KB
@@ -87,12 +89,47 @@ struct LogitsParams {
   __nv_bfloat16* g;          // [n_rows, ldg]
   int64_t ldg;
   float g_scale;             // s / total_batch
+  float* radial;             // [n_classes] += sum_i G_ij cos_ij  (= w_hat_j . dwh_j, the normalize-backward projection)
+  int radial_mode;           // 2 = on (default); 0/1 are timing experiments (skip / no atomics)
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// Column sums of a 32x32 block held one row per lane: lane L returns sum over lanes r of h_r[L]
+// (recursive halving: 31 shuffles instead of 32 five-step reductions).
+__device__ __forceinline__ float warp_colsum32(const float (&h)[32], int lane) {
+  float a[16];
+  bool up = lane & 16;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float send = up ? h[k] : h[k + 16], keep = up ? h[k + 16] : h[k];
+    a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  up = lane & 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float send = up ? a[k] : a[k + 8], keep = up ? a[k + 8] : a[k];
+    a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  up = lane & 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float send = up ? a[k] : a[k + 4], keep = up ? a[k + 4] : a[k];
+    a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  up = lane & 2;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float send = up ? a[k] : a[k + 2], keep = up ? a[k + 2] : a[k];
+    a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  up = lane & 1;
+  const float send = up ? a[0] : a[1], keep = up ? a[1] : a[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
 struct PipeState {
@@ -107,7 +144,7 @@ struct PipeState {
 // logits kernel: A = x_hat row block (stationary in smem), B = w_hat class tiles (streamed)
 // ================================================================================================
 template <int BN, int STAGES, int MODE>
-__global__ void __launch_bounds__(kThreads, 1) logits_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+__global__ void __launch_bounds__(kLogitsThreads, 1) logits_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                                                              const LogitsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -129,19 +166,20 @@ __global__ void __launch_bounds__(kThreads, 1) logits_kernel(const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kLogitsEpiWarps); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); }
-  if (warp == 5) tmem_alloc<2 * BN>(tmem_slot);
+  constexpr int kProducerWarp = kLogitsEpiWarps, kMmaWarp = kLogitsEpiWarps + 1;
+  if (warp == kProducerWarp && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); }
+  if (warp == kMmaWarp) tmem_alloc<2 * BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == kProducerWarp) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       PipeState ps;
@@ -163,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) logits_kernel(const __grid_consta
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
@@ -202,9 +240,12 @@ __global__ void __launch_bounds__(kThreads, 1) logits_kernel(const __grid_consta
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 0..3), thread = row
+    // ------------------------------------------------------------------ epilogue (warps 0..7), thread = row;
+    // warp w reads TMEM lanes [32 (w & 3), +32) and the column half (w >> 2) of every tile
+    const int quad = warp & 3, chalf = warp >> 2;
+    constexpr int CH = BN / 2;
     const float s2 = p.s * kLog2e, ms2 = p.m * p.s * kLog2e;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     int cur_rb = -1;
     constexpr int kNoLabel = -(1 << 30);
     int row = 0, my_label = kNoLabel;
@@ -216,11 +257,11 @@ __global__ void __launch_bounds__(kThreads, 1) logits_kernel(const __grid_consta
       const int rb = (int)(t / p.n_ct), ct = (int)(t % p.n_ct);
       if (rb != cur_rb) {
         if (MODE == MODE_STATS && cur_rb >= 0 && row_ok) {
-          p.part_max[(int64_t)blockIdx.x * p.n_rows + row] = run_m * kLn2;
-          p.part_sum[(int64_t)blockIdx.x * p.n_rows + row] = run_l;
+          p.part_max[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = run_m * kLn2;
+          p.part_sum[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = run_l;
         }
         cur_rb = rb;
-        row = rb * BM + threadIdx.x;
+        row = rb * BM + quad * 32 + lane;
         row_ok = row < p.n_rows;
         my_label = kNoLabel;
         if (row_ok) {
@@ -237,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) logits_kernel(const __grid_consta
       const int col0 = ct * BN;
       const bool tile_has_oob = col0 + BN > p.n_classes;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = chalf * CH; c < (chalf + 1) * CH; c += 32) {
         uint32_t v[32];
         tmem_ld_x32(tmem_base + lane_base + acc * BN + c, v);
         tmem_ld_wait();
@@ -278,10 +319,20 @@ __global__ void __launch_bounds__(kThreads, 1) logits_kernel(const __grid_consta
             if (j + 1 == hit) g1 -= 1.0f;
             pk[j >> 1] = pack_bf16x2(g0 * p.g_scale, g1 * p.g_scale);
           }
-          if (row_ok && cb < p.ldg) {
-            uint4* dst = reinterpret_cast<uint4*>(p.g + (int64_t)row * p.ldg + cb);
+          if (cb < p.ldg) {   // blocked scratch: [class block of 64][row block][128 rows][64 classes]; padded rows hold zeros
+            uint4* dst = reinterpret_cast<uint4*>(p.g + ((int64_t)((cb >> 6) * p.n_rb + rb) * BM + quad * 32 + lane) * 64 + (cb & 32));
 #pragma unroll
             for (int q = 0; q < 4; ++q) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          }
+          if (p.radial_mode) {   // radial_j += sum over this warp's 32 rows of bf16(G_ij) * cos_ij   (rows past n_rows hold G = 0)
+            float h[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              h[j] = __uint_as_float(pk[j >> 1] << 16) * __uint_as_float(v[j]);
+              h[j + 1] = __uint_as_float(pk[j >> 1] & 0xffff0000u) * __uint_as_float(v[j + 1]);
+            }
+            const float cs = warp_colsum32(h, lane);
+            if (p.radial_mode > 1 && cb + lane < p.n_classes) atomicAdd(p.radial + cb + lane, cs);
           }
         }
       }
@@ -290,13 +341,13 @@ __global__ void __launch_bounds__(kThreads, 1) logits_kernel(const __grid_consta
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
     if (MODE == MODE_STATS && cur_rb >= 0 && row_ok) {
-      p.part_max[(int64_t)blockIdx.x * p.n_rows + row] = run_m * kLn2;
-      p.part_sum[(int64_t)blockIdx.x * p.n_rows + row] = run_l;
+      p.part_max[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = run_m * kLn2;
+      p.part_sum[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = run_l;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<2 * BN>(tmem_base);
+  if (warp == kMmaWarp) tmem_dealloc<2 * BN>(tmem_base);
 }
 
 // ================================================================================================
@@ -310,7 +361,7 @@ struct DxParams {
   int accumulate;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CS>
 __global__ void __launch_bounds__(kThreads, 1) dx_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_w,
                                                          const DxParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -324,20 +375,23 @@ __global__ void __launch_bounds__(kThreads, 1) dx_kernel(const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int u = blockIdx.x;
-  const int ks = u % p.ksplit, eh = (u / p.ksplit) % p.n_eh, rb = u / (p.ksplit * p.n_eh);
+  // cluster = CS consecutive row blocks working on the same (e-half, class slice): they share the w_hat stream
+  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0;
+  const int grp = blockIdx.x / CS;
+  const int ks = grp % p.ksplit, eh = (grp / p.ksplit) % p.n_eh, rb = (grp / (p.ksplit * p.n_eh)) * CS + (int)crank;
+  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1);
   const int n_kb_total = (p.n_classes + BK - 1) / BK;
   const int kb0 = (int)((int64_t)n_kb_total * ks / p.ksplit), kb1 = (int)((int64_t)n_kb_total * (ks + 1) / p.ksplit);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CS); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
   if (warp == 4 && lane == 0) { prefetch_tmap(&tmap_g); prefetch_tmap(&tmap_w); }
   if (warp == 5) tmem_alloc<BN>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  if (CS > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -349,9 +403,18 @@ __global__ void __launch_bounds__(kThreads, 1) dx_kernel(const __grid_constant__
         uint8_t* sa = smem + ps.stage * kStageBytes;
         uint8_t* sb = sa + kChunkBytes;
         mbar_arrive_expect_tx(&full[ps.stage], kStageBytes);
-        tma_load_2d(sa, &tmap_g, &full[ps.stage], kb * BK, rb * BM);
+        tma_load_2d(sa, &tmap_g, &full[ps.stage], 0, (kb * p.n_rb + rb) * BM);      // one contiguous 16 KB block of the G scratch
+        if (CS == 1) {
 #pragma unroll
-        for (int nb = 0; nb < BN / 64; ++nb) tma_load_2d(sb + nb * kBoxBytes, &tmap_w, &full[ps.stage], eh * BN + nb * 64, kb * BK);
+          for (int nb = 0; nb < BN / 64; ++nb) tma_load_2d(sb + nb * kBoxBytes, &tmap_w, &full[ps.stage], eh * BN + nb * 64, kb * BK);
+        } else {                                  // this CTA fetches 1/CS of the w_hat boxes for the whole cluster
+          constexpr int kPer = (BN / 64) / CS;
+#pragma unroll
+          for (int q = 0; q < kPer; ++q) {
+            const int nb = (int)crank * kPer + q;
+            tma_load_2d_mc(sb + nb * kBoxBytes, &tmap_w, &full[ps.stage], eh * BN + nb * 64, kb * BK, kMask);
+          }
+        }
         ps.advance(STAGES);
       }
     }
@@ -370,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) dx_kernel(const __grid_constant__
           const uint64_t db = make_desc_sw128(b_addr + kk * 2048, kBoxBytes, 1024);
           umma_bf16_ss(tmem_base, da, db, idesc, (kb != kb0) || (kk != 0));
         }
-        umma_commit(&empty[ps.stage]);
+        if (CS == 1) umma_commit(&empty[ps.stage]); else umma_commit_mc(&empty[ps.stage], kMask);
         ps.advance(STAGES);
       }
       umma_commit(tmem_full);
@@ -408,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) dx_kernel(const __grid_constant__
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CS > 1) cluster_sync_all(); else __syncthreads();     // peers may still multicast into / arrive on this CTA
   if (warp == 5) tmem_dealloc<BN>(tmem_base);
 }
 
@@ -424,190 +487,218 @@ __global__ void reduce_dx_kernel(const float4* __restrict__ part, int ksplit, in
 }
 
 // ================================================================================================
-// dw kernel: D[128 classes x E] = G^T[classes, rows] * x_hat[rows, E], epilogue = normalize backward
+// dw kernel: D[128 classes x EN e] = G^T[classes, rows] * x_hat[rows, e-slice], epilogue = normalize backward
 //   A = G^T (MN-major: M = classes contiguous in a G row), B = x_hat (MN-major: N = e contiguous), K = rows
-//   Epilogue (thread = class row, full E in TMEM):
-//     pass 1  t_j  = w_hat_j . dwh_j                      (w_hat tile staged by per-warp TMA loads, swizzled smem)
-//     pass 2  dw_j = (dwh_j - w_hat_j t_j) * inv_norm_j   -> swizzled smem staging -> per-warp TMA store / reduce-add
-//   All epilogue traffic is warp-local (own mbarriers, own bulk groups): no CTA-wide barriers.
+//   Work item = (class tile, e-slice of EN = min(E, 256) columns): the accumulator is EN TMEM columns, two of them
+//   are allocated so the epilogue of item k overlaps the MMAs of item k+1.
+//   The radial term t_j = w_hat_j . dwh_j of the normalize backward was accumulated by the G kernel
+//   (LogitsParams::radial), so the epilogue is a single pass:
+//       dw_j[e] = (acc[e] - w_hat_j[e] * t_j) * inv_norm_j
+//   Each epilogue warp owns 32 classes: its w_hat rows arrive by its own TMA loads into swizzled smem (issued one
+//   item ahead), the result leaves through swizzled staging boxes and its own TMA stores / reduce-adds.
+//   Cluster of CS CTAs = CS class tiles in lock step sharing the x_hat stream by TMA multicast.
 // ================================================================================================
 struct DwParams {
   int n_rows, n_classes, emb;     // n_classes = classes in this chunk
-  int n_ct;
+  int n_ct, n_rb;
   const float* inv_norm;          // [n_classes]
+  const float* radial;            // [n_classes]
   int accumulate;
+  long long* dbg;                 // optional cycle counters of CTA 0 (developer instrumentation), else nullptr
 };
 
-template <int EMB, int STAGES>
+template <int EMB, int STAGES, int CS>
 __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
                                                          const __grid_constant__ CUtensorMap tmap_wh, const __grid_constant__ CUtensorMap tmap_dw,
                                                          const DwParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int EN = EMB < 256 ? EMB : 256;              // accumulator width = N of one MMA
+  constexpr int NH = EMB / EN;                           // e-slices per class tile
+  constexpr int NBOX = EN / 64;                          // 64-wide boxes per e-slice
   constexpr int kABytes = 2 * kBoxBytes;                 // 128 classes x 64 rows
-  constexpr int kBBytes = (EMB / 64) * kBoxBytes;        // EMB x 64 rows
+  constexpr int kBBytes = NBOX * kBoxBytes;              // EN x 64 rows
   constexpr int kStageBytes = kABytes + kBBytes;
-  constexpr int UN = EMB < 256 ? EMB : 256;              // N per MMA instruction
-  constexpr int kWBox = 32 * 128;                        // per-warp w_hat chunk: 32 classes x 64 e bf16 = 4 KB
-  constexpr int kOBox = 32 * 128;                        // per-warp out staging: 32 classes x 32 e fp32 = 4 KB
-  uint8_t* smem_w = smem + STAGES * kStageBytes;         // [4 warps][2] w_hat chunks
-  uint8_t* smem_o = smem_w + 4 * 2 * kWBox;              // [4 warps][2] staging
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + 4 * 2 * kOBox);
+  constexpr int kWBox = 32 * 128;                        // per-warp w_hat box: 32 classes x 64 e bf16 = 4 KB
+  constexpr int kWWarp = NBOX * kWBox;                   // per-warp w_hat slice
+  constexpr int kOBox = 32 * 128;                        // per-warp staging box: 32 classes x 32 e fp32 = 4 KB
+  uint8_t* smem_w = smem + STAGES * kStageBytes;         // [4 warps][NBOX] w_hat boxes
+  uint8_t* smem_o = smem_w + 4 * kWWarp;                 // [4 warps] staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + 4 * kOBox);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
-  uint64_t* tmem_full = bars + 2 * STAGES;
-  uint64_t* tmem_empty = bars + 2 * STAGES + 1;
-  uint64_t* wfull = bars + 2 * STAGES + 2;               // [4 warps][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 10);
+  uint64_t* tmem_full = bars + 2 * STAGES;               // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;          // [2]
+  uint64_t* wfull = bars + 2 * STAGES + 4;               // [4 warps]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kb = (p.n_rows + BK - 1) / BK;
+  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0;
+  const int n_clusters = gridDim.x / CS, cid = blockIdx.x / CS;
+  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1);
+  // item i -> class tile ((i / NH) * n_clusters + cid) * CS + crank, e-slice i % NH.  Every CTA of a cluster runs the
+  // same number of items (tiles past n_ct are phantoms: TMA zero-fills their loads and clips their stores).
+  auto tile_of = [&](int i) { return ((i / NH) * n_clusters + cid) * CS + (int)crank; };
+  auto more = [&](int i) { return ((i / NH) * n_clusters + cid) * CS < p.n_ct; };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, kEpiWarps);
-    for (int i = 0; i < 8; ++i) mbar_init(&wfull[i], 1);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
+    for (int i = 0; i < 4; ++i) mbar_init(&wfull[i], 1);
     fence_barrier_init();
   }
   if (warp == 4 && lane == 0) { prefetch_tmap(&tmap_g); prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_wh); prefetch_tmap(&tmap_dw); }
-  if (warp == 5) tmem_alloc<EMB>(tmem_slot);
+  if (warp == 5) tmem_alloc<2 * EN>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  if (CS > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
     if (lane == 0) {
       PipeState ps;
-      for (int ct = blockIdx.x; ct < p.n_ct; ct += gridDim.x) {
+      for (int i = 0; more(i); ++i) {
+        const int ct = tile_of(i), hs = i % NH;
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&empty[ps.stage], ps.phase ^ 1);
           uint8_t* sa = smem + ps.stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
           mbar_arrive_expect_tx(&full[ps.stage], kStageBytes);
-          tma_load_2d(sa, &tmap_g, &full[ps.stage], ct * BM, kb * BK);
-          tma_load_2d(sa + kBoxBytes, &tmap_g, &full[ps.stage], ct * BM + 64, kb * BK);
+          // G scratch blocks (2 ct, kb / 2) and (2 ct + 1, kb / 2): 64 rows x 64 classes each, contiguous 8 KB
+          tma_load_2d(sa, &tmap_g, &full[ps.stage], 0, ((2 * ct) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64);
+          tma_load_2d(sa + kBoxBytes, &tmap_g, &full[ps.stage], 0, ((2 * ct + 1) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64);
+          if (CS == 1) {
 #pragma unroll
-          for (int nb = 0; nb < EMB / 64; ++nb) tma_load_2d(sb + nb * kBoxBytes, &tmap_x, &full[ps.stage], nb * 64, kb * BK);
+            for (int nb = 0; nb < NBOX; ++nb) tma_load_2d(sb + nb * kBoxBytes, &tmap_x, &full[ps.stage], hs * EN + nb * 64, kb * BK);
+          } else {                                // 1/CS of the x_hat boxes, delivered to every CTA of the cluster
+            constexpr int kPer = NBOX / CS;
+#pragma unroll
+            for (int q = 0; q < kPer; ++q) {
+              const int nb = (int)crank * kPer + q;
+              tma_load_2d_mc(sb + nb * kBoxBytes, &tmap_x, &full[ps.stage], hs * EN + nb * 64, kb * BK, kMask);
+            }
+          }
           ps.advance(STAGES);
         }
       }
     }
   } else if (warp == 5) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, UN, true, true);
+      constexpr uint32_t idesc = make_idesc_bf16(BM, EN, true, true);
       PipeState ps;
-      int it = 0;
-      for (int ct = blockIdx.x; ct < p.n_ct; ct += gridDim.x, ++it) {
-        mbar_wait(tmem_empty, (uint32_t)((it & 1) ^ 1));
+      long long t_we = 0, t_wf = 0, t_all = clock64();
+      for (int it = 0; more(it); ++it) {
+        const int acc = it & 1;
+        long long c0 = clock64();
+        mbar_wait(&tmem_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+        t_we += clock64() - c0;
         tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * EN;
         for (int kb = 0; kb < n_kb; ++kb) {
+          c0 = clock64();
           mbar_wait(&full[ps.stage], ps.phase);
+          t_wf += clock64() - c0;
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + ps.stage * kStageBytes);
           const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint64_t da = make_desc_sw128(a_addr + kk * 2048, kBoxBytes, 1024);
-#pragma unroll
-            for (int nh = 0; nh < EMB / UN; ++nh) {
-              const uint64_t db = make_desc_sw128(b_addr + nh * (UN / 64) * kBoxBytes + kk * 2048, kBoxBytes, 1024);
-              umma_bf16_ss(tmem_base + nh * UN, da, db, idesc, (kb | kk) != 0);
-            }
+            const uint64_t db = make_desc_sw128(b_addr + kk * 2048, kBoxBytes, 1024);
+            umma_bf16_ss(d_tmem, da, db, idesc, (kb | kk) != 0);
           }
-          umma_commit(&empty[ps.stage]);
+          if (CS == 1) umma_commit(&empty[ps.stage]); else umma_commit_mc(&empty[ps.stage], kMask);
           ps.advance(STAGES);
         }
-        umma_commit(tmem_full);
+        umma_commit(&tmem_full[acc]);
       }
+      if (p.dbg && blockIdx.x == 0) { p.dbg[0] = t_we; p.dbg[1] = t_wf; p.dbg[2] = clock64() - t_all; }
     }
   } else {
     // ------------------------------------------------------------------ epilogue: warp w owns classes [32w, 32w+32) of the tile
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    uint8_t* wbuf = smem_w + warp * 2 * kWBox;
-    uint8_t* obuf = smem_o + warp * 2 * kOBox;
-    uint64_t* wbar = wfull + warp * 2;
-    constexpr int NKC = EMB / 64;                         // w_hat chunks per pass
-    uint32_t wn = 0;                                      // w_hat chunk counter of this warp (slot = wn & 1, parity = (wn >> 1) & 1)
-    uint32_t on = 0;                                      // staging step counter
-    int it = 0;
-    for (int ct = blockIdx.x; ct < p.n_ct; ct += gridDim.x, ++it) {
+    uint8_t* wbuf = smem_w + warp * kWWarp;
+    uint8_t* obuf = smem_o + warp * kOBox;
+    uint64_t* wbar = &wfull[warp];
+    long long t_wfull = 0, t_ww = 0, t_ep = 0;
+    auto issue_w = [&](int i) {                           // this warp's w_hat rows of item i (lane 0 only)
+      const int cls0 = tile_of(i) * BM + warp * 32, hs = i % NH;
+      mbar_arrive_expect_tx(wbar, kWWarp);
+#pragma unroll
+      for (int nb = 0; nb < NBOX; ++nb) tma_load_2d(wbuf + nb * kWBox, &tmap_wh, wbar, hs * EN + nb * 64, cls0);
+    };
+    if (lane == 0 && more(0)) issue_w(0);
+    for (int it = 0; more(it); ++it) {
+      const int ct = tile_of(it), hs = it % NH;
+      const int acc = it & 1;
       const int cls0 = ct * BM + warp * 32;
       const int cls = cls0 + lane;
       const bool ok = cls < p.n_classes;
       const float inv_n = ok ? p.inv_norm[cls] : 0.f;
-      if (lane == 0) {                                    // prefetch the first w_hat chunk while the MMAs finish
-        mbar_arrive_expect_tx(&wbar[wn & 1], kWBox);
-        tma_load_2d(wbuf + (wn & 1) * kWBox, &tmap_wh, &wbar[wn & 1], 0, cls0);
-      }
-      mbar_wait(tmem_full, (uint32_t)(it & 1));
+      const float nr = ok ? -p.radial[cls] : 0.f;
+      long long c0 = clock64();
+      mbar_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1));
+      t_wfull += clock64() - c0;
+      c0 = clock64();
+      mbar_wait(wbar, (uint32_t)(it & 1));
+      t_ww += clock64() - c0;
+      c0 = clock64();
       tc_fence_after();
-      float radial = 0.f;
 #pragma unroll 1
-      for (int i = 0; i < 2 * NKC; ++i) {
-        const int kc = i % NKC;
-        const bool pass2 = i >= NKC;
-        __syncwarp();                                     // everyone is done with the slot the next load overwrites
-        if (lane == 0 && i + 1 < 2 * NKC) {
-          const uint32_t nx = wn + 1;
-          mbar_arrive_expect_tx(&wbar[nx & 1], kWBox);
-          tma_load_2d(wbuf + (nx & 1) * kWBox, &tmap_wh, &wbar[nx & 1], ((i + 1) % NKC) * 64, cls0);
-        }
-        mbar_wait(&wbar[wn & 1], (wn >> 1) & 1);
-        const uint8_t* wrow = wbuf + (wn & 1) * kWBox;
-        ++wn;
+      for (int nb = 0; nb < NBOX; ++nb) {                 // one 64-e w_hat box = two 32-column groups
+        uint4 wq[8];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {                     // two groups of 32 e per 64-wide chunk
+        for (int q = 0; q < 8; ++q) wq[q] = *reinterpret_cast<const uint4*>(wbuf + nb * kWBox + sw128_off(lane, q));
+        __syncwarp();                                     // the box is dead now: it doubles as the second staging buffer
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
           uint32_t v[32];
-          tmem_ld_x32(tmem_base + lane_base + kc * 64 + h * 32, v);
-          float wf[32];
+          tmem_ld_x32(tmem_base + lane_base + acc * EN + nb * 64 + h * 32, v);
+          tmem_ld_wait();
+          uint8_t* orow = h == 0 ? obuf : wbuf + nb * kWBox;
+          if (h == 0 && lane == 0) tma_store_wait_read<1>();   // the previous store out of obuf has been read
+          __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 w8 = *reinterpret_cast<const uint4*>(wrow + sw128_off(lane, h * 4 + q));
-            // bf16 -> fp32 is a 16-bit shift
-            wf[q * 8 + 0] = __uint_as_float(w8.x << 16); wf[q * 8 + 1] = __uint_as_float(w8.x & 0xffff0000u);
-            wf[q * 8 + 2] = __uint_as_float(w8.y << 16); wf[q * 8 + 3] = __uint_as_float(w8.y & 0xffff0000u);
-            wf[q * 8 + 4] = __uint_as_float(w8.z << 16); wf[q * 8 + 5] = __uint_as_float(w8.z & 0xffff0000u);
-            wf[q * 8 + 6] = __uint_as_float(w8.w << 16); wf[q * 8 + 7] = __uint_as_float(w8.w & 0xffff0000u);
+            const uint4 w8 = wq[h * 4 + q];
+            float4 r0, r1;
+            r0.x = fmaf(__uint_as_float(w8.x << 16), nr, __uint_as_float(v[q * 8 + 0])) * inv_n;
+            r0.y = fmaf(__uint_as_float(w8.x & 0xffff0000u), nr, __uint_as_float(v[q * 8 + 1])) * inv_n;
+            r0.z = fmaf(__uint_as_float(w8.y << 16), nr, __uint_as_float(v[q * 8 + 2])) * inv_n;
+            r0.w = fmaf(__uint_as_float(w8.y & 0xffff0000u), nr, __uint_as_float(v[q * 8 + 3])) * inv_n;
+            r1.x = fmaf(__uint_as_float(w8.z << 16), nr, __uint_as_float(v[q * 8 + 4])) * inv_n;
+            r1.y = fmaf(__uint_as_float(w8.z & 0xffff0000u), nr, __uint_as_float(v[q * 8 + 5])) * inv_n;
+            r1.z = fmaf(__uint_as_float(w8.w << 16), nr, __uint_as_float(v[q * 8 + 6])) * inv_n;
+            r1.w = fmaf(__uint_as_float(w8.w & 0xffff0000u), nr, __uint_as_float(v[q * 8 + 7])) * inv_n;
+            *reinterpret_cast<float4*>(orow + sw128_off(lane, 2 * q)) = r0;
+            *reinterpret_cast<float4*>(orow + sw128_off(lane, 2 * q + 1)) = r1;
           }
-          tmem_ld_wait();
-          if (!pass2) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) radial = fmaf(wf[j], __uint_as_float(v[j]), radial);
-          } else {
-            uint8_t* orow = obuf + (on & 1) * kOBox;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 r;
-              r.x = (__uint_as_float(v[4 * q + 0]) - wf[4 * q + 0] * radial) * inv_n;
-              r.y = (__uint_as_float(v[4 * q + 1]) - wf[4 * q + 1] * radial) * inv_n;
-              r.z = (__uint_as_float(v[4 * q + 2]) - wf[4 * q + 2] * radial) * inv_n;
-              r.w = (__uint_as_float(v[4 * q + 3]) - wf[4 * q + 3] * radial) * inv_n;
-              *reinterpret_cast<float4*>(orow + sw128_off(lane, q)) = r;
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              if (p.accumulate) tma_reduce_add_2d(&tmap_dw, orow, kc * 64 + h * 32, cls0);
-              else tma_store_2d(&tmap_dw, orow, kc * 64 + h * 32, cls0);
-              tma_store_commit();
-              tma_store_wait_read<1>();                   // the other staging buffer is free again
-            }
-            ++on;
-            __syncwarp();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.accumulate) tma_reduce_add_2d(&tmap_dw, orow, hs * EN + nb * 64 + h * 32, cls0);
+            else tma_store_2d(&tmap_dw, orow, hs * EN + nb * 64 + h * 32, cls0);
+            tma_store_commit();
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty);
+      if (lane == 0) {
+        mbar_arrive(&tmem_empty[acc]);
+        tma_store_wait_read<0>();                         // every staging box (incl. the reused w_hat boxes) has been read
+        if (more(it + 1)) issue_w(it + 1);
+      }
+      __syncwarp();
+      t_ep += clock64() - c0;
     }
     if (lane == 0) tma_store_wait_all();
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[3] = t_wfull; p.dbg[4] = t_ww; p.dbg[5] = t_ep; }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 5) tmem_dealloc<EMB>(tmem_base);
+  if (CS > 1) cluster_sync_all(); else __syncthreads();     // peers may still multicast into / arrive on this CTA
+  if (warp == 5) tmem_dealloc<2 * EN>(tmem_base);
 }
 
 }  // namespace tc
@@ -631,7 +722,7 @@ static int launch_logits(const CUtensorMap& tx, const CUtensorMap& tw, const Log
   const size_t smem = (size_t)(p.emb / BK) * kChunkBytes + (size_t)STAGES * BN * BK * 2 + 1024 + 256;
   auto kern = logits_kernel<BN, STAGES, MODE>;
   PFC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kThreads, smem, st>>>(tx, tw, p);
+  kern<<<grid, kLogitsThreads, smem, st>>>(tx, tw, p);
   PFC_LAUNCH_CHECK();
   return 0;
 }
@@ -649,7 +740,7 @@ static int dispatch_logits(const CUtensorMap& tx, const CUtensorMap& tw, const L
 
 static bool tensor_emb_ok(int emb) { return emb == 64 || emb == 128 || emb == 256 || emb == 512; }
 
-int tc_fwd_num_partials(int64_t n_rows, int64_t n_classes) { return fwd_grid(n_rows, n_classes, g_fwd_bn); }
+int tc_fwd_num_partials(int64_t n_rows, int64_t n_classes) { return 2 * fwd_grid(n_rows, n_classes, g_fwd_bn); }
 
 int tc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m,
                  float* part_max, float* part_sum, float* target_logit, cudaStream_t st) {
@@ -664,7 +755,7 @@ int tc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t
   p.n_rb = (int)((n_rows + BM - 1) / BM); p.n_ct = (int)((n_classes + bn - 1) / bn);
   p.s = s; p.m = m; p.part_max = part_max; p.part_sum = part_sum; p.target_logit = target_logit;
   const int grid = fwd_grid(n_rows, n_classes, bn);
-  PFC_CUDA(cudaMemsetAsync(part_sum, 0, sizeof(float) * (size_t)grid * n_rows, st));
+  PFC_CUDA(cudaMemsetAsync(part_sum, 0, sizeof(float) * (size_t)grid * 2 * n_rows, st));
   PFC_CUDA(cudaMemsetAsync(target_logit, 0, sizeof(float) * (size_t)n_rows, st));
   prof_begin(PH_FWD, st);
   int rc = dispatch_logits<MODE_STATS>(tx, tw, p, bn, grid, st);
@@ -677,14 +768,14 @@ struct BwdPlan {
   int64_t chunk;        // classes per chunk (multiple of 256)
   int64_t ldg;          // row pitch of the G scratch (elements)
   int ksplit, n_eh, dx_bn;
-  size_t g_bytes, dxp_bytes;
+  size_t g_bytes, dxp_bytes, radial_bytes;
 };
 
 static BwdPlan make_bwd_plan(int64_t n_rows, int64_t n_classes, int emb) {
   BwdPlan pl{};
   int64_t budget = 256ll << 20;     // bytes of bf16 G scratch per chunk (fewer, larger launches measured faster)
   if (const char* e = getenv("FEDFR_G_CHUNK_MB")) { long v = atol(e); if (v > 0) budget = (int64_t)v << 20; }
-  int64_t chunk = budget / (n_rows * 2);
+  int64_t chunk = budget / (((n_rows + BM - 1) / BM) * BM * 2);
   chunk = chunk / 256 * 256;
   if (chunk < 256) chunk = 256;
   const int64_t c_pad = (n_classes + 255) / 256 * 256;
@@ -701,37 +792,87 @@ static BwdPlan make_bwd_plan(int64_t n_rows, int64_t n_classes, int emb) {
   if (ks > min_kb) ks = min_kb;
   if (ks > 64) ks = 64;
   pl.ksplit = (int)ks;
-  pl.g_bytes = ((size_t)n_rows * pl.ldg * 2 + 1023) / 1024 * 1024;
+  pl.g_bytes = (size_t)n_rb * BM * pl.ldg * 2;          // blocked: [ldg / 64][n_rb][128][64] bf16
   pl.dxp_bytes = ((size_t)pl.ksplit * n_rows * emb * 4 + 1023) / 1024 * 1024;
+  pl.radial_bytes = ((size_t)n_classes * 4 + 1023) / 1024 * 1024;
   return pl;
 }
 
 size_t tc_bwd_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb) {
   BwdPlan pl = make_bwd_plan(n_rows, n_classes, emb);
-  return pl.g_bytes + pl.dxp_bytes + 1024;
+  return pl.g_bytes + pl.dxp_bytes + pl.radial_bytes + 1024;
+}
+
+static int g_radial_mode = 2;
+static long long* g_dbg = nullptr;                   // developer instrumentation buffer (device), see pfc_set_debug_buffer
+static int g_dx_cluster = 2, g_dw_cluster = 2;      // cluster sizes (1, 2 or 4); tuning knobs
+
+template <class Kern, class... Args>
+static int launch_cluster(Kern kern, int grid, int cs, size_t smem, cudaStream_t st, Args... args) {
+  PFC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PFC_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+  PFC_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN, int CS>
+static int launch_dx_cs(const CUtensorMap& tg, const CUtensorMap& tw, const DxParams& p, int grid, cudaStream_t st) {
+  constexpr int STAGES = BN == 256 ? 4 : 6;
+  const size_t smem = (size_t)STAGES * (kChunkBytes + (BN / 64) * kBoxBytes) + 1024 + 256;
+  return launch_cluster(dx_kernel<BN, STAGES, CS>, grid, CS, smem, st, tg, tw, p);
 }
 
 template <int BN>
-static int launch_dx(const CUtensorMap& tg, const CUtensorMap& tw, const DxParams& p, int grid, cudaStream_t st) {
-  constexpr int STAGES = BN == 256 ? 4 : 6;
-  const size_t smem = (size_t)STAGES * (kChunkBytes + (BN / 64) * kBoxBytes) + 1024 + 256;
-  auto kern = dx_kernel<BN, STAGES>;
-  PFC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kThreads, smem, st>>>(tg, tw, p);
-  PFC_LAUNCH_CHECK();
-  return 0;
+static int launch_dx(const CUtensorMap& tg, const CUtensorMap& tw, const DxParams& p, int grid, int cs, cudaStream_t st) {
+  if constexpr (BN == 256) {
+    if (cs == 4) return launch_dx_cs<BN, 4>(tg, tw, p, grid, st);
+    if (cs == 2) return launch_dx_cs<BN, 2>(tg, tw, p, grid, st);
+  } else if constexpr (BN == 128) {
+    if (cs == 2) return launch_dx_cs<BN, 2>(tg, tw, p, grid, st);
+  }
+  return launch_dx_cs<BN, 1>(tg, tw, p, grid, st);
+}
+
+template <int EMB, int CS>
+static int launch_dw_cs(const CUtensorMap& tg, const CUtensorMap& tx, const CUtensorMap& twh, const CUtensorMap& tdw, const DwParams& p, int grid,
+                        cudaStream_t st) {
+  constexpr int EN = EMB < 256 ? EMB : 256;
+  constexpr int kStage = 2 * kBoxBytes + (EN / 64) * kBoxBytes;
+  constexpr int kEpi = 4 * (EN / 64) * 4096 + 4 * 4096;          // per-warp w_hat boxes + staging
+  constexpr int STAGES = (232448 - 1280 - kEpi) / kStage > 8 ? 8 : (232448 - 1280 - kEpi) / kStage;
+  static_assert(STAGES >= 2, "dw kernel smem budget");
+  const size_t smem = (size_t)STAGES * kStage + kEpi + 1024 + 256;
+  return launch_cluster(dw_kernel<EMB, STAGES, CS>, grid, CS, smem, st, tg, tx, twh, tdw, p);
 }
 
 template <int EMB>
-static int launch_dw(const CUtensorMap& tg, const CUtensorMap& tx, const CUtensorMap& twh, const CUtensorMap& tdw, const DwParams& p, int grid,
-                     cudaStream_t st) {
-  constexpr int STAGES = EMB == 512 ? 2 : (EMB == 256 ? 4 : 6);
-  const size_t smem = (size_t)STAGES * (2 * kBoxBytes + (EMB / 64) * kBoxBytes) + 8 * 4096 * 2 + 1024 + 256;
-  auto kern = dw_kernel<EMB, STAGES>;
-  PFC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kThreads, smem, st>>>(tg, tx, twh, tdw, p);
-  PFC_LAUNCH_CHECK();
-  return 0;
+static int launch_dw(const CUtensorMap& tg, const CUtensorMap& tx, const CUtensorMap& twh, const CUtensorMap& tdw, const DwParams& p, int n_ct,
+                     int cs, cudaStream_t st) {
+  if (EMB < 128) cs = 1;
+  if (EMB == 128 && cs > 2) cs = 2;
+  const int sms = sm_count();
+  int n_groups = (n_ct + cs - 1) / cs;
+  int max_clusters = sms / cs;
+  if (cs == 4) max_clusters = max_clusters * 9 / 10;     // GPCs of 18 SMs strand 2 SMs per GPC with 4-CTA clusters
+  const int clusters = n_groups < max_clusters ? n_groups : max_clusters;
+  const int grid = clusters * cs;
+  if constexpr (EMB >= 128) {
+    if (cs == 4) { if constexpr (EMB >= 256) return launch_dw_cs<EMB, 4>(tg, tx, twh, tdw, p, grid, st); }
+    if (cs == 2) return launch_dw_cs<EMB, 2>(tg, tx, twh, tdw, p, grid, st);
+  }
+  return launch_dw_cs<EMB, 1>(tg, tx, twh, tdw, p, grid, st);
 }
 
 int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_max, const float* row_sum,
@@ -740,11 +881,13 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
   PFC_REQUIRE(tensor_emb_ok(emb), PFC_E_SHAPE, "tensor path supports emb in {64,128,256,512}, got %d (use PFC_PATH_CHECK)", emb);
   PFC_REQUIRE(n_rows > 0 && n_classes > 0 && n_classes < (1ll << 30) && n_rows < (1ll << 24), PFC_E_SHAPE, "pfc_bwd: shape out of range");
   const BwdPlan pl = make_bwd_plan(n_rows, n_classes, emb);
-  PFC_REQUIRE(workspace_bytes >= pl.g_bytes + pl.dxp_bytes, PFC_E_WORKSPACE, "pfc_bwd: workspace too small (%zu < %zu)", workspace_bytes,
-              pl.g_bytes + pl.dxp_bytes);
+  PFC_REQUIRE(workspace_bytes >= pl.g_bytes + pl.dxp_bytes + pl.radial_bytes, PFC_E_WORKSPACE, "pfc_bwd: workspace too small (%zu < %zu)",
+              workspace_bytes, pl.g_bytes + pl.dxp_bytes + pl.radial_bytes);
   PFC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, PFC_E_ARG, "pfc_bwd: workspace must be 1024-byte aligned");
   auto* g = reinterpret_cast<__nv_bfloat16*>(workspace);
   float* dx_part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.g_bytes);
+  float* radial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.g_bytes + pl.dxp_bytes);
+  PFC_CUDA(cudaMemsetAsync(radial, 0, (size_t)n_classes * 4, st));
   const auto* wh = reinterpret_cast<const __nv_bfloat16*>(w_hat);
   const int bn = g_fwd_bn;
   const int n_rb = (int)((n_rows + BM - 1) / BM);
@@ -760,42 +903,46 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
     LogitsParams lp{};
     lp.label = label; lp.n_rows = (int)n_rows; lp.n_classes = (int)cc; lp.class_base = (int)c0; lp.emb = emb;
     lp.n_rb = n_rb; lp.n_ct = (int)((cc + bn - 1) / bn); lp.s = s; lp.m = m;
-    lp.row_max = row_max; lp.row_sum = row_sum; lp.g = g; lp.ldg = pl.ldg; lp.g_scale = s * inv_total_batch;
+    lp.row_max = row_max; lp.row_sum = row_sum; lp.g = g; lp.ldg = pl.ldg; lp.g_scale = s * inv_total_batch; lp.radial = radial + c0; lp.radial_mode = g_radial_mode;
     prof_begin(PH_GRAD, st);
     if (int rc = dispatch_logits<MODE_GRAD>(tx_k, tw_k, lp, bn, fwd_grid(n_rows, cc, bn), st)) return rc;
     prof_end(PH_GRAD, st);
     // (2) dx partial slabs
     CUtensorMap tg_k, tw_mn, tg_mn;
-    if (int rc = make_tmap_bf16_2d(&tg_k, g, n_rows, cc, pl.ldg, BM)) return rc;            // A K-major [128 rows x 64 classes]
+    const uint64_t g_rows = (uint64_t)(pl.ldg / 64) * n_rb * BM;                              // rows of the blocked scratch viewed as [g_rows, 64]
+    if (int rc = make_tmap_bf16_2d(&tg_k, g, g_rows, 64, 64, BM)) return rc;                  // A K-major [128 rows x 64 classes] = one block
     if (int rc = make_tmap_bf16_2d(&tw_mn, wh + c0 * emb, cc, emb, emb, 64)) return rc;     // B MN-major boxes [64 classes x 64 e]
     DxParams dp{};
     dp.n_rows = (int)n_rows; dp.n_classes = (int)cc; dp.emb = emb; dp.n_rb = n_rb; dp.n_eh = pl.n_eh; dp.ksplit = pl.ksplit;
     dp.dx_part = dx_part; dp.accumulate = chunk_idx > 0;
-    const int dgrid = n_rb * pl.n_eh * pl.ksplit;
+    int dcs = g_dx_cluster;
+    if (pl.dx_bn < 128) dcs = 1;
+    if (pl.dx_bn == 128 && dcs > 2) dcs = 2;
+    const int n_rbg = (n_rb + dcs - 1) / dcs;
+    const int dgrid = n_rbg * dcs * pl.n_eh * pl.ksplit;
     int rc = 0;
     prof_begin(PH_DX, st);
     switch (pl.dx_bn) {
-      case 256: rc = launch_dx<256>(tg_k, tw_mn, dp, dgrid, st); break;
-      case 128: rc = launch_dx<128>(tg_k, tw_mn, dp, dgrid, st); break;
-      default: rc = launch_dx<64>(tg_k, tw_mn, dp, dgrid, st); break;
+      case 256: rc = launch_dx<256>(tg_k, tw_mn, dp, dgrid, dcs, st); break;
+      case 128: rc = launch_dx<128>(tg_k, tw_mn, dp, dgrid, dcs, st); break;
+      default: rc = launch_dx<64>(tg_k, tw_mn, dp, dgrid, dcs, st); break;
     }
     if (rc) return rc;
     prof_end(PH_DX, st);
     // (3) dw chunk
-    if (int rc2 = make_tmap_bf16_2d(&tg_mn, g, n_rows, cc, pl.ldg, 64)) return rc2;         // A MN-major boxes [64 rows x 64 classes]
+    if (int rc2 = make_tmap_bf16_2d(&tg_mn, g, g_rows, 64, 64, 64)) return rc2;              // A MN-major boxes [64 rows x 64 classes] = half a block
     DwParams wp{};
-    wp.n_rows = (int)n_rows; wp.n_classes = (int)cc; wp.emb = emb; wp.n_ct = (int)((cc + BM - 1) / BM);
-    wp.inv_norm = inv_norm + c0; wp.accumulate = accumulate_dw;
+    wp.n_rows = (int)n_rows; wp.n_classes = (int)cc; wp.emb = emb; wp.n_ct = (int)((cc + BM - 1) / BM); wp.n_rb = n_rb;
+    wp.inv_norm = inv_norm + c0; wp.radial = radial + c0; wp.accumulate = accumulate_dw; wp.dbg = g_dbg;
     CUtensorMap twh_e, tdw_e;
     if (int rc3 = make_tmap_bf16_2d(&twh_e, wh + c0 * emb, cc, emb, emb, 32)) return rc3;      // epilogue: per-warp [32 classes x 64 e]
     if (int rc3 = make_tmap_f32_2d(&tdw_e, dw + c0 * emb, cc, emb, emb, 32)) return rc3;       // epilogue: per-warp [32 classes x 32 e] fp32
-    const int wgrid = wp.n_ct < sm_count() ? wp.n_ct : sm_count();
     prof_begin(PH_DW, st);
     switch (emb) {
-      case 512: rc = launch_dw<512>(tg_mn, tx_mn, twh_e, tdw_e, wp, wgrid, st); break;
-      case 256: rc = launch_dw<256>(tg_mn, tx_mn, twh_e, tdw_e, wp, wgrid, st); break;
-      case 128: rc = launch_dw<128>(tg_mn, tx_mn, twh_e, tdw_e, wp, wgrid, st); break;
-      default: rc = launch_dw<64>(tg_mn, tx_mn, twh_e, tdw_e, wp, wgrid, st); break;
+      case 512: rc = launch_dw<512>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, st); break;
+      case 256: rc = launch_dw<256>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, st); break;
+      case 128: rc = launch_dw<128>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, st); break;
+      default: rc = launch_dw<64>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, st); break;
     }
     if (rc) return rc;
     prof_end(PH_DW, st);
@@ -809,5 +956,11 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
 }
 
 void tc_set_fwd_bn(int bn) { g_fwd_bn = (bn == 256) ? 256 : 128; }
+void tc_set_debug(long long* p) { g_dbg = p; }
+void tc_set_radial_mode(int m) { g_radial_mode = m; }
+void tc_set_clusters(int dx_cs, int dw_cs) {
+  if (dx_cs == 1 || dx_cs == 2 || dx_cs == 4) g_dx_cluster = dx_cs;
+  if (dw_cs == 1 || dw_cs == 2 || dw_cs == 4) g_dw_cluster = dw_cs;
+}
 
 }  // namespace pfc

@@ -171,7 +171,10 @@ def _check_fwd_bwd(path, B, C, E, s=64.0, m=0.4, inspect_g=False):
         ws = ops._ws["bwd"]
         off = (-ws.data_ptr()) % 1024
         ldg = (C + 255) // 256 * 256
-        gbuf = ws[off: off + B * ldg * 2].view(torch.bfloat16).view(B, ldg)[:, :C]
+        n_rb = (B + 127) // 128
+        # blocked scratch: [ldg / 64][n_rb][128 rows][64 classes]
+        gbuf = ws[off: off + n_rb * 128 * ldg * 2].view(torch.bfloat16).view(ldg // 64, n_rb, 128, 64)
+        gbuf = gbuf.permute(1, 2, 0, 3).reshape(n_rb * 128, ldg)[:B, :C]
         print(f"  G: rel err {rel(gbuf, g):.3e}  max|G| ref {float(g.abs().max()):.3e}")
         g_used = gbuf.double()
         print(f"  dx vs G-from-kernel: {rel(dx, g_used @ wr):.3e}")
