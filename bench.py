@@ -163,6 +163,8 @@ def run_ours(args):
     B, C, E, sr = WORKLOADS[args.workload]
     if args.logits_tile:
         N.check(N.lib.pfc_set_logits_tile(args.logits_tile), "pfc_set_logits_tile")
+    if args.logits_pair >= 0:
+        N.lib.pfc_set_logits_pair(args.logits_pair)
     if args.radial_mode != 2:
         N.lib.pfc_set_radial_mode(args.radial_mode)
     if args.dx_cluster or args.dw_cluster:
@@ -292,6 +294,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--logits-tile", type=int, default=0)
     ap.add_argument("--radial-mode", type=int, default=2)
+    ap.add_argument("--logits-pair", type=int, default=-1)
     ap.add_argument("--dx-cluster", type=int, default=0)
     ap.add_argument("--dw-cluster", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

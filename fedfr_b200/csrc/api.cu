@@ -14,6 +14,7 @@ void tc_set_fwd_bn(int bn);
 void tc_set_clusters(int dx_cs, int dw_cs);
 void tc_set_debug(long long* p);
 void tc_set_radial_mode(int m);
+void tc_set_logits_pair(int on);
 int simt_fwd_num_partials(int64_t n_rows, int64_t n_classes);
 int simt_fwd_stats(const float* x, const float* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m,
                    float* part_max, float* part_sum, float* target_logit, cudaStream_t st);
@@ -69,6 +70,11 @@ int pfc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64
 int pfc_set_logits_tile(int bn) {
   PFC_REQUIRE(bn == 128 || bn == 256, PFC_E_ARG, "pfc_set_logits_tile: bn must be 128 or 256");
   tc_set_fwd_bn(bn);
+  return 0;
+}
+
+int pfc_set_logits_pair(int on) {   /* 1 = CTA-pair (cta_group::2) logits kernels (default), 0 = single-CTA */
+  tc_set_logits_pair(on);
   return 0;
 }
 

@@ -351,6 +351,248 @@ __global__ void __launch_bounds__(kLogitsThreads, 1) logits_kernel(const __grid_
 }
 
 // ================================================================================================
+// logits kernel, CTA-pair version (cta_group::2): one tcgen05.mma of M = 256 covers two row blocks.
+//   Each CTA of the pair keeps ITS 128-row x_hat block stationary in smem and receives only ITS 128-class half of every
+//   256-class w_hat tile (16 KB per k-block instead of 32 KB): the L2 -> SM delivery per MMA is halved, which is what
+//   bounds the single-CTA kernel (measured ~42 B/clk/SM).  The leader CTA (even cluster rank) issues the MMAs; its
+//   tcgen05.commit is multicast to the barriers of both CTAs; every CTA runs its own epilogue on its own TMEM rows.
+//   MODE_GRAD stores G through per-warp swizzled staging boxes and TMA stores into the blocked scratch.
+// ================================================================================================
+template <int STAGES, int MODE>
+__global__ void __launch_bounds__(kLogitsThreads, 1) logits2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                                                                    const __grid_constant__ CUtensorMap tmap_g, const LogitsParams p) {
+  constexpr int BN = 256;                 // classes per pair tile
+  constexpr int BH = 128;                 // classes per CTA (its half of the B operand)
+  constexpr int kBStage = BH * BK * 2;    // 16 KB
+  constexpr int kGBox = 32 * 128;         // per-warp G staging: 32 rows x 64 classes bf16
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int n_kb = p.emb / BK;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + n_kb * kChunkBytes;
+  uint8_t* smem_g = smem_b + STAGES * kBStage;                                   // [8 warps] staging (MODE_GRAD only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_g + (MODE == MODE_GRAD ? kLogitsEpiWarps * kGBox : 0));
+  uint64_t* full = bars;                          // [STAGES]  used in the leader only (both CTAs' TMA bytes land here)
+  uint64_t* empty = bars + STAGES;                // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;        // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;   // [2]      used in the leader only (arrivals from both CTAs)
+  uint64_t* a_full = bars + 2 * STAGES + 4;       //          leader only
+  uint64_t* a_empty = bars + 2 * STAGES + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_rp = (p.n_rb + 1) >> 1;                                 // row-block pairs
+  const int64_t n_items = (int64_t)n_rp * p.n_ct;
+  const int64_t t0 = n_items * pair / n_pairs, t1 = n_items * (pair + 1) / n_pairs;
+  constexpr int kProducerWarp = kLogitsEpiWarps, kMmaWarp = kLogitsEpiWarps + 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kLogitsEpiWarps); }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == kProducerWarp && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); if (MODE == MODE_GRAD) prefetch_tmap(&tmap_g); }
+  if (warp == kMmaWarp) tmem_alloc_2cta<2 * BN>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs; bytes are credited to the leader)
+    if (lane == 0) {
+      PipeState ps;
+      int cur_rp = -1, a_loads = 0;
+      const uint32_t a_full_leader = mapa_u32(smem_u32(a_full), 0);
+      for (int64_t t = t0; t < t1; ++t) {
+        const int rp = (int)(t / p.n_ct), ct = (int)(t % p.n_ct);
+        if (rp != cur_rp) {
+          if (a_loads > 0) mbar_wait(a_empty, (a_loads - 1) & 1);
+          if (leader) mbar_arrive_expect_tx(a_full, 2 * n_kb * kChunkBytes);
+          const int rb = rp * 2 + (int)crank;
+          for (int kb = 0; kb < n_kb; ++kb) tma_load_2d_2cta(smem_a + kb * kChunkBytes, &tmap_x, a_full_leader, kb * BK, rb * BM);
+          cur_rp = rp;
+          ++a_loads;
+        }
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&empty[ps.stage], ps.phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full[ps.stage], 2 * kBStage);
+          tma_load_2d_2cta(smem_b + ps.stage * kBStage, &tmap_w, mapa_u32(smem_u32(&full[ps.stage]), 0), kb * BK, ct * BN + (int)crank * BH);
+          ps.advance(STAGES);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, false, false);
+      PipeState ps;
+      int cur_rp = -1, a_uses = 0;
+      int64_t it = 0;
+      for (int64_t t = t0; t < t1; ++t, ++it) {
+        const int rp = (int)(t / p.n_ct);
+        if (rp != cur_rp) {
+          mbar_wait(a_full, a_uses & 1);
+          ++a_uses;
+          cur_rp = rp;
+        }
+        const int acc = (int)(it & 1);
+        mbar_wait(&tmem_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&full[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + kb * kChunkBytes);
+          const uint32_t b_addr = smem_u32(smem_b + ps.stage * kBStage);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t da = make_desc_sw128(a_addr + kk * 32, 0, 1024);
+            const uint64_t db = make_desc_sw128(b_addr + kk * 32, 0, 1024);
+            umma_bf16_ss_2cta(d_tmem, da, db, idesc, (kb | kk) != 0);
+          }
+          umma_commit_2cta(&empty[ps.stage], 3);
+          ps.advance(STAGES);
+        }
+        umma_commit_2cta(&tmem_full[acc], 3);
+        const bool last_of_rp = (t + 1 == t1) || ((int)((t + 1) / p.n_ct) != rp);
+        if (last_of_rp) umma_commit_2cta(a_empty, 3);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps per CTA), thread = row of THIS CTA's block
+    const int quad = warp & 3, chalf = warp >> 2;
+    constexpr int CH = BN / 2;
+    const float s2 = p.s * kLog2e, ms2 = p.m * p.s * kLog2e;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    constexpr int kNoLabel = -(1 << 30);
+    uint8_t* gbuf = smem_g + warp * kGBox;
+    int cur_rp = -1, rb = 0;
+    int row = 0, my_label = kNoLabel;
+    bool row_ok = false;
+    float run_m = -INFINITY, run_l = 0.f;
+    float M2 = 0.f, rS = 0.f;
+    int64_t it = 0;
+    for (int64_t t = t0; t < t1; ++t, ++it) {
+      const int rp = (int)(t / p.n_ct), ct = (int)(t % p.n_ct);
+      if (rp != cur_rp) {
+        if (MODE == MODE_STATS && cur_rp >= 0 && row_ok) {
+          p.part_max[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = run_m * kLn2;
+          p.part_sum[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = run_l;
+        }
+        cur_rp = rp;
+        rb = rp * 2 + (int)crank;
+        row = rb * BM + quad * 32 + lane;
+        row_ok = row < p.n_rows;
+        my_label = kNoLabel;
+        if (row_ok) {
+          const int64_t y = p.label[row];
+          if (y >= 0) my_label = (int)(y - p.class_base);
+        }
+        run_m = -INFINITY; run_l = 0.f;
+        M2 = 0.f; rS = 0.f;
+        if (MODE == MODE_GRAD && row_ok) { M2 = p.row_max[row] * kLog2e; rS = 1.0f / p.row_sum[row]; }
+      }
+      const int acc = (int)(it & 1);
+      mbar_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const int col0 = ct * BN;
+      const bool tile_has_oob = col0 + BN > p.n_classes;
+#pragma unroll 1
+      for (int c = chalf * CH; c < (chalf + 1) * CH; c += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_base + lane_base + acc * BN + c, v);
+        tmem_ld_wait();
+        const int cb = col0 + c;
+        float z[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) z[j] = __uint_as_float(v[j]) * s2;
+        const int hit = my_label - cb;
+        if (hit >= 0 && hit < 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j == hit) {
+            z[j] -= ms2;
+            if (MODE == MODE_STATS) p.target_logit[row] = p.s * (__uint_as_float(v[j]) - p.m);
+          }
+        }
+        if (MODE == MODE_STATS) {
+          if (tile_has_oob) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (cb + j >= p.n_classes) z[j] = -INFINITY;
+          }
+          float cm = z[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) cm = fmaxf(cm, z[j]);
+          if (cm > -INFINITY) {
+            const float nm = fmaxf(run_m, cm);
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) { s0 += fast_exp2(z[j] - nm); s1 += fast_exp2(z[j + 1] - nm); }
+            run_l = run_l * fast_exp2(run_m - nm) + (s0 + s1);
+            run_m = nm;
+          }
+        } else {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float g0 = fast_exp2(z[j] - M2) * rS, g1 = fast_exp2(z[j + 1] - M2) * rS;
+            if (j == hit) g0 -= 1.0f;
+            if (j + 1 == hit) g1 -= 1.0f;
+            pk[j >> 1] = pack_bf16x2(g0 * p.g_scale, g1 * p.g_scale);
+          }
+          // G -> swizzled staging box [32 rows x 64 classes]; one TMA store per 64 classes into the blocked scratch
+          const int half = (c >> 5) & 1;
+          if (half == 0) {
+            if (lane == 0) tma_store_wait_read<0>();      // the previous store out of this warp's box has been read
+            __syncwarp();
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(gbuf + sw128_off(lane, half * 4 + q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          if (half == 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && cb < p.ldg && rb < p.n_rb) {      // (a phantom row block of an odd pair has no scratch)
+              tma_store_2d(&tmap_g, gbuf, 0, ((cb >> 6) * p.n_rb + rb) * BM + quad * 32);
+              tma_store_commit();
+            }
+          }
+          if (p.radial_mode) {
+            float h[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              h[j] = __uint_as_float(pk[j >> 1] << 16) * __uint_as_float(v[j]);
+              h[j + 1] = __uint_as_float(pk[j >> 1] & 0xffff0000u) * __uint_as_float(v[j + 1]);
+            }
+            const float cs = warp_colsum32(h, lane);
+            if (p.radial_mode > 1 && cb + lane < p.n_classes) atomicAdd(p.radial + cb + lane, cs);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {                                     // the accumulator lives in both CTAs; the leader's MMA warp waits for all 16 warps
+        if (leader) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_cluster_addr(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+      }
+    }
+    if (MODE == MODE_STATS && cur_rp >= 0 && row_ok) {
+      p.part_max[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = run_m * kLn2;
+      p.part_sum[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = run_l;
+    }
+    if (MODE == MODE_GRAD && lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == kMmaWarp) tmem_dealloc_2cta<2 * BN>(tmem_base);
+}
+
+// ================================================================================================
 // dx kernel: D[128 rows x BN e] = sum over a class slice of G[rows, classes] * w_hat[classes, e]
 //   A = G (K-major, K = classes), B = w_hat (MN-major: N = e contiguous, K = classes)
 // ================================================================================================
@@ -727,6 +969,38 @@ static int launch_logits(const CUtensorMap& tx, const CUtensorMap& tw, const Log
   return 0;
 }
 
+static int g_logits_pair = 1;      // 1: CTA-pair (cta_group::2) logits kernels, 0: single-CTA kernels
+
+template <int STAGES, int MODE>
+static int launch_logits2(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tg, const LogitsParams& p, int grid, cudaStream_t st) {
+  const size_t smem = (size_t)(p.emb / BK) * kChunkBytes + (size_t)STAGES * 128 * BK * 2 + (MODE == MODE_GRAD ? kLogitsEpiWarps * 4096 : 0) + 1024 + 256;
+  auto kern = logits2_kernel<STAGES, MODE>;
+  PFC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kLogitsThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PFC_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tw, tg, p));
+  PFC_LAUNCH_CHECK();
+  return 0;
+}
+
+// grid of the pair kernels: one pair per two SMs, never more pairs than work items
+static int pair_grid(int64_t n_rows, int64_t n_classes) {
+  const int64_t n_rp = ((n_rows + BM - 1) / BM + 1) / 2, n_ct = (n_classes + 255) / 256;
+  const int64_t items = n_rp * n_ct;
+  const int64_t pairs = sm_count() / 2;
+  return (int)(2 * (items < pairs ? items : pairs));
+}
+
 template <int MODE>
 static int dispatch_logits(const CUtensorMap& tx, const CUtensorMap& tw, const LogitsParams& p, int bn, int grid, cudaStream_t st) {
   const int n_kb = p.emb / BK;
@@ -740,25 +1014,27 @@ static int dispatch_logits(const CUtensorMap& tx, const CUtensorMap& tw, const L
 
 static bool tensor_emb_ok(int emb) { return emb == 64 || emb == 128 || emb == 256 || emb == 512; }
 
-int tc_fwd_num_partials(int64_t n_rows, int64_t n_classes) { return 2 * fwd_grid(n_rows, n_classes, g_fwd_bn); }
+int tc_fwd_num_partials(int64_t n_rows, int64_t n_classes) {
+  return 2 * (g_logits_pair ? pair_grid(n_rows, n_classes) : fwd_grid(n_rows, n_classes, g_fwd_bn));
+}
 
 int tc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m,
                  float* part_max, float* part_sum, float* target_logit, cudaStream_t st) {
   PFC_REQUIRE(tensor_emb_ok(emb), PFC_E_SHAPE, "tensor path supports emb in {64,128,256,512}, got %d (use PFC_PATH_CHECK)", emb);
   PFC_REQUIRE(n_rows > 0 && n_classes > 0 && n_classes < (1ll << 30) && n_rows < (1ll << 24), PFC_E_SHAPE, "pfc_fwd_stats: shape out of range");
-  const int bn = g_fwd_bn;
+  const int bn = g_logits_pair ? 256 : g_fwd_bn;
   CUtensorMap tx, tw;
   if (int rc = make_tmap_bf16_2d(&tx, x, n_rows, emb, emb, BM)) return rc;
-  if (int rc = make_tmap_bf16_2d(&tw, w_hat, n_classes, emb, emb, bn)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tw, w_hat, n_classes, emb, emb, g_logits_pair ? 128 : bn)) return rc;
   LogitsParams p{};
   p.label = label; p.n_rows = (int)n_rows; p.n_classes = (int)n_classes; p.class_base = 0; p.emb = emb;
   p.n_rb = (int)((n_rows + BM - 1) / BM); p.n_ct = (int)((n_classes + bn - 1) / bn);
   p.s = s; p.m = m; p.part_max = part_max; p.part_sum = part_sum; p.target_logit = target_logit;
-  const int grid = fwd_grid(n_rows, n_classes, bn);
+  const int grid = g_logits_pair ? pair_grid(n_rows, n_classes) : fwd_grid(n_rows, n_classes, bn);
   PFC_CUDA(cudaMemsetAsync(part_sum, 0, sizeof(float) * (size_t)grid * 2 * n_rows, st));
   PFC_CUDA(cudaMemsetAsync(target_logit, 0, sizeof(float) * (size_t)n_rows, st));
   prof_begin(PH_FWD, st);
-  int rc = dispatch_logits<MODE_STATS>(tx, tw, p, bn, grid, st);
+  int rc = g_logits_pair ? launch_logits2<4, MODE_STATS>(tx, tw, tw, p, grid, st) : dispatch_logits<MODE_STATS>(tx, tw, p, bn, grid, st);
   prof_end(PH_FWD, st);
   return rc;
 }
@@ -889,7 +1165,7 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
   float* radial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.g_bytes + pl.dxp_bytes);
   PFC_CUDA(cudaMemsetAsync(radial, 0, (size_t)n_classes * 4, st));
   const auto* wh = reinterpret_cast<const __nv_bfloat16*>(w_hat);
-  const int bn = g_fwd_bn;
+  const int bn = g_logits_pair ? 256 : g_fwd_bn;
   const int n_rb = (int)((n_rows + BM - 1) / BM);
   CUtensorMap tx_k, tx_mn;
   if (int rc = make_tmap_bf16_2d(&tx_k, x, n_rows, emb, emb, BM)) return rc;       // logits: A K-major [128 x 64]
@@ -899,17 +1175,23 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
     const int64_t cc = (n_classes - c0 < pl.chunk) ? n_classes - c0 : pl.chunk;
     // (1) G chunk
     CUtensorMap tw_k;
-    if (int rc = make_tmap_bf16_2d(&tw_k, wh + c0 * emb, cc, emb, emb, bn)) return rc;
+    if (int rc = make_tmap_bf16_2d(&tw_k, wh + c0 * emb, cc, emb, emb, g_logits_pair ? 128 : bn)) return rc;
     LogitsParams lp{};
     lp.label = label; lp.n_rows = (int)n_rows; lp.n_classes = (int)cc; lp.class_base = (int)c0; lp.emb = emb;
     lp.n_rb = n_rb; lp.n_ct = (int)((cc + bn - 1) / bn); lp.s = s; lp.m = m;
     lp.row_max = row_max; lp.row_sum = row_sum; lp.g = g; lp.ldg = pl.ldg; lp.g_scale = s * inv_total_batch; lp.radial = radial + c0; lp.radial_mode = g_radial_mode;
+    const uint64_t g_rows = (uint64_t)(pl.ldg / 64) * n_rb * BM;                              // rows of the blocked scratch viewed as [g_rows, 64]
     prof_begin(PH_GRAD, st);
-    if (int rc = dispatch_logits<MODE_GRAD>(tx_k, tw_k, lp, bn, fwd_grid(n_rows, cc, bn), st)) return rc;
+    if (g_logits_pair) {
+      CUtensorMap tg_st;
+      if (int rc = make_tmap_bf16_2d(&tg_st, g, g_rows, 64, 64, 32)) return rc;                // epilogue store boxes [32 rows x 64 classes]
+      if (int rc = launch_logits2<4, MODE_GRAD>(tx_k, tw_k, tg_st, lp, pair_grid(n_rows, cc), st)) return rc;
+    } else {
+      if (int rc = dispatch_logits<MODE_GRAD>(tx_k, tw_k, lp, bn, fwd_grid(n_rows, cc, bn), st)) return rc;
+    }
     prof_end(PH_GRAD, st);
     // (2) dx partial slabs
     CUtensorMap tg_k, tw_mn, tg_mn;
-    const uint64_t g_rows = (uint64_t)(pl.ldg / 64) * n_rb * BM;                              // rows of the blocked scratch viewed as [g_rows, 64]
     if (int rc = make_tmap_bf16_2d(&tg_k, g, g_rows, 64, 64, BM)) return rc;                  // A K-major [128 rows x 64 classes] = one block
     if (int rc = make_tmap_bf16_2d(&tw_mn, wh + c0 * emb, cc, emb, emb, 64)) return rc;     // B MN-major boxes [64 classes x 64 e]
     DxParams dp{};
@@ -958,6 +1240,7 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
 void tc_set_fwd_bn(int bn) { g_fwd_bn = (bn == 256) ? 256 : 128; }
 void tc_set_debug(long long* p) { g_dbg = p; }
 void tc_set_radial_mode(int m) { g_radial_mode = m; }
+void tc_set_logits_pair(int on) { g_logits_pair = on ? 1 : 0; }
 void tc_set_clusters(int dx_cs, int dw_cs) {
   if (dx_cs == 1 || dx_cs == 2 || dx_cs == 4) g_dx_cluster = dx_cs;
   if (dw_cs == 1 || dw_cs == 2 || dw_cs == 4) g_dw_cluster = dw_cs;
