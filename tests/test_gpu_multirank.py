@@ -1,0 +1,77 @@
+"""2-rank NCCL run of the CUDA path against the goldens the unmodified reference produced on 2 gloo ranks
+(class sharding with a ragged split, gathered labels/features, stats exchange, reduce-scatter, x W).
+Needs >= 2 GPUs; skipped otherwise."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-7 * b.size ** 0.5))
+
+
+def _worker(rank, world, name, check_mode, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import fedfr_b200
+        from golden_util import Case
+        case = Case(name)
+        cfg = case.cfg
+        dev = torch.device("cuda", rank)
+        head = fedfr_b200.PartialFC(rank, rank, world, cfg["batch"], False, fedfr_b200.CosFace(s=cfg["s"], m=cfg["m"]), cfg["num_classes"],
+                                    sample_rate=cfg["sample_rate"], embedding_size=cfg["emb"], prefix="/tmp", check_mode=check_mode)
+        head.weight.copy_(case.weights[rank].to(dev))
+        head.weight_mom.zero_()
+        opt = torch.optim.SGD([{"params": head.parameters()}], lr=cfg["lr"], momentum=0.9, weight_decay=5e-4)
+        errs = {}
+        real_rand = torch.rand
+        for step in range(cfg["steps"]):
+            if case.has(rank, step, "perm"):
+                perm = torch.from_numpy(case.get(rank, step, "perm")).to(dev)
+                torch.rand = lambda *a, **k: perm.clone()
+            x_grad, loss = head.forward_backward(case.labels[rank].to(dev), case.features[rank].to(dev), opt)
+            torch.rand = real_rand
+            if case.has(rank, step, "index"):
+                assert np.array_equal(head.index.cpu().numpy(), case.get(rank, step, "index"))
+            errs[f"loss{step}"] = abs(float(loss) - float(case.get(rank, step, "loss"))) / max(1.0, abs(float(case.get(rank, step, "loss"))))
+            errs[f"dx{step}"] = _rel(x_grad.cpu().numpy(), case.get(rank, step, "x_grad"))
+            errs[f"dw{step}"] = _rel(head.sub_weight.grad.cpu().numpy(), case.get(rank, step, "dw"))
+            opt.step()
+            head.update()
+            opt.zero_grad()
+            head.weight.copy_(torch.from_numpy(case.get(rank, step, "weight_after")).to(dev))
+            head.weight_mom.copy_(torch.from_numpy(case.get(rank, step, "mom_after")).to(dev))
+        ret[rank] = errs
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("check_mode", [True, False])
+@pytest.mark.parametrize("name,port", [("w2_sr1_ragged", 29741), ("w2_sr03", 29742)])
+def test_two_gpu_matches_reference(name, port, check_mode):
+    import __graft_entry__ as g
+    g.build()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, name, check_mode, port + (10 if check_mode else 0), ret), nprocs=2, join=True)
+    tol = 1e-4 if check_mode else 1e-2
+    for r in (0, 1):
+        for k, v in ret[r].items():
+            assert v < tol, (r, k, v, dict(ret[r]))
