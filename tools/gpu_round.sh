@@ -1,0 +1,18 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, bench line, ncu launch list, ncu full captures of the GEMM-shaped kernels.
+# usage: tools/gpu_round.sh <tag> [skip-tests]
+TAG=${1:-rXX}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $OUT/gpu.txt 2>&1
+if [ "$2" != "skip-tests" ]; then
+  timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log
+  tail -5 $OUT/pytest_gpu.log
+fi
+timeout 600 python bench.py --steps 20 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
+cat $OUT/bench.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120 --csv --log-file $OUT/launches.csv \
+  python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/launches_bench.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'logits2_kernel|dx_kernel|dw_kernel|normalize' -s 12 -c 5 \
+  -o $OUT/prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/prof_bench.log 2>&1
+ls -la $OUT
