@@ -167,6 +167,13 @@ def run_ours(args):
         N.lib.pfc_set_logits_pair(args.logits_pair)
     if args.radial_mode != 2:
         N.lib.pfc_set_radial_mode(args.radial_mode)
+    if args.graph >= 0:
+        N.lib.pfc_set_graph(args.graph)
+    if args.chunk_mb:
+        N.lib.pfc_set_chunk_mb(args.chunk_mb)
+    if args.pipe:
+        v = [int(t) for t in args.pipe.split(",")] + [0, 0, 0, 0]
+        N.lib.pfc_set_pipeline(v[0], v[1], v[2], v[3], v[4])
     if args.dx_cluster or args.dw_cluster:
         N.lib.pfc_set_clusters(args.dx_cluster, args.dw_cluster)
     torch.manual_seed(100 + rank)
@@ -298,6 +305,9 @@ def main():
     ap.add_argument("--dx-cluster", type=int, default=0)
     ap.add_argument("--dw-cluster", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=-1, help="1/0: replay the backward as a cached CUDA graph (library default: 1)")
+    ap.add_argument("--pipe", default="", help="backward chain pipeline: 'on,smG,smDx,smDw,ring' (e.g. 1,56,32,60,3) or 0")
+    ap.add_argument("--chunk-mb", type=int, default=0, help="bf16 G scratch per backward chunk in MiB (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

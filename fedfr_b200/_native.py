@@ -62,6 +62,11 @@ lib.pfc_set_clusters.restype = _i32
 lib.pfc_set_clusters.argtypes = [_i32, _i32]
 lib.pfc_set_logits_tile.restype = _i32
 lib.pfc_set_logits_tile.argtypes = [_i32]
+lib.pfc_set_pipeline.restype = _i32
+lib.pfc_set_pipeline.argtypes = [_i32, _i32, _i32, _i32, _i32]
+for _knob in ("pfc_set_graph", "pfc_set_chunk_mb", "pfc_set_logits_pair", "pfc_set_radial_mode"):
+    getattr(lib, _knob).restype = _i32
+    getattr(lib, _knob).argtypes = [_i32]
 
 
 def check(rc: int, what: str) -> None:

@@ -15,6 +15,9 @@ void tc_set_clusters(int dx_cs, int dw_cs);
 void tc_set_debug(long long* p);
 void tc_set_radial_mode(int m);
 void tc_set_logits_pair(int on);
+void tc_set_graph(int on);
+void tc_set_chunk_mb(int mb);
+void tc_set_pipeline(int on, int sm_g, int sm_dx, int sm_dw, int ring);
 int simt_fwd_num_partials(int64_t n_rows, int64_t n_classes);
 int simt_fwd_stats(const float* x, const float* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m,
                    float* part_max, float* part_sum, float* target_logit, cudaStream_t st);
@@ -85,6 +88,21 @@ int pfc_set_radial_mode(int m) {   /* timing experiment only: anything but 2 giv
 
 int pfc_set_debug_buffer(void* dev_ptr) {
   tc_set_debug(reinterpret_cast<long long*>(dev_ptr));
+  return 0;
+}
+
+int pfc_set_graph(int on) {   /* 1 = replay the backward as a cached CUDA graph (default), 0 = launch kernel by kernel */
+  tc_set_graph(on);
+  return 0;
+}
+
+int pfc_set_pipeline(int on, int sm_g, int sm_dx, int sm_dw, int ring) {   /* concurrent G / dx / dw chains; SMs per chain (0 = keep) */
+  tc_set_pipeline(on, sm_g, sm_dx, sm_dw, ring);
+  return 0;
+}
+
+int pfc_set_chunk_mb(int mb) {   /* bf16 G scratch per backward chunk in MiB (0 = default) */
+  tc_set_chunk_mb(mb);
   return 0;
 }
 

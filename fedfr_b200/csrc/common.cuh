@@ -16,6 +16,7 @@ extern long long g_launch_count;      // kernels launched by this library (bench
 enum { PH_NORMALIZE = 0, PH_FWD = 1, PH_GRAD = 2, PH_DX = 3, PH_DW = 4, PH_COUNT = 5 };
 void prof_begin(int phase, cudaStream_t st);
 void prof_end(int phase, cudaStream_t st);
+bool prof_enabled();
 
 #define PFC_REQUIRE(cond, code, ...)                \
   do {                                              \

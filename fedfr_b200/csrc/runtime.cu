@@ -13,6 +13,7 @@ struct ProfSpan { cudaEvent_t a, b; int phase; };
 static ProfSpan g_spans[4096];
 static int g_n_spans = 0;
 static cudaEvent_t g_open[PH_COUNT];
+bool prof_enabled() { return g_prof_on != 0; }
 void prof_begin(int phase, cudaStream_t st) {
   if (!g_prof_on || g_n_spans >= 4096) return;
   cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); g_open[phase] = e;

@@ -10,6 +10,8 @@
 // 128-byte-swizzled operand tiles, mbarrier pipelines (smem full/empty, TMEM full/empty).
 #include "tc_common.cuh"
 #include <mutex>
+#include <string.h>
+#include <vector>
 
 namespace pfc {
 
@@ -1040,35 +1042,72 @@ int tc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t
 }
 
 // ---- backward chunking -------------------------------------------------------------------------
+// The class axis is cut into chunks.  Per chunk: G kernel (recompute logits -> G scratch), then dx and dw consume the
+// scratch.  With more than two chunks the three kernels run as three concurrent chains on disjoint SM subsets
+// (G on the caller's stream, dx and dw on side streams, a ring of G buffers in between): the G kernel is bound by its
+// epilogue issue slots, dx by L2 delivery and dw by the HBM write of dw, so they overlap well, and a chunk is consumed
+// while it is still L2-resident.
 struct BwdPlan {
   int64_t chunk;        // classes per chunk (multiple of 256)
   int64_t ldg;          // row pitch of the G scratch (elements)
+  int n_chunks, ring;   // ring = G buffers
+  bool pipelined;
+  int sm_g, sm_dx, sm_dw;   // SMs (CTAs) per chain
   int ksplit, n_eh, dx_bn;
-  size_t g_bytes, dxp_bytes, radial_bytes;
+  size_t g_bytes, g_buf_bytes, dxp_bytes, radial_bytes;
 };
+
+static int64_t g_chunk_budget_mb;                   // 0 = default
+static int g_pipe = 0;                              // 1 = concurrent chains (see pfc_set_pipeline)
+static int g_split[3] = {56, 32, 60};               // SMs for the G / dx / dw chains in pipelined mode
+static int g_ring = 3;
 
 static BwdPlan make_bwd_plan(int64_t n_rows, int64_t n_classes, int emb) {
   BwdPlan pl{};
-  int64_t budget = 256ll << 20;     // bytes of bf16 G scratch per chunk (fewer, larger launches measured faster)
-  if (const char* e = getenv("FEDFR_G_CHUNK_MB")) { long v = atol(e); if (v > 0) budget = (int64_t)v << 20; }
-  int64_t chunk = budget / (((n_rows + BM - 1) / BM) * BM * 2);
-  chunk = chunk / 256 * 256;
-  if (chunk < 256) chunk = 256;
+  const int64_t n_rb = (n_rows + BM - 1) / BM;
   const int64_t c_pad = (n_classes + 255) / 256 * 256;
-  if (chunk > c_pad) chunk = c_pad;
+  const int64_t row_bytes = n_rb * BM * 2;           // bytes of G scratch per class
+  int64_t budget_seq = 256ll << 20, budget_pipe = 32ll << 20;
+  if (const char* e = getenv("FEDFR_G_CHUNK_MB")) { long v = atol(e); if (v > 0) budget_seq = budget_pipe = (int64_t)v << 20; }
+  if (g_chunk_budget_mb > 0) budget_seq = budget_pipe = g_chunk_budget_mb << 20;
+  auto chunk_for = [&](int64_t budget) {
+    int64_t c = budget / row_bytes / 256 * 256;
+    if (c < 256) c = 256;
+    if (c > c_pad) c = c_pad;
+    return c;
+  };
+  int64_t chunk = chunk_for(budget_pipe);
+  int64_t n_chunks = (n_classes + chunk - 1) / chunk;
+  // ring == 1: G runs alone (it may use every SM), then dx and dw of the chunk run side by side on disjoint SMs
+  const bool fits = g_ring == 1 ? (g_split[1] + g_split[2] <= sm_count() && g_split[0] <= sm_count())
+                                : (g_split[0] + g_split[1] + g_split[2] <= sm_count());
+  pl.pipelined = g_pipe && fits && (g_ring == 1 || n_chunks >= 4);
+  if (pl.pipelined && g_ring == 1) budget_pipe = budget_seq;
+  chunk = chunk_for(budget_pipe);
+  n_chunks = (n_classes + chunk - 1) / chunk;
+  if (!pl.pipelined) {
+    chunk = chunk_for(budget_seq);
+    n_chunks = (n_classes + chunk - 1) / chunk;
+  }
   pl.chunk = chunk;
   pl.ldg = chunk;
+  pl.n_chunks = (int)n_chunks;
+  pl.ring = pl.pipelined ? g_ring : 1;
   pl.dx_bn = emb < 256 ? emb : 256;
   pl.n_eh = emb / pl.dx_bn;
-  const int64_t n_rb = (n_rows + BM - 1) / BM;
+  const int sms = sm_count();
+  pl.sm_g = pl.pipelined ? g_split[0] : sms;
+  pl.sm_dx = pl.pipelined ? g_split[1] : sms;
+  pl.sm_dw = pl.pipelined ? g_split[2] : sms;
   int64_t units = n_rb * pl.n_eh;
-  int64_t ks = sm_count() / units;
+  int64_t ks = pl.sm_dx / units;
   if (ks < 1) ks = 1;
   const int64_t min_kb = ((chunk < n_classes ? chunk : n_classes) + BK - 1) / BK;
   if (ks > min_kb) ks = min_kb;
   if (ks > 64) ks = 64;
   pl.ksplit = (int)ks;
-  pl.g_bytes = (size_t)n_rb * BM * pl.ldg * 2;          // blocked: [ldg / 64][n_rb][128][64] bf16
+  pl.g_buf_bytes = (size_t)n_rb * BM * pl.ldg * 2;      // blocked: [ldg / 64][n_rb][128][64] bf16
+  pl.g_bytes = pl.g_buf_bytes * pl.ring;
   pl.dxp_bytes = ((size_t)pl.ksplit * n_rows * emb * 4 + 1023) / 1024 * 1024;
   pl.radial_bytes = ((size_t)n_classes * 4 + 1023) / 1024 * 1024;
   return pl;
@@ -1135,13 +1174,13 @@ static int launch_dw_cs(const CUtensorMap& tg, const CUtensorMap& tx, const CUte
 
 template <int EMB>
 static int launch_dw(const CUtensorMap& tg, const CUtensorMap& tx, const CUtensorMap& twh, const CUtensorMap& tdw, const DwParams& p, int n_ct,
-                     int cs, cudaStream_t st) {
+                     int cs, int sms, cudaStream_t st) {
   if (EMB < 128) cs = 1;
   if (EMB == 128 && cs > 2) cs = 2;
-  const int sms = sm_count();
   int n_groups = (n_ct + cs - 1) / cs;
   int max_clusters = sms / cs;
   if (cs == 4) max_clusters = max_clusters * 9 / 10;     // GPCs of 18 SMs strand 2 SMs per GPC with 4-CTA clusters
+  if (max_clusters < 1) max_clusters = 1;
   const int clusters = n_groups < max_clusters ? n_groups : max_clusters;
   const int grid = clusters * cs;
   if constexpr (EMB >= 128) {
@@ -1151,29 +1190,76 @@ static int launch_dw(const CUtensorMap& tg, const CUtensorMap& tx, const CUtenso
   return launch_dw_cs<EMB, 1>(tg, tx, twh, tdw, p, grid, st);
 }
 
-int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_max, const float* row_sum,
-           int64_t n_rows, int64_t n_classes, int emb, float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
-           void* workspace, size_t workspace_bytes, cudaStream_t st) {
+// side streams of the pipelined backward (per device)
+static cudaStream_t g_side_stream[64][2];
+static int side_streams(cudaStream_t* sx, cudaStream_t* sw) {
+  int dev = 0;
+  PFC_CUDA(cudaGetDevice(&dev));
+  PFC_REQUIRE(dev >= 0 && dev < 64, PFC_E_ARG, "device index out of range");
+  for (int i = 0; i < 2; ++i)
+    if (!g_side_stream[dev][i]) PFC_CUDA(cudaStreamCreateWithFlags(&g_side_stream[dev][i], cudaStreamNonBlocking));
+  *sx = g_side_stream[dev][0];
+  *sw = g_side_stream[dev][1];
+  return 0;
+}
+
+struct EventPool {          // edge markers of one enqueue; destroying a recorded event is deferred by the runtime
+  std::vector<cudaEvent_t> ev;
+  ~EventPool() { for (auto e : ev) cudaEventDestroy(e); }
+  cudaEvent_t get() {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ev.push_back(e);
+    return e;
+  }
+};
+#define PFC_EDGE(from_stream, to_stream)                                  \
+  do {                                                                    \
+    cudaEvent_t edge_ev = pool.get();                                     \
+    PFC_REQUIRE(edge_ev != nullptr, PFC_E_ARG, "cudaEventCreate failed"); \
+    PFC_CUDA(cudaEventRecord(edge_ev, (from_stream)));                    \
+    PFC_CUDA(cudaStreamWaitEvent((to_stream), edge_ev, 0));               \
+  } while (0)
+
+static int tc_bwd_enqueue(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_max, const float* row_sum,
+                          int64_t n_rows, int64_t n_classes, int emb, float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
+                          void* workspace, size_t workspace_bytes, cudaStream_t st) {
   PFC_REQUIRE(tensor_emb_ok(emb), PFC_E_SHAPE, "tensor path supports emb in {64,128,256,512}, got %d (use PFC_PATH_CHECK)", emb);
   PFC_REQUIRE(n_rows > 0 && n_classes > 0 && n_classes < (1ll << 30) && n_rows < (1ll << 24), PFC_E_SHAPE, "pfc_bwd: shape out of range");
   const BwdPlan pl = make_bwd_plan(n_rows, n_classes, emb);
   PFC_REQUIRE(workspace_bytes >= pl.g_bytes + pl.dxp_bytes + pl.radial_bytes, PFC_E_WORKSPACE, "pfc_bwd: workspace too small (%zu < %zu)",
               workspace_bytes, pl.g_bytes + pl.dxp_bytes + pl.radial_bytes);
   PFC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, PFC_E_ARG, "pfc_bwd: workspace must be 1024-byte aligned");
-  auto* g = reinterpret_cast<__nv_bfloat16*>(workspace);
+  char* g_base = reinterpret_cast<char*>(workspace);
   float* dx_part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.g_bytes);
   float* radial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.g_bytes + pl.dxp_bytes);
-  PFC_CUDA(cudaMemsetAsync(radial, 0, (size_t)n_classes * 4, st));
   const auto* wh = reinterpret_cast<const __nv_bfloat16*>(w_hat);
   const int bn = g_logits_pair ? 256 : g_fwd_bn;
   const int n_rb = (int)((n_rows + BM - 1) / BM);
   CUtensorMap tx_k, tx_mn;
   if (int rc = make_tmap_bf16_2d(&tx_k, x, n_rows, emb, emb, BM)) return rc;       // logits: A K-major [128 x 64]
   if (int rc = make_tmap_bf16_2d(&tx_mn, x, n_rows, emb, emb, 64)) return rc;      // dw: B MN-major boxes [64 rows x 64 e]
+
+  // chains: G on the caller's stream, dx and dw on side streams when pipelined
+  cudaStream_t sG = st, sX = st, sW = st;
+  EventPool pool;
+  PFC_CUDA(cudaMemsetAsync(radial, 0, (size_t)n_classes * 4, st));
+  if (pl.pipelined) {
+    if (int rc = side_streams(&sX, &sW)) return rc;
+    PFC_EDGE(st, sX);
+    PFC_EDGE(st, sW);
+  }
+  std::vector<cudaEvent_t> done_x(pl.n_chunks, nullptr), done_w(pl.n_chunks, nullptr);
+
   int chunk_idx = 0;
   for (int64_t c0 = 0; c0 < n_classes; c0 += pl.chunk, ++chunk_idx) {
     const int64_t cc = (n_classes - c0 < pl.chunk) ? n_classes - c0 : pl.chunk;
+    auto* g = reinterpret_cast<__nv_bfloat16*>(g_base + (size_t)(chunk_idx % pl.ring) * pl.g_buf_bytes);
     // (1) G chunk
+    if (pl.pipelined && chunk_idx >= pl.ring) {          // the ring slot is free once its consumers are done
+      PFC_CUDA(cudaStreamWaitEvent(sG, done_x[chunk_idx - pl.ring], 0));
+      PFC_CUDA(cudaStreamWaitEvent(sG, done_w[chunk_idx - pl.ring], 0));
+    }
     CUtensorMap tw_k;
     if (int rc = make_tmap_bf16_2d(&tw_k, wh + c0 * emb, cc, emb, emb, g_logits_pair ? 128 : bn)) return rc;
     LogitsParams lp{};
@@ -1181,15 +1267,23 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
     lp.n_rb = n_rb; lp.n_ct = (int)((cc + bn - 1) / bn); lp.s = s; lp.m = m;
     lp.row_max = row_max; lp.row_sum = row_sum; lp.g = g; lp.ldg = pl.ldg; lp.g_scale = s * inv_total_batch; lp.radial = radial + c0; lp.radial_mode = g_radial_mode;
     const uint64_t g_rows = (uint64_t)(pl.ldg / 64) * n_rb * BM;                              // rows of the blocked scratch viewed as [g_rows, 64]
-    prof_begin(PH_GRAD, st);
+    prof_begin(PH_GRAD, sG);
     if (g_logits_pair) {
       CUtensorMap tg_st;
       if (int rc = make_tmap_bf16_2d(&tg_st, g, g_rows, 64, 64, 32)) return rc;                // epilogue store boxes [32 rows x 64 classes]
-      if (int rc = launch_logits2<4, MODE_GRAD>(tx_k, tw_k, tg_st, lp, pair_grid(n_rows, cc), st)) return rc;
+      int grid = pair_grid(n_rows, cc);
+      if (grid > pl.sm_g / 2 * 2) grid = pl.sm_g / 2 * 2;
+      if (int rc = launch_logits2<4, MODE_GRAD>(tx_k, tw_k, tg_st, lp, grid, sG)) return rc;
     } else {
-      if (int rc = dispatch_logits<MODE_GRAD>(tx_k, tw_k, lp, bn, fwd_grid(n_rows, cc, bn), st)) return rc;
+      int grid = fwd_grid(n_rows, cc, bn);
+      if (grid > pl.sm_g) grid = pl.sm_g;
+      if (int rc = dispatch_logits<MODE_GRAD>(tx_k, tw_k, lp, bn, grid, sG)) return rc;
     }
-    prof_end(PH_GRAD, st);
+    prof_end(PH_GRAD, sG);
+    if (pl.pipelined) {
+      PFC_EDGE(sG, sX);
+      PFC_CUDA(cudaStreamWaitEvent(sW, pool.ev.back(), 0));
+    }
     // (2) dx partial slabs
     CUtensorMap tg_k, tw_mn, tg_mn;
     if (int rc = make_tmap_bf16_2d(&tg_k, g, g_rows, 64, 64, BM)) return rc;                  // A K-major [128 rows x 64 classes] = one block
@@ -1203,14 +1297,19 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
     const int n_rbg = (n_rb + dcs - 1) / dcs;
     const int dgrid = n_rbg * dcs * pl.n_eh * pl.ksplit;
     int rc = 0;
-    prof_begin(PH_DX, st);
+    prof_begin(PH_DX, sX);
     switch (pl.dx_bn) {
-      case 256: rc = launch_dx<256>(tg_k, tw_mn, dp, dgrid, dcs, st); break;
-      case 128: rc = launch_dx<128>(tg_k, tw_mn, dp, dgrid, dcs, st); break;
-      default: rc = launch_dx<64>(tg_k, tw_mn, dp, dgrid, dcs, st); break;
+      case 256: rc = launch_dx<256>(tg_k, tw_mn, dp, dgrid, dcs, sX); break;
+      case 128: rc = launch_dx<128>(tg_k, tw_mn, dp, dgrid, dcs, sX); break;
+      default: rc = launch_dx<64>(tg_k, tw_mn, dp, dgrid, dcs, sX); break;
     }
     if (rc) return rc;
-    prof_end(PH_DX, st);
+    prof_end(PH_DX, sX);
+    if (pl.pipelined) {
+      done_x[chunk_idx] = pool.get();
+      PFC_REQUIRE(done_x[chunk_idx] != nullptr, PFC_E_ARG, "cudaEventCreate failed");
+      PFC_CUDA(cudaEventRecord(done_x[chunk_idx], sX));
+    }
     // (3) dw chunk
     if (int rc2 = make_tmap_bf16_2d(&tg_mn, g, g_rows, 64, 64, 64)) return rc2;              // A MN-major boxes [64 rows x 64 classes] = half a block
     DwParams wp{};
@@ -1219,15 +1318,24 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
     CUtensorMap twh_e, tdw_e;
     if (int rc3 = make_tmap_bf16_2d(&twh_e, wh + c0 * emb, cc, emb, emb, 32)) return rc3;      // epilogue: per-warp [32 classes x 64 e]
     if (int rc3 = make_tmap_f32_2d(&tdw_e, dw + c0 * emb, cc, emb, emb, 32)) return rc3;       // epilogue: per-warp [32 classes x 32 e] fp32
-    prof_begin(PH_DW, st);
+    prof_begin(PH_DW, sW);
     switch (emb) {
-      case 512: rc = launch_dw<512>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, st); break;
-      case 256: rc = launch_dw<256>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, st); break;
-      case 128: rc = launch_dw<128>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, st); break;
-      default: rc = launch_dw<64>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, st); break;
+      case 512: rc = launch_dw<512>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
+      case 256: rc = launch_dw<256>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
+      case 128: rc = launch_dw<128>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
+      default: rc = launch_dw<64>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
     }
     if (rc) return rc;
-    prof_end(PH_DW, st);
+    prof_end(PH_DW, sW);
+    if (pl.pipelined) {
+      done_w[chunk_idx] = pool.get();
+      PFC_REQUIRE(done_w[chunk_idx] != nullptr, PFC_E_ARG, "cudaEventCreate failed");
+      PFC_CUDA(cudaEventRecord(done_w[chunk_idx], sW));
+    }
+  }
+  if (pl.pipelined) {                                   // join: both side chains are in order, their last markers suffice
+    PFC_CUDA(cudaStreamWaitEvent(st, done_x[pl.n_chunks - 1], 0));
+    PFC_CUDA(cudaStreamWaitEvent(st, done_w[pl.n_chunks - 1], 0));
   }
   const int64_t n_vec = n_rows * emb / 4;
   int64_t blocks = (n_vec + 255) / 256;
@@ -1237,6 +1345,91 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
   return 0;
 }
 
+// ---- step graphs -------------------------------------------------------------------------------
+// The backward is a fixed sequence of launches for a given argument set (chunk loop: G, dx, dw kernels + the dx
+// reduction).  It is captured once into a CUDA graph on a library-owned stream and replayed on the caller's stream:
+// one submission per step instead of ~100 launches, tensor-map encodes and attribute calls.  Entries are keyed on
+// every argument and tuning knob; a different pointer set simply captures another graph (small LRU).
+struct BwdKey {
+  const void *x, *w_hat, *inv_norm, *label, *row_max, *row_sum, *dx, *dw, *workspace;
+  int64_t n_rows, n_classes;
+  size_t workspace_bytes;
+  int emb, accumulate_dw, knobs[8];
+  float s, m, inv_total_batch;
+  int device;
+};
+struct BwdGraph {
+  BwdKey key;
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0;
+  uint64_t stamp = 0;
+};
+constexpr int kGraphCache = 16;
+static BwdGraph g_graphs[kGraphCache];
+static uint64_t g_graph_clock = 0;
+static int g_use_graph = 1;
+static cudaStream_t g_capture_stream[64];
+static std::mutex g_graph_mutex;
+
+int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_max, const float* row_sum,
+           int64_t n_rows, int64_t n_classes, int emb, float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
+           void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (st != nullptr && st != cudaStreamLegacy) (void)cudaStreamIsCapturing(st, &cap);
+  if (!g_use_graph || prof_enabled() || g_dbg != nullptr || cap != cudaStreamCaptureStatusNone)
+    return tc_bwd_enqueue(x, w_hat, inv_norm, label, row_max, row_sum, n_rows, n_classes, emb, s, m, inv_total_batch, dx, dw, accumulate_dw,
+                          workspace, workspace_bytes, st);
+  std::lock_guard<std::mutex> lock(g_graph_mutex);
+  BwdKey key;
+  memset(&key, 0, sizeof(key));
+  key.x = x; key.w_hat = w_hat; key.inv_norm = inv_norm; key.label = label; key.row_max = row_max; key.row_sum = row_sum; key.dx = dx; key.dw = dw;
+  key.workspace = workspace; key.n_rows = n_rows; key.n_classes = n_classes; key.workspace_bytes = workspace_bytes; key.emb = emb;
+  key.accumulate_dw = accumulate_dw; key.s = s; key.m = m; key.inv_total_batch = inv_total_batch;
+  key.knobs[0] = g_fwd_bn; key.knobs[1] = g_logits_pair; key.knobs[2] = g_radial_mode; key.knobs[3] = g_dx_cluster; key.knobs[4] = g_dw_cluster;
+  key.knobs[5] = (int)make_bwd_plan(n_rows, n_classes, emb).chunk;
+  key.knobs[6] = g_pipe * 1000 + g_ring; key.knobs[7] = (g_split[0] << 20) | (g_split[1] << 10) | g_split[2];
+  PFC_CUDA(cudaGetDevice(&key.device));
+  BwdGraph* slot = nullptr;
+  for (auto& e : g_graphs)
+    if (e.exec && memcmp(&e.key, &key, sizeof(key)) == 0) { slot = &e; break; }
+  if (!slot) {
+    slot = &g_graphs[0];
+    for (auto& e : g_graphs) {
+      if (!e.exec) { slot = &e; break; }
+      if (e.stamp < slot->stamp) slot = &e;
+    }
+    if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+    PFC_REQUIRE(key.device >= 0 && key.device < 64, PFC_E_ARG, "pfc_bwd: device index out of range");
+    cudaStream_t& cs = g_capture_stream[key.device];
+    if (!cs) PFC_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    const long long l0 = g_launch_count;
+    PFC_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    const int rc = tc_bwd_enqueue(x, w_hat, inv_norm, label, row_max, row_sum, n_rows, n_classes, emb, s, m, inv_total_batch, dx, dw,
+                                  accumulate_dw, workspace, workspace_bytes, cs);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    slot->launches = g_launch_count - l0;
+    g_launch_count = l0;
+    if (rc != 0) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return rc; }
+    PFC_CUDA(ce);
+    const cudaError_t ie = cudaGraphInstantiate(&slot->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { slot->exec = nullptr; PFC_CUDA(ie); }
+    slot->key = key;
+  }
+  slot->stamp = ++g_graph_clock;
+  PFC_CUDA(cudaGraphLaunch(slot->exec, st));
+  g_launch_count += slot->launches;
+  return 0;
+}
+
+void tc_set_graph(int on) { g_use_graph = on ? 1 : 0; }
+void tc_set_pipeline(int on, int sm_g, int sm_dx, int sm_dw, int ring) {
+  g_pipe = on ? 1 : 0;
+  if (sm_g > 0 && sm_dx > 0 && sm_dw > 0) { g_split[0] = sm_g; g_split[1] = sm_dx; g_split[2] = sm_dw; }
+  if (ring >= 1 && ring <= 8) g_ring = ring;
+}
+void tc_set_chunk_mb(int mb) { g_chunk_budget_mb = mb > 0 ? mb : 0; }
 void tc_set_fwd_bn(int bn) { g_fwd_bn = (bn == 256) ? 256 : 128; }
 void tc_set_debug(long long* p) { g_dbg = p; }
 void tc_set_radial_mode(int m) { g_radial_mode = m; }

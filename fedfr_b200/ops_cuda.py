@@ -26,6 +26,16 @@ class CudaOps:
         self._ws = {}
 
     # ------------------------------------------------------------------ helpers
+    def _persist(self, name, shape, dtype):
+        """Per-step scratch tensor with a stable address (the backward is replayed as a CUDA graph keyed on its
+        pointer arguments, so step-to-step address churn would force re-captures)."""
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None:
+            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            self._ws[key] = t
+        return t
+
     def _buf(self, key, nbytes):
         t = self._ws.get(key)
         if t is None or t.numel() < nbytes:
@@ -69,7 +79,7 @@ class CudaOps:
     def normalize(self, sub_weight):
         """-> (w_hat operand, inv_norm).  bf16 on the tensor path, fp32 in check mode."""
         n, emb = sub_weight.shape
-        inv = torch.empty(n, dtype=torch.float32, device=self.device)
+        inv = self._persist("inv_norm", (n,), torch.float32)
         if self.path == N.PATH_CHECK:
             w_hat = torch.empty((n, emb), dtype=torch.float32, device=self.device)
             N.check(N.lib.pfc_normalize_rows(N.ptr(sub_weight), None, n, emb, None, N.ptr(w_hat), N.ptr(inv), _stream(self.device)),
@@ -88,7 +98,7 @@ class CudaOps:
     def cast_features(self, total_features):
         if self.path == N.PATH_CHECK:
             return total_features
-        x = torch.empty(total_features.shape, dtype=torch.bfloat16, device=self.device)
+        x = self._persist("x_hat", total_features.shape, torch.bfloat16)
         N.check(N.lib.pfc_cast_rows_bf16(N.ptr(total_features), total_features.shape[0], total_features.shape[1], N.ptr(x),
                                          _stream(self.device)), "pfc_cast_rows_bf16")
         return x
@@ -98,8 +108,8 @@ class CudaOps:
         bt, emb = x_hat.shape
         cs = w_hat.shape[0]
         n_part = N.lib.pfc_fwd_num_partials(bt, cs, emb, self.path)
-        part = torch.empty((2, n_part, bt), dtype=torch.float32, device=self.device)
-        tz = torch.empty(bt, dtype=torch.float32, device=self.device)
+        part = self._persist("part", (2, n_part, bt), torch.float32)
+        tz = self._persist("target_logit", (bt,), torch.float32)
         st = _stream(self.device)
         N.check(N.lib.pfc_fwd_stats(N.ptr(x_hat), N.ptr(w_hat), N.ptr(label), bt, cs, emb, float(s), float(m), N.ptr(part[0]), N.ptr(part[1]),
                                     N.ptr(tz), self.path, st), "pfc_fwd_stats")
@@ -110,18 +120,19 @@ class CudaOps:
     def finalize(self, gathered_stats):
         """[W, Bt, 3] -> (row_max [Bt], row_sum [Bt], loss 0-d)."""
         w, bt, _ = gathered_stats.shape
-        row_max = torch.empty(bt, dtype=torch.float32, device=self.device)
-        row_sum = torch.empty_like(row_max)
+        row_max = self._persist("row_max", (bt,), torch.float32)
+        row_sum = self._persist("row_sum", (bt,), torch.float32)
         loss = torch.empty((), dtype=torch.float32, device=self.device)
         N.check(N.lib.pfc_finalize_stats(N.ptr(gathered_stats), w, bt, N.ptr(row_max), N.ptr(row_sum), N.ptr(loss), _stream(self.device)),
                 "pfc_finalize_stats")
         return row_max, row_sum, loss
 
     def bwd(self, x_hat, w_hat, inv_norm, label, row_max, row_sum, s, m, inv_total_batch, dw, accumulate):
-        """Writes/accumulates ``dw`` [Cs, E]; returns this shard's partial ``dx`` [Bt, E]."""
+        """Writes/accumulates ``dw`` [Cs, E]; returns this shard's partial ``dx`` [Bt, E] (library-owned scratch,
+        overwritten by the next step: callers hand out a copy)."""
         bt, emb = x_hat.shape
         cs = w_hat.shape[0]
-        dx = torch.empty((bt, emb), dtype=torch.float32, device=self.device)
+        dx = self._persist("dx", (bt, emb), torch.float32)
         nbytes = N.lib.pfc_bwd_workspace_bytes(bt, cs, emb, self.path)
         ws = self._buf("bwd", nbytes + 1024)
         off = (-ws.data_ptr()) % 1024

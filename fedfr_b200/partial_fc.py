@@ -88,6 +88,7 @@ class PartialFC(Module):
         else:
             self.sub_weight = Parameter(torch.empty((0, 0), device=self.device))
         self._norm = None       # (w_hat, inv_norm) of the current step
+        self._label_buf = None
 
     # ------------------------------------------------------------------ shard I/O (partial_fc.py:71-87)
     def save_params(self):
@@ -161,6 +162,10 @@ class PartialFC(Module):
                              "partial_fc.py:120-122,132-134)")
         ops = self._ops
         total_label, w_hat = self.prepare(label, optimizer)
+        if self._label_buf is None or self._label_buf.shape != total_label.shape:
+            self._label_buf = torch.empty_like(total_label)
+        self._label_buf.copy_(total_label)          # stable address for the replayed backward graph
+        total_label = self._label_buf
         inv_norm = self._norm[1]
         total_features = torch.zeros(size=[B * W, E], device=self.device)
         self._all_gather(total_features, features.data.to(torch.float32))
@@ -183,7 +188,7 @@ class PartialFC(Module):
                            self.sub_weight.grad, accumulate)
 
         if W == 1:
-            x_grad = dx_total
+            x_grad = dx_total.clone()               # dx_total is step scratch with a stable address
         else:
             x_grad = torch.zeros_like(features, dtype=torch.float32, device=self.device)
             dist.reduce_scatter(x_grad, list(dx_total.chunk(W, dim=0)))
