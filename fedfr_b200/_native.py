@@ -38,6 +38,7 @@ SIGNATURES = {
     "pfc_sample_index": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "pfc_fwd_num_partials": (_i32, [_i64, _i64, _i32, _i32]),
     "pfc_fwd_stats": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _i32, _vp]),
+    "pfc_normalize_fwd_stats": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "pfc_merge_stats": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "pfc_finalize_stats": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "pfc_bwd_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
@@ -62,6 +63,8 @@ lib.pfc_set_clusters.restype = _i32
 lib.pfc_set_clusters.argtypes = [_i32, _i32]
 lib.pfc_set_logits_tile.restype = _i32
 lib.pfc_set_logits_tile.argtypes = [_i32]
+lib.pfc_set_fwd_overlap.restype = _i32
+lib.pfc_set_fwd_overlap.argtypes = [_i32, _i32]
 lib.pfc_set_pipeline.restype = _i32
 lib.pfc_set_pipeline.argtypes = [_i32, _i32, _i32, _i32, _i32]
 for _knob in ("pfc_set_graph", "pfc_set_chunk_mb", "pfc_set_logits_pair", "pfc_set_radial_mode"):

@@ -1,50 +1,20 @@
 // HBM-bound row kernels: normalise (+gather) -> bf16, cast, gather, scatter.
 // One warp per row, 128-bit accesses; rows are 2 KB (E=512 fp32) so a warp owns 4 float4 per lane.
 #include "common.cuh"
+#include "rows_device.cuh"
 
 namespace pfc {
 
 // normalize(sub_weight) (partial_fc.py:127) fused with the sampled gather (partial_fc.py:105).
 // Algorithmic bytes per row: read 4E, write 2E (bf16) + 4.
-template <int kVecPerLane>
+template <int kVecPerLane, int kRows>
 __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __restrict__ w, const int64_t* __restrict__ index,
                                                              int64_t n_rows, int emb, __nv_bfloat16* __restrict__ out_bf16,
                                                              float* __restrict__ out_f32, float* __restrict__ inv_norm) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  const int nvec = emb >> 2;
-  for (int64_t r = warp; r < n_rows; r += n_warps) {
-    const int64_t src = index ? index[r] : r;
-    const float4* p = reinterpret_cast<const float4*>(w + src * emb);
-    float4 v[kVecPerLane];
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < kVecPerLane; ++i) {
-      const int c = lane + i * 32;
-      if (c < nvec) {
-        v[i] = ld_stream_f4(p + c);
-        ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-      }
-    }
-    ss = warp_sum(ss);
-    const float nrm = fmaxf(sqrtf(ss), 1e-12f);
-    const float inv = 1.0f / nrm;
-    if (lane == 0 && inv_norm) inv_norm[r] = inv;
-#pragma unroll
-    for (int i = 0; i < kVecPerLane; ++i) {
-      const int c = lane + i * 32;
-      if (c < nvec) {
-        // divide (not multiply by the reciprocal) so the fp32 output matches F.normalize bit for bit
-        float4 o = make_float4(v[i].x / nrm, v[i].y / nrm, v[i].z / nrm, v[i].w / nrm);
-        if (out_bf16) {
-          uint2 pk = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-          *reinterpret_cast<uint2*>(out_bf16 + r * emb + c * 4) = pk;
-        }
-        if (out_f32) st_stream_f4(reinterpret_cast<float4*>(out_f32 + r * emb) + c, o);
-      }
-    }
-  }
+  normalize_rows_warp<kVecPerLane, kRows>(w, index, n_rows, emb, out_bf16, out_f32, inv_norm, warp, n_warps, lane);
 }
 
 __global__ void __launch_bounds__(256) cast_rows_kernel(const float4* __restrict__ x, int64_t n_vec, uint2* __restrict__ out) {
@@ -102,6 +72,35 @@ static int row_grid(int64_t n_rows) {
   return (int)blocks;
 }
 
+// blocks_per_sm > 0 caps the grid at that many blocks per SM and keeps two rows per warp in flight: the shape used when
+// the kernel shares the SMs with a tensor-core kernel (pfc_normalize_fwd_stats).
+int launch_normalize_rows(const float* w, const int64_t* index, int64_t n_rows, int emb, __nv_bfloat16* ob, float* of, float* inv_norm,
+                          int blocks_per_sm, cudaStream_t st) {
+  PFC_REQUIRE(w && n_rows >= 0 && emb > 0, PFC_E_ARG, "pfc_normalize_rows: bad argument");
+  PFC_REQUIRE(emb % 4 == 0 && emb <= 2048, PFC_E_SHAPE, "pfc_normalize_rows: emb=%d must be a multiple of 4 and <= 2048", emb);
+  if (n_rows == 0) return 0;
+  const int vec_per_lane = (emb / 4 + 31) / 32;
+  int grid = row_grid(n_rows);
+  if (blocks_per_sm > 0) {
+    int64_t blocks = (n_rows + 15) / 16;
+    const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+    grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+    if (vec_per_lane <= 1) normalize_rows_kernel<1, 2><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, of, inv_norm);
+    else if (vec_per_lane <= 2) normalize_rows_kernel<2, 2><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, of, inv_norm);
+    else if (vec_per_lane <= 4) normalize_rows_kernel<4, 2><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, of, inv_norm);
+    else if (vec_per_lane <= 8) normalize_rows_kernel<8, 1><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, of, inv_norm);
+    else normalize_rows_kernel<16, 1><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, of, inv_norm);
+  } else {
+    if (vec_per_lane <= 1) normalize_rows_kernel<1, 1><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, of, inv_norm);
+    else if (vec_per_lane <= 2) normalize_rows_kernel<2, 1><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, of, inv_norm);
+    else if (vec_per_lane <= 4) normalize_rows_kernel<4, 1><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, of, inv_norm);
+    else if (vec_per_lane <= 8) normalize_rows_kernel<8, 1><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, of, inv_norm);
+    else normalize_rows_kernel<16, 1><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, of, inv_norm);
+  }
+  PFC_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace pfc
 
 using namespace pfc;
@@ -111,20 +110,9 @@ extern "C" {
 int pfc_normalize_rows(const float* w, const int64_t* index, int64_t n_rows, int emb, void* w_hat_bf16, float* w_hat_f32,
                        float* inv_norm, void* stream) {
   if (int rc = require_sm100()) return rc;
-  PFC_REQUIRE(w && n_rows >= 0 && emb > 0, PFC_E_ARG, "pfc_normalize_rows: bad argument");
-  PFC_REQUIRE(emb % 4 == 0 && emb <= 2048, PFC_E_SHAPE, "pfc_normalize_rows: emb=%d must be a multiple of 4 and <= 2048", emb);
-  if (n_rows == 0) return 0;
-  const int vec_per_lane = (emb / 4 + 31) / 32;
-  auto* ob = reinterpret_cast<__nv_bfloat16*>(w_hat_bf16);
-  const int grid = row_grid(n_rows);
   cudaStream_t st = as_stream(stream);
   prof_begin(PH_NORMALIZE, st);
-  if (vec_per_lane <= 1) normalize_rows_kernel<1><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, w_hat_f32, inv_norm);
-  else if (vec_per_lane <= 2) normalize_rows_kernel<2><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, w_hat_f32, inv_norm);
-  else if (vec_per_lane <= 4) normalize_rows_kernel<4><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, w_hat_f32, inv_norm);
-  else if (vec_per_lane <= 8) normalize_rows_kernel<8><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, w_hat_f32, inv_norm);
-  else normalize_rows_kernel<16><<<grid, 256, 0, st>>>(w, index, n_rows, emb, ob, w_hat_f32, inv_norm);
-  PFC_LAUNCH_CHECK();
+  if (int rc = launch_normalize_rows(w, index, n_rows, emb, reinterpret_cast<__nv_bfloat16*>(w_hat_bf16), w_hat_f32, inv_norm, 0, st)) return rc;
   prof_end(PH_NORMALIZE, st);
   return 0;
 }

@@ -9,6 +9,7 @@
 // All kernels: 192 threads = 4 epilogue warps (TMEM lanes 0..127) + 1 TMA producer warp + 1 MMA issuer warp,
 // 128-byte-swizzled operand tiles, mbarrier pipelines (smem full/empty, TMEM full/empty).
 #include "tc_common.cuh"
+#include "rows_device.cuh"
 #include <mutex>
 #include <string.h>
 #include <vector>
@@ -85,6 +86,13 @@ struct LogitsParams {
   float* part_max;           // [gridDim.x, n_rows]   (log-e units)
   float* part_sum;
   float* target_logit;       // [n_rows]
+  int accumulate_stats;      // 1: continue from the (max, sum) already in this CTA's slots (class-chunked forward)
+  // normaliser warps (logits2_kernel<.., NORM = true>): normalize() of the NEXT class chunk rides under this chunk's MMAs
+  const float* norm_w;       // fp32 rows (already offset to the chunk unless norm_index != NULL)
+  const int64_t* norm_index;
+  int64_t norm_rows;
+  __nv_bfloat16* norm_out;   // [norm_rows, emb]
+  float* norm_inv;           // [norm_rows]
   // MODE_GRAD
   const float* row_max;      // [n_rows]
   const float* row_sum;
@@ -271,6 +279,10 @@ __global__ void __launch_bounds__(kLogitsThreads, 1) logits_kernel(const __grid_
           if (y >= 0) my_label = (int)(y - p.class_base);          // relative to this launch; out of range never matches
         }
         run_m = -INFINITY; run_l = 0.f;
+        if (MODE == MODE_STATS && p.accumulate_stats && row_ok) {
+          const float l0 = p.part_sum[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row];
+          if (l0 > 0.f) { run_l = l0; run_m = p.part_max[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] * kLog2e; }
+        }
         if (MODE == MODE_GRAD && row_ok) { M2 = p.row_max[row] * kLog2e; rS = 1.0f / p.row_sum[row]; }
       }
       const int acc = (int)(it & 1);
@@ -360,9 +372,11 @@ __global__ void __launch_bounds__(kLogitsThreads, 1) logits_kernel(const __grid_
 //   tcgen05.commit is multicast to the barriers of both CTAs; every CTA runs its own epilogue on its own TMEM rows.
 //   MODE_GRAD stores G through per-warp swizzled staging boxes and TMA stores into the blocked scratch.
 // ================================================================================================
-template <int STAGES, int MODE>
-__global__ void __launch_bounds__(kLogitsThreads, 1) logits2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                                                                    const __grid_constant__ CUtensorMap tmap_g, const LogitsParams p) {
+constexpr int kNormWarps = 8;          // extra HBM-streaming warps of the NORM variant
+template <int STAGES, int MODE, bool NORM>
+__global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0), 1)
+    logits2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                   const __grid_constant__ CUtensorMap tmap_g, const LogitsParams p) {
   constexpr int BN = 256;                 // classes per pair tile
   constexpr int BH = 128;                 // classes per CTA (its half of the B operand)
   constexpr int kBStage = BH * BK * 2;    // 16 KB
@@ -466,6 +480,10 @@ __global__ void __launch_bounds__(kLogitsThreads, 1) logits2_kernel(const __grid
         if (last_of_rp) umma_commit_2cta(a_empty, 3);
       }
     }
+  } else if (NORM && warp >= kLogitsEpiWarps + 2) {
+    // ------------------------------------------------------------------ normaliser warps: pure HBM streaming (fp32 rows -> bf16 + 1/norm)
+    normalize_rows_warp<4, 2, 2>(p.norm_w, p.norm_index, p.norm_rows, p.emb, p.norm_out, nullptr, p.norm_inv,
+                              (int64_t)blockIdx.x * kNormWarps + (warp - (kLogitsEpiWarps + 2)), (int64_t)gridDim.x * kNormWarps, lane);
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps per CTA), thread = row of THIS CTA's block
     const int quad = warp & 3, chalf = warp >> 2;
@@ -497,6 +515,10 @@ __global__ void __launch_bounds__(kLogitsThreads, 1) logits2_kernel(const __grid
           if (y >= 0) my_label = (int)(y - p.class_base);
         }
         run_m = -INFINITY; run_l = 0.f;
+        if (MODE == MODE_STATS && p.accumulate_stats && row_ok) {
+          const float l0 = p.part_sum[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row];
+          if (l0 > 0.f) { run_l = l0; run_m = p.part_max[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] * kLog2e; }
+        }
         M2 = 0.f; rS = 0.f;
         if (MODE == MODE_GRAD && row_ok) { M2 = p.row_max[row] * kLog2e; rS = 1.0f / p.row_sum[row]; }
       }
@@ -973,14 +995,14 @@ static int launch_logits(const CUtensorMap& tx, const CUtensorMap& tw, const Log
 
 static int g_logits_pair = 1;      // 1: CTA-pair (cta_group::2) logits kernels, 0: single-CTA kernels
 
-template <int STAGES, int MODE>
+template <int STAGES, int MODE, bool NORM = false>
 static int launch_logits2(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tg, const LogitsParams& p, int grid, cudaStream_t st) {
   const size_t smem = (size_t)(p.emb / BK) * kChunkBytes + (size_t)STAGES * 128 * BK * 2 + (MODE == MODE_GRAD ? kLogitsEpiWarps * 4096 : 0) + 1024 + 256;
-  auto kern = logits2_kernel<STAGES, MODE>;
+  auto kern = logits2_kernel<STAGES, MODE, NORM>;
   PFC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kLogitsThreads);
+  cfg.blockDim = dim3(kLogitsThreads + (NORM ? kNormWarps * 32 : 0));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1346,52 +1368,50 @@ static int tc_bwd_enqueue(const void* x, const void* w_hat, const float* inv_nor
 }
 
 // ---- step graphs -------------------------------------------------------------------------------
-// The backward is a fixed sequence of launches for a given argument set (chunk loop: G, dx, dw kernels + the dx
-// reduction).  It is captured once into a CUDA graph on a library-owned stream and replayed on the caller's stream:
-// one submission per step instead of ~100 launches, tensor-map encodes and attribute calls.  Entries are keyed on
-// every argument and tuning knob; a different pointer set simply captures another graph (small LRU).
-struct BwdKey {
-  const void *x, *w_hat, *inv_norm, *label, *row_max, *row_sum, *dx, *dw, *workspace;
-  int64_t n_rows, n_classes;
-  size_t workspace_bytes;
-  int emb, accumulate_dw, knobs[8];
-  float s, m, inv_total_batch;
-  int device;
-};
-struct BwdGraph {
-  BwdKey key;
+// The forward and the backward are fixed launch sequences for a given argument set.  Each is captured once into a CUDA
+// graph on a library-owned stream and replayed on the caller's stream: one submission per phase instead of ~100
+// launches, tensor-map encodes and attribute calls, and the concurrent branches (normalise || logits, dx || dw) become
+// graph branches.  Entries are keyed on every argument and tuning knob; another pointer set captures another graph (LRU).
+struct GraphEntry {
+  unsigned char key[256];
+  size_t key_len = 0;
   cudaGraphExec_t exec = nullptr;
   long long launches = 0;
   uint64_t stamp = 0;
 };
-constexpr int kGraphCache = 16;
-static BwdGraph g_graphs[kGraphCache];
+constexpr int kGraphCache = 24;
+static GraphEntry g_graphs[kGraphCache];
 static uint64_t g_graph_clock = 0;
 static int g_use_graph = 1;
 static cudaStream_t g_capture_stream[64];
 static std::mutex g_graph_mutex;
 
-int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_max, const float* row_sum,
-           int64_t n_rows, int64_t n_classes, int emb, float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
-           void* workspace, size_t workspace_bytes, cudaStream_t st) {
+struct KeyBuilder {
+  unsigned char buf[256];
+  size_t len = 0;
+  KeyBuilder() { memset(buf, 0, sizeof(buf)); }
+  template <class T> KeyBuilder& add(const T& v) {
+    if (len + sizeof(T) <= sizeof(buf)) { memcpy(buf + len, &v, sizeof(T)); len += sizeof(T); }
+    return *this;
+  }
+};
+
+static bool graph_eligible(cudaStream_t st) {
+  if (!g_use_graph || prof_enabled() || g_dbg != nullptr) return false;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  if (st != nullptr && st != cudaStreamLegacy) (void)cudaStreamIsCapturing(st, &cap);
-  if (!g_use_graph || prof_enabled() || g_dbg != nullptr || cap != cudaStreamCaptureStatusNone)
-    return tc_bwd_enqueue(x, w_hat, inv_norm, label, row_max, row_sum, n_rows, n_classes, emb, s, m, inv_total_batch, dx, dw, accumulate_dw,
-                          workspace, workspace_bytes, st);
+  if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread) (void)cudaStreamIsCapturing(st, &cap);
+  return cap == cudaStreamCaptureStatusNone;
+}
+
+template <class Enqueue>
+static int run_cached_graph(const KeyBuilder& kb, cudaStream_t st, Enqueue enqueue) {
   std::lock_guard<std::mutex> lock(g_graph_mutex);
-  BwdKey key;
-  memset(&key, 0, sizeof(key));
-  key.x = x; key.w_hat = w_hat; key.inv_norm = inv_norm; key.label = label; key.row_max = row_max; key.row_sum = row_sum; key.dx = dx; key.dw = dw;
-  key.workspace = workspace; key.n_rows = n_rows; key.n_classes = n_classes; key.workspace_bytes = workspace_bytes; key.emb = emb;
-  key.accumulate_dw = accumulate_dw; key.s = s; key.m = m; key.inv_total_batch = inv_total_batch;
-  key.knobs[0] = g_fwd_bn; key.knobs[1] = g_logits_pair; key.knobs[2] = g_radial_mode; key.knobs[3] = g_dx_cluster; key.knobs[4] = g_dw_cluster;
-  key.knobs[5] = (int)make_bwd_plan(n_rows, n_classes, emb).chunk;
-  key.knobs[6] = g_pipe * 1000 + g_ring; key.knobs[7] = (g_split[0] << 20) | (g_split[1] << 10) | g_split[2];
-  PFC_CUDA(cudaGetDevice(&key.device));
-  BwdGraph* slot = nullptr;
+  int device = 0;
+  PFC_CUDA(cudaGetDevice(&device));
+  PFC_REQUIRE(device >= 0 && device < 64, PFC_E_ARG, "device index out of range");
+  GraphEntry* slot = nullptr;
   for (auto& e : g_graphs)
-    if (e.exec && memcmp(&e.key, &key, sizeof(key)) == 0) { slot = &e; break; }
+    if (e.exec && e.key_len == kb.len && memcmp(e.key, kb.buf, kb.len) == 0) { slot = &e; break; }
   if (!slot) {
     slot = &g_graphs[0];
     for (auto& e : g_graphs) {
@@ -1399,13 +1419,11 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
       if (e.stamp < slot->stamp) slot = &e;
     }
     if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
-    PFC_REQUIRE(key.device >= 0 && key.device < 64, PFC_E_ARG, "pfc_bwd: device index out of range");
-    cudaStream_t& cs = g_capture_stream[key.device];
+    cudaStream_t& cs = g_capture_stream[device];
     if (!cs) PFC_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     const long long l0 = g_launch_count;
     PFC_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-    const int rc = tc_bwd_enqueue(x, w_hat, inv_norm, label, row_max, row_sum, n_rows, n_classes, emb, s, m, inv_total_batch, dx, dw,
-                                  accumulate_dw, workspace, workspace_bytes, cs);
+    const int rc = enqueue(cs);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
     slot->launches = g_launch_count - l0;
@@ -1415,12 +1433,105 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
     const cudaError_t ie = cudaGraphInstantiate(&slot->exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ie != cudaSuccess) { slot->exec = nullptr; PFC_CUDA(ie); }
-    slot->key = key;
+    memcpy(slot->key, kb.buf, sizeof(kb.buf));
+    slot->key_len = kb.len;
   }
   slot->stamp = ++g_graph_clock;
   PFC_CUDA(cudaGraphLaunch(slot->exec, st));
   g_launch_count += slot->launches;
   return 0;
+}
+
+int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_max, const float* row_sum,
+           int64_t n_rows, int64_t n_classes, int emb, float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
+           void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  auto enqueue = [&](cudaStream_t cs) {
+    return tc_bwd_enqueue(x, w_hat, inv_norm, label, row_max, row_sum, n_rows, n_classes, emb, s, m, inv_total_batch, dx, dw, accumulate_dw,
+                          workspace, workspace_bytes, cs);
+  };
+  if (!graph_eligible(st)) return enqueue(st);
+  KeyBuilder kb;
+  kb.add(1).add(x).add(w_hat).add(inv_norm).add(label).add(row_max).add(row_sum).add(dx).add(dw).add(workspace).add(n_rows).add(n_classes)
+      .add(workspace_bytes).add(emb).add(accumulate_dw).add(s).add(m).add(inv_total_batch).add(g_fwd_bn).add(g_logits_pair).add(g_radial_mode)
+      .add(g_dx_cluster).add(g_dw_cluster).add(make_bwd_plan(n_rows, n_classes, emb).chunk).add(g_pipe).add(g_ring).add(g_split[0])
+      .add(g_split[1]).add(g_split[2]);
+  return run_cached_graph(kb, st, enqueue);
+}
+
+// ---- fused forward: normalise (HBM bound) || logits + stats (tensor bound) ---------------------
+// The class axis is cut into chunks; normalize(k+1) runs on a side stream while the logits kernel works on chunk k, so
+// the fp32 weight read hides behind the MMAs.  The logits kernel continues its per-CTA (max, sum) slots across chunks.
+int launch_normalize_rows(const float* w, const int64_t* index, int64_t n_rows, int emb, __nv_bfloat16* ob, float* of, float* inv_norm,
+                          int blocks_per_sm, cudaStream_t st);
+static int g_fwd_chunks = 4;
+static int g_norm_blocks_per_sm = 2;
+
+static int tc_normalize_fwd_enqueue(const float* w, const int64_t* index, const void* x, const int64_t* label, int64_t n_rows, int64_t n_classes,
+                                    int emb, float s, float m, void* w_hat, float* inv_norm, float* part_max, float* part_sum,
+                                    float* target_logit, cudaStream_t st) {
+  PFC_REQUIRE(tensor_emb_ok(emb), PFC_E_SHAPE, "tensor path supports emb in {64,128,256,512}, got %d (use PFC_PATH_CHECK)", emb);
+  PFC_REQUIRE(n_rows > 0 && n_classes > 0 && n_classes < (1ll << 30) && n_rows < (1ll << 24), PFC_E_SHAPE, "pfc_normalize_fwd_stats: shape out of range");
+  auto* wh = reinterpret_cast<__nv_bfloat16*>(w_hat);
+  const int bn = g_logits_pair ? 256 : g_fwd_bn;
+  int64_t n_chunks = g_logits_pair ? g_fwd_chunks : 1;                 // the normaliser warps live in the CTA-pair kernel
+  if (n_chunks > n_classes / 16384) n_chunks = n_classes / 16384;      // a chunk must keep every SM busy for a while
+  if (n_chunks < 1) n_chunks = 1;
+  const int64_t chunk = ((n_classes + n_chunks - 1) / n_chunks + 255) / 256 * 256;
+  const int grid_full = g_logits_pair ? pair_grid(n_rows, n_classes) : fwd_grid(n_rows, n_classes, bn);
+  PFC_CUDA(cudaMemsetAsync(part_sum, 0, sizeof(float) * (size_t)grid_full * 2 * n_rows, st));
+  PFC_CUDA(cudaMemsetAsync(target_logit, 0, sizeof(float) * (size_t)n_rows, st));
+  CUtensorMap tx;
+  if (int rc = make_tmap_bf16_2d(&tx, x, n_rows, emb, emb, BM)) return rc;
+  auto chunk_len = [&](int64_t c0) { return (n_classes - c0 < chunk) ? n_classes - c0 : chunk; };
+  // chunk 0 is normalised by the stand-alone kernel; chunk k+1 by the normaliser warps of the logits kernel of chunk k
+  prof_begin(PH_NORMALIZE, st);
+  if (int rc = launch_normalize_rows(index ? w : w, index, chunk_len(0), emb, wh, nullptr, inv_norm, 0, st)) return rc;
+  prof_end(PH_NORMALIZE, st);
+  int k = 0;
+  for (int64_t c0 = 0; c0 < n_classes; c0 += chunk, ++k) {
+    const int64_t cc = chunk_len(c0);
+    const int64_t n0 = c0 + chunk;                                     // first class of the next chunk
+    const bool has_next = n0 < n_classes;
+    CUtensorMap tw;
+    if (int rc = make_tmap_bf16_2d(&tw, wh + c0 * emb, cc, emb, emb, g_logits_pair ? 128 : bn)) return rc;
+    LogitsParams p{};
+    p.label = label; p.n_rows = (int)n_rows; p.n_classes = (int)cc; p.class_base = (int)c0; p.emb = emb;
+    p.n_rb = (int)((n_rows + BM - 1) / BM); p.n_ct = (int)((cc + bn - 1) / bn);
+    p.s = s; p.m = m; p.part_max = part_max; p.part_sum = part_sum; p.target_logit = target_logit; p.accumulate_stats = k > 0;
+    if (has_next) {
+      p.norm_w = index ? w : w + n0 * emb; p.norm_index = index ? index + n0 : nullptr; p.norm_rows = chunk_len(n0);
+      p.norm_out = wh + n0 * emb; p.norm_inv = inv_norm + n0;
+    }
+    const int grid = g_logits_pair ? pair_grid(n_rows, cc) : fwd_grid(n_rows, cc, bn);
+    static const int exp_mode = getenv("FEDFR_EXP") ? atoi(getenv("FEDFR_EXP")) : 0;      // timing experiments only (wrong results)
+    if (exp_mode == 1) p.norm_rows = 0;          // big CTA, idle normaliser warps
+    if (exp_mode == 2) p.n_ct = 0;               // normaliser warps only
+    prof_begin(PH_FWD, st);
+    int rc;
+    if (!g_logits_pair) rc = dispatch_logits<MODE_STATS>(tx, tw, p, bn, grid, st);
+    else if (has_next) rc = launch_logits2<4, MODE_STATS, true>(tx, tw, tw, p, grid, st);
+    else rc = launch_logits2<4, MODE_STATS>(tx, tw, tw, p, grid, st);
+    if (rc) return rc;
+    prof_end(PH_FWD, st);
+  }
+  return 0;
+}
+
+int tc_normalize_fwd(const float* w, const int64_t* index, const void* x, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb,
+                     float s, float m, void* w_hat, float* inv_norm, float* part_max, float* part_sum, float* target_logit, cudaStream_t st) {
+  auto enqueue = [&](cudaStream_t cs) {
+    return tc_normalize_fwd_enqueue(w, index, x, label, n_rows, n_classes, emb, s, m, w_hat, inv_norm, part_max, part_sum, target_logit, cs);
+  };
+  if (!graph_eligible(st)) return enqueue(st);
+  KeyBuilder kb;
+  kb.add(2).add(w).add(index).add(x).add(label).add(n_rows).add(n_classes).add(emb).add(s).add(m).add(w_hat).add(inv_norm).add(part_max)
+      .add(part_sum).add(target_logit).add(g_fwd_bn).add(g_logits_pair).add(g_fwd_chunks).add(g_norm_blocks_per_sm);
+  return run_cached_graph(kb, st, enqueue);
+}
+
+void tc_set_fwd_overlap(int chunks, int norm_blocks_per_sm) {
+  if (chunks >= 1 && chunks <= 64) g_fwd_chunks = chunks;
+  if (norm_blocks_per_sm >= 1 && norm_blocks_per_sm <= 8) g_norm_blocks_per_sm = norm_blocks_per_sm;
 }
 
 void tc_set_graph(int on) { g_use_graph = on ? 1 : 0; }

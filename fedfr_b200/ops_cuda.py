@@ -95,6 +95,34 @@ class CudaOps:
                     "pfc_normalize_rows")
         return w_hat, inv
 
+    def _w_hat_buffer(self, n, emb):
+        if self.path == N.PATH_CHECK:
+            return self._persist("w_hat_f32", (n, emb), torch.float32)
+        key = ("w_hat", n, emb)
+        w_hat = self._ws.get(key)
+        if w_hat is None:
+            self._ws = {k: v for k, v in self._ws.items() if not (isinstance(k, tuple) and k[0] == "w_hat")}
+            w_hat = torch.empty((n, emb), dtype=torch.bfloat16, device=self.device)
+            self._ws[key] = w_hat
+        return w_hat
+
+    def normalize_fwd_stats(self, sub_weight, x_hat, label, s, m):
+        """normalize(sub_weight) fused with fwd_stats (one graph: the normalisation of class chunk k+1 runs under the
+        logits kernel of chunk k).  -> (w_hat, inv_norm, stats [Bt, 3])."""
+        n, emb = sub_weight.shape
+        bt = x_hat.shape[0]
+        w_hat = self._w_hat_buffer(n, emb)
+        inv = self._persist("inv_norm", (n,), torch.float32)
+        n_part = N.lib.pfc_fwd_num_partials(bt, n, emb, self.path)
+        part = self._persist("part", (2, n_part, bt), torch.float32)
+        tz = self._persist("target_logit", (bt,), torch.float32)
+        st = _stream(self.device)
+        N.check(N.lib.pfc_normalize_fwd_stats(N.ptr(sub_weight), None, N.ptr(x_hat), N.ptr(label), bt, n, emb, float(s), float(m), N.ptr(w_hat),
+                                              N.ptr(inv), N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), self.path, st), "pfc_normalize_fwd_stats")
+        stats = self._persist("stats", (bt, 3), torch.float32)
+        N.check(N.lib.pfc_merge_stats(N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), n_part, bt, N.ptr(stats), st), "pfc_merge_stats")
+        return w_hat, inv, stats
+
     def cast_features(self, total_features):
         if self.path == N.PATH_CHECK:
             return total_features

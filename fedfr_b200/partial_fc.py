@@ -140,15 +140,18 @@ class PartialFC(Module):
             dist.all_gather(list(out.chunk(self.world_size, dim=0)), inp)
 
     @torch.no_grad()
-    def prepare(self, label, optimizer):
+    def prepare(self, label, optimizer, _defer_normalize=False):
         """partial_fc.py:118-128: gather labels, sample, rewire the optimizer onto ``sub_weight`` and its
-        momentum buffer, normalise the sub-shard.  Returns ``(total_label, norm_weight)``."""
+        momentum buffer, normalise the sub-shard.  Returns ``(total_label, norm_weight)``.
+        (``forward_backward`` defers the normalisation: it is fused with the logits kernel.)"""
         total_label = torch.zeros(size=[self.batch_size * self.world_size], device=self.device, dtype=torch.long)
         self._all_gather(total_label, label.to(self.device))
         self.sample(total_label)
         optimizer.state.pop(optimizer.param_groups[-1]['params'][0], None)
         optimizer.param_groups[-1]['params'][0] = self.sub_weight
         optimizer.state[self.sub_weight]['momentum_buffer'] = self.sub_weight_mom
+        if _defer_normalize:
+            return total_label, None
         self._norm = self._ops.normalize(self.sub_weight.data)
         return total_label, self._norm[0]
 
@@ -161,18 +164,23 @@ class PartialFC(Module):
             raise ValueError("features/label batch must equal the constructor's batch_size (gather buffers are pre-sized, "
                              "partial_fc.py:120-122,132-134)")
         ops = self._ops
-        total_label, w_hat = self.prepare(label, optimizer)
+        fused = hasattr(ops, "normalize_fwd_stats")
+        total_label, w_hat = self.prepare(label, optimizer, _defer_normalize=fused)
         if self._label_buf is None or self._label_buf.shape != total_label.shape:
             self._label_buf = torch.empty_like(total_label)
         self._label_buf.copy_(total_label)          # stable address for the replayed backward graph
         total_label = self._label_buf
-        inv_norm = self._norm[1]
         total_features = torch.zeros(size=[B * W, E], device=self.device)
         self._all_gather(total_features, features.data.to(torch.float32))
         x_hat = ops.cast_features(total_features)
 
         # forward: per-shard (max, sum-exp, target logit), then one exchange instead of three all-reduces
-        stats = ops.fwd_stats(x_hat, w_hat, total_label, self._s, self._m)
+        if fused:       # normalize(sub_weight) chunk k+1 runs underneath the logits kernel of chunk k
+            w_hat, inv_norm, stats = ops.normalize_fwd_stats(self.sub_weight.data, x_hat, total_label, self._s, self._m)
+            self._norm = (w_hat, inv_norm)
+        else:
+            inv_norm = self._norm[1]
+            stats = ops.fwd_stats(x_hat, w_hat, total_label, self._s, self._m)
         if W == 1:
             gathered = stats.unsqueeze(0)
         else:
