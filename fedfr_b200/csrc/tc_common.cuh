@@ -206,6 +206,12 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* m
 __device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
+// Same without memory ordering: for barriers that only hand a TMEM accumulator back to the MMA issuer (the tcgen05 loads
+// are complete after tcgen05.wait::ld + fence::before_thread_sync; no generic-proxy data travels with the arrival), so
+// the arriving thread does not have to drain its outstanding global stores / atomics first.
+__device__ __forceinline__ void mbar_arrive_cluster_addr_relaxed(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, 128-byte swizzle, bf16.

@@ -109,6 +109,59 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// Column sums of a 32x32 block held one row per lane, packed-add version: lane L returns sum over lanes r of h_r[L].
+// Recursive halving: 31 shuffles; the adds are issued as f32x2 pairs.
+__device__ __forceinline__ float warp_colsum32_x2(const float2 (&h)[16], int lane) {
+  // h[q] = columns (2q, 2q+1).  Step 16 exchanges columns k <-> k+16, i.e. pairs q <-> q+8.
+  float2 a[8];
+  bool up = lane & 16;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float2 send = up ? h[q] : h[q + 8], keep = up ? h[q + 8] : h[q];
+    float2 got;
+    got.x = __shfl_xor_sync(0xffffffffu, send.x, 16);
+    got.y = __shfl_xor_sync(0xffffffffu, send.y, 16);
+    a[q] = __fadd2_rn(keep, got);
+  }
+  float2 b[4];
+  up = lane & 8;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float2 send = up ? a[q] : a[q + 4], keep = up ? a[q + 4] : a[q];
+    float2 got;
+    got.x = __shfl_xor_sync(0xffffffffu, send.x, 8);
+    got.y = __shfl_xor_sync(0xffffffffu, send.y, 8);
+    b[q] = __fadd2_rn(keep, got);
+  }
+  float2 c[2];
+  up = lane & 4;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const float2 send = up ? b[q] : b[q + 2], keep = up ? b[q + 2] : b[q];
+    float2 got;
+    got.x = __shfl_xor_sync(0xffffffffu, send.x, 4);
+    got.y = __shfl_xor_sync(0xffffffffu, send.y, 4);
+    c[q] = __fadd2_rn(keep, got);
+  }
+  up = lane & 2;
+  {
+    const float2 send = up ? c[0] : c[1], keep = up ? c[1] : c[0];
+    float2 got;
+    got.x = __shfl_xor_sync(0xffffffffu, send.x, 2);
+    got.y = __shfl_xor_sync(0xffffffffu, send.y, 2);
+    c[0] = __fadd2_rn(keep, got);
+  }
+  up = lane & 1;
+  const float send = up ? c[0].x : c[0].y, keep = up ? c[0].y : c[0].x;
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
 // Column sums of a 32x32 block held one row per lane: lane L returns sum over lanes r of h_r[L]
 // (recursive halving: 31 shuffles instead of 32 five-step reductions).
 __device__ __forceinline__ float warp_colsum32(const float (&h)[32], int lane) {
@@ -488,7 +541,7 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0),
     // ------------------------------------------------------------------ epilogue (8 warps per CTA), thread = row of THIS CTA's block
     const int quad = warp & 3, chalf = warp >> 2;
     constexpr int CH = BN / 2;
-    const float s2 = p.s * kLog2e, ms2 = p.m * p.s * kLog2e;
+    const float s2 = p.s * kLog2e;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     constexpr int kNoLabel = -(1 << 30);
     uint8_t* gbuf = smem_g + warp * kGBox;
@@ -527,48 +580,61 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0),
       tc_fence_after();
       const int col0 = ct * BN;
       const bool tile_has_oob = col0 + BN > p.n_classes;
-#pragma unroll 1
-      for (int c = chalf * CH; c < (chalf + 1) * CH; c += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(tmem_base + lane_base + acc * BN + c, v);
-        tmem_ld_wait();
+      // one 32-column group; the TMEM load of the next group is in flight while this one is processed
+      auto process_group = [&](uint32_t (&v)[32], const int c) {
         const int cb = col0 + c;
-        float z[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) z[j] = __uint_as_float(v[j]) * s2;
-        const int hit = my_label - cb;
-        if (hit >= 0 && hit < 32) {
+        const int hit = my_label - cb;                       // in [0,32) iff this row's target class is in this column group
+        const bool has_hit = hit >= 0 && hit < 32;
+        if (has_hit) {                                       // rare: fold the margin into the cosine, v[hit] -= m
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (j == hit) {
-            z[j] -= ms2;
             if (MODE == MODE_STATS) p.target_logit[row] = p.s * (__uint_as_float(v[j]) - p.m);
+            v[j] = __float_as_uint(__uint_as_float(v[j]) - p.m);
           }
         }
         if (MODE == MODE_STATS) {
           if (tile_has_oob) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (cb + j >= p.n_classes) z[j] = -INFINITY;
+            for (int j = 0; j < 32; ++j) if (cb + j >= p.n_classes) v[j] = __float_as_uint(-INFINITY);
           }
-          float cm = z[0];
+          // group max on the raw cosines (s > 0), three inputs per instruction
+          float cm = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
 #pragma unroll
-          for (int j = 1; j < 32; ++j) cm = fmaxf(cm, z[j]);
+          for (int j = 3; j < 31; j += 2) cm = fmax3(cm, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+          cm = fmaxf(cm, __uint_as_float(v[31])) * s2;
           if (cm > -INFINITY) {
             const float nm = fmaxf(run_m, cm);
-            float s0 = 0.f, s1 = 0.f;
+            const float2 s2v = make_float2(s2, s2), nmv = make_float2(-nm, -nm);
+            float2 sum = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) { s0 += fast_exp2(z[j] - nm); s1 += fast_exp2(z[j + 1] - nm); }
-            run_l = run_l * fast_exp2(run_m - nm) + (s0 + s1);
+            for (int j = 0; j < 32; j += 2) {
+              const float2 zz = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), s2v, nmv);
+              sum = __fadd2_rn(sum, make_float2(fast_exp2(zz.x), fast_exp2(zz.y)));
+            }
+            run_l = run_l * fast_exp2(run_m - nm) + (sum.x + sum.y);
             run_m = nm;
           }
         } else {
+          // G = (exp2(s2 cos - M2) * rS - onehot) * g_scale, packed two columns per instruction
+          const float2 s2v = make_float2(s2, s2), m2v = make_float2(-M2, -M2);
+          const float gs = rS * p.g_scale;
+          const float2 gsv = make_float2(gs, gs);
+          float2 g[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float2 zz = __ffma2_rn(make_float2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), s2v, m2v);
+            g[q] = __fmul2_rn(make_float2(fast_exp2(zz.x), fast_exp2(zz.y)), gsv);
+          }
+          if (has_hit) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              if (2 * q == hit) g[q].x -= p.g_scale;
+              if (2 * q + 1 == hit) g[q].y -= p.g_scale;
+            }
+          }
           uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float g0 = fast_exp2(z[j] - M2) * rS, g1 = fast_exp2(z[j + 1] - M2) * rS;
-            if (j == hit) g0 -= 1.0f;
-            if (j + 1 == hit) g1 -= 1.0f;
-            pk[j >> 1] = pack_bf16x2(g0 * p.g_scale, g1 * p.g_scale);
-          }
+          for (int q = 0; q < 16; ++q) pk[q] = pack_bf16x2(g[q].x, g[q].y);
           // G -> swizzled staging box [32 rows x 64 classes]; one TMA store per 64 classes into the blocked scratch
           const int half = (c >> 5) & 1;
           if (half == 0) {
@@ -586,23 +652,40 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0),
               tma_store_commit();
             }
           }
-          if (p.radial_mode) {
-            float h[32];
+          if (p.radial_mode) {                              // radial_j += sum over this warp's 32 rows of G_ij cos_ij
+            if (has_hit) {                                  // undo the margin: the projection uses the plain cosine
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              h[j] = __uint_as_float(pk[j >> 1] << 16) * __uint_as_float(v[j]);
-              h[j + 1] = __uint_as_float(pk[j >> 1] & 0xffff0000u) * __uint_as_float(v[j + 1]);
+              for (int j = 0; j < 32; ++j) if (j == hit) v[j] = __float_as_uint(__uint_as_float(v[j]) + p.m);
             }
-            const float cs = warp_colsum32(h, lane);
+            float2 h[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) h[q] = __fmul2_rn(g[q], make_float2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])));
+            const float cs = warp_colsum32_x2(h, lane);
             if (p.radial_mode > 1 && cb + lane < p.n_classes) atomicAdd(p.radial + cb + lane, cs);
           }
+        }
+      };
+      {
+        constexpr int NG = CH / 32;
+        static_assert(NG % 2 == 0, "two groups per pipeline round");
+        const uint32_t t_base = tmem_base + lane_base + acc * BN + chalf * CH;
+        uint32_t va[32], vb[32];
+        tmem_ld_x32(t_base, va);
+#pragma unroll
+        for (int gi = 0; gi < NG; gi += 2) {
+          tmem_ld_wait();
+          tmem_ld_x32(t_base + (gi + 1) * 32, vb);
+          process_group(va, chalf * CH + gi * 32);
+          tmem_ld_wait();
+          if (gi + 2 < NG) tmem_ld_x32(t_base + (gi + 2) * 32, va);
+          process_group(vb, chalf * CH + (gi + 1) * 32);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {                                     // the accumulator lives in both CTAs; the leader's MMA warp waits for all 16 warps
         if (leader) mbar_arrive(&tmem_empty[acc]);
-        else mbar_arrive_cluster_addr(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+        else mbar_arrive_cluster_addr_relaxed(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
       }
     }
     if (MODE == MODE_STATS && cur_rp >= 0 && row_ok) {
