@@ -174,6 +174,9 @@ def run_ours(args):
     if args.fwd_overlap:
         v = [int(t) for t in args.fwd_overlap.split(",")] + [0]
         N.lib.pfc_set_fwd_overlap(v[0], v[1])
+    if args.prefetch:
+        v = [int(t) for t in args.prefetch.split(",")]
+        N.lib.pfc_set_prefetch(v[0], v[1], v[2])
     if args.pipe:
         v = [int(t) for t in args.pipe.split(",")] + [0, 0, 0, 0]
         N.lib.pfc_set_pipeline(v[0], v[1], v[2], v[3], v[4])
@@ -311,6 +314,7 @@ def main():
     ap.add_argument("--graph", type=int, default=-1, help="1/0: replay the backward as a cached CUDA graph (library default: 1)")
     ap.add_argument("--pipe", default="", help="backward chain pipeline: 'on,smG,smDx,smDw,ring' (e.g. 1,56,32,60,3) or 0")
     ap.add_argument("--fwd-overlap", default="", help="fused forward: 'chunks,normalize_blocks_per_sm' (e.g. 6,2)")
+    ap.add_argument("--prefetch", default="", help="TMA L2 prefetch: 'logits,dx_distance,dw' (e.g. 1,6,1)")
     ap.add_argument("--chunk-mb", type=int, default=0, help="bf16 G scratch per backward chunk in MiB (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":

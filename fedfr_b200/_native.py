@@ -63,6 +63,8 @@ lib.pfc_set_clusters.restype = _i32
 lib.pfc_set_clusters.argtypes = [_i32, _i32]
 lib.pfc_set_logits_tile.restype = _i32
 lib.pfc_set_logits_tile.argtypes = [_i32]
+lib.pfc_set_prefetch.restype = _i32
+lib.pfc_set_prefetch.argtypes = [_i32, _i32, _i32]
 lib.pfc_set_fwd_overlap.restype = _i32
 lib.pfc_set_fwd_overlap.argtypes = [_i32, _i32]
 lib.pfc_set_pipeline.restype = _i32

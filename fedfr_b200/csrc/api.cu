@@ -21,6 +21,7 @@ void tc_set_debug(long long* p);
 void tc_set_radial_mode(int m);
 void tc_set_logits_pair(int on);
 void tc_set_graph(int on);
+void tc_set_prefetch(int logits, int dx, int dw);
 void tc_set_chunk_mb(int mb);
 void tc_set_pipeline(int on, int sm_g, int sm_dx, int sm_dw, int ring);
 int simt_fwd_num_partials(int64_t n_rows, int64_t n_classes);
@@ -124,6 +125,11 @@ int pfc_set_graph(int on) {   /* 1 = replay the backward as a cached CUDA graph 
 
 int pfc_set_pipeline(int on, int sm_g, int sm_dx, int sm_dw, int ring) {   /* concurrent G / dx / dw chains; SMs per chain (0 = keep) */
   tc_set_pipeline(on, sm_g, sm_dx, sm_dw, ring);
+  return 0;
+}
+
+int pfc_set_prefetch(int logits, int dx_distance, int dw) {   /* TMA L2 prefetch ahead of the smem rings */
+  tc_set_prefetch(logits, dx_distance, dw);
   return 0;
 }
 

@@ -85,6 +85,13 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// pull one box of a tiled tensor into L2 (no shared memory, no barrier): issued a few tiles ahead of the matching
+// tma_load_2d so that the load itself only pays the L2 latency and a shallow smem ring keeps HBM busy
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // smem -> global tile store (bulk async group); the tensor map clips rows/columns outside the tensor
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),

@@ -101,6 +101,7 @@ struct LogitsParams {
   float g_scale;             // s / total_batch
   float* radial;             // [n_classes] += sum_i G_ij cos_ij  (= w_hat_j . dwh_j, the normalize-backward projection)
   int radial_mode;           // 2 = on (default); 0/1 are timing experiments (skip / no atomics)
+  int prefetch;              // 1: TMA L2 prefetch of the next class tile
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -488,6 +489,10 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0),
           cur_rp = rp;
           ++a_loads;
         }
+        if (p.prefetch && t + 1 < t1) {                       // this CTA's half of the next class tile -> L2
+          const int nct = (int)((t + 1) % p.n_ct);
+          for (int kb = 0; kb < n_kb; ++kb) tma_prefetch_2d(&tmap_w, kb * BK, nct * BN + (int)crank * BH);
+        }
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&empty[ps.stage], ps.phase ^ 1);
           if (leader) mbar_arrive_expect_tx(&full[ps.stage], 2 * kBStage);
@@ -708,6 +713,7 @@ struct DxParams {
   int n_rb, n_eh, ksplit;
   float* dx_part;          // [ksplit, n_rows, emb]
   int accumulate;
+  int prefetch;            // > 0: TMA L2 prefetch distance in k-blocks
 };
 
 template <int BN, int STAGES, int CS>
@@ -748,6 +754,18 @@ __global__ void __launch_bounds__(kThreads, 1) dx_kernel(const __grid_constant__
     if (lane == 0) {
       PipeState ps;
       for (int kb = kb0; kb < kb1; ++kb) {
+        if (p.prefetch && kb + p.prefetch < kb1) {          // k-block (kb + distance) -> L2 while the ring is still busy with kb
+          const int pk = kb + p.prefetch;
+          tma_prefetch_2d(&tmap_g, 0, (pk * p.n_rb + rb) * BM);
+          if (CS == 1) {
+#pragma unroll
+            for (int nb = 0; nb < BN / 64; ++nb) tma_prefetch_2d(&tmap_w, eh * BN + nb * 64, pk * BK);
+          } else {
+            constexpr int kPer = (BN / 64) / CS;
+#pragma unroll
+            for (int q = 0; q < kPer; ++q) tma_prefetch_2d(&tmap_w, eh * BN + ((int)crank * kPer + q) * 64, pk * BK);
+          }
+        }
         mbar_wait(&empty[ps.stage], ps.phase ^ 1);
         uint8_t* sa = smem + ps.stage * kStageBytes;
         uint8_t* sb = sa + kChunkBytes;
@@ -853,6 +871,7 @@ struct DwParams {
   const float* inv_norm;          // [n_classes]
   const float* radial;            // [n_classes]
   int accumulate;
+  int prefetch;                   // 1: TMA L2 prefetch of the next tile's G / w_hat boxes
   long long* dbg;                 // optional cycle counters of CTA 0 (developer instrumentation), else nullptr
 };
 
@@ -909,6 +928,13 @@ __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__
       PipeState ps;
       for (int i = 0; more(i); ++i) {
         const int ct = tile_of(i), hs = i % NH;
+        if (p.prefetch && hs == 0 && more(i + NH)) {          // G boxes of the next class tile -> L2 (HBM latency off the smem ring)
+          const int nt = tile_of(i + NH);
+          for (int kb = 0; kb < n_kb; ++kb) {
+            tma_prefetch_2d(&tmap_g, 0, ((2 * nt) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64);
+            tma_prefetch_2d(&tmap_g, 0, ((2 * nt + 1) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64);
+          }
+        }
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&empty[ps.stage], ps.phase ^ 1);
           uint8_t* sa = smem + ps.stage * kStageBytes;
@@ -976,6 +1002,11 @@ __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__
       mbar_arrive_expect_tx(wbar, kWWarp);
 #pragma unroll
       for (int nb = 0; nb < NBOX; ++nb) tma_load_2d(wbuf + nb * kWBox, &tmap_wh, wbar, hs * EN + nb * 64, cls0);
+      if (p.prefetch && more(i + 1)) {                    // and the rows of the item after that -> L2
+        const int n0 = tile_of(i + 1) * BM + warp * 32, nh = (i + 1) % NH;
+#pragma unroll
+        for (int nb = 0; nb < NBOX; ++nb) tma_prefetch_2d(&tmap_wh, nh * EN + nb * 64, n0);
+      }
     };
     if (lane == 0 && more(0)) issue_w(0);
     for (int it = 0; more(it); ++it) {
@@ -1224,6 +1255,7 @@ size_t tc_bwd_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb) {
 }
 
 static int g_radial_mode = 2;
+static int g_prefetch[3] = {0, 0, 0};               // TMA L2 prefetch knobs: logits (0/1), dx (k-block distance), dw (0/1); measured slower, off
 static long long* g_dbg = nullptr;                   // developer instrumentation buffer (device), see pfc_set_debug_buffer
 static int g_dx_cluster = 2, g_dw_cluster = 2;      // cluster sizes (1, 2 or 4); tuning knobs
 
@@ -1370,7 +1402,7 @@ static int tc_bwd_enqueue(const void* x, const void* w_hat, const float* inv_nor
     LogitsParams lp{};
     lp.label = label; lp.n_rows = (int)n_rows; lp.n_classes = (int)cc; lp.class_base = (int)c0; lp.emb = emb;
     lp.n_rb = n_rb; lp.n_ct = (int)((cc + bn - 1) / bn); lp.s = s; lp.m = m;
-    lp.row_max = row_max; lp.row_sum = row_sum; lp.g = g; lp.ldg = pl.ldg; lp.g_scale = s * inv_total_batch; lp.radial = radial + c0; lp.radial_mode = g_radial_mode;
+    lp.row_max = row_max; lp.row_sum = row_sum; lp.g = g; lp.ldg = pl.ldg; lp.g_scale = s * inv_total_batch; lp.radial = radial + c0; lp.radial_mode = g_radial_mode; lp.prefetch = g_prefetch[0];
     const uint64_t g_rows = (uint64_t)(pl.ldg / 64) * n_rb * BM;                              // rows of the blocked scratch viewed as [g_rows, 64]
     prof_begin(PH_GRAD, sG);
     if (g_logits_pair) {
@@ -1395,7 +1427,7 @@ static int tc_bwd_enqueue(const void* x, const void* w_hat, const float* inv_nor
     if (int rc = make_tmap_bf16_2d(&tw_mn, wh + c0 * emb, cc, emb, emb, 64)) return rc;     // B MN-major boxes [64 classes x 64 e]
     DxParams dp{};
     dp.n_rows = (int)n_rows; dp.n_classes = (int)cc; dp.emb = emb; dp.n_rb = n_rb; dp.n_eh = pl.n_eh; dp.ksplit = pl.ksplit;
-    dp.dx_part = dx_part; dp.accumulate = chunk_idx > 0;
+    dp.dx_part = dx_part; dp.accumulate = chunk_idx > 0; dp.prefetch = g_prefetch[1];
     int dcs = g_dx_cluster;
     if (pl.dx_bn < 128) dcs = 1;
     if (pl.dx_bn == 128 && dcs > 2) dcs = 2;
@@ -1419,7 +1451,7 @@ static int tc_bwd_enqueue(const void* x, const void* w_hat, const float* inv_nor
     if (int rc2 = make_tmap_bf16_2d(&tg_mn, g, g_rows, 64, 64, 64)) return rc2;              // A MN-major boxes [64 rows x 64 classes] = half a block
     DwParams wp{};
     wp.n_rows = (int)n_rows; wp.n_classes = (int)cc; wp.emb = emb; wp.n_ct = (int)((cc + BM - 1) / BM); wp.n_rb = n_rb;
-    wp.inv_norm = inv_norm + c0; wp.radial = radial + c0; wp.accumulate = accumulate_dw; wp.dbg = g_dbg;
+    wp.inv_norm = inv_norm + c0; wp.radial = radial + c0; wp.accumulate = accumulate_dw; wp.dbg = g_dbg; wp.prefetch = g_prefetch[2];
     CUtensorMap twh_e, tdw_e;
     if (int rc3 = make_tmap_bf16_2d(&twh_e, wh + c0 * emb, cc, emb, emb, 32)) return rc3;      // epilogue: per-warp [32 classes x 64 e]
     if (int rc3 = make_tmap_f32_2d(&tdw_e, dw + c0 * emb, cc, emb, emb, 32)) return rc3;       // epilogue: per-warp [32 classes x 32 e] fp32
@@ -1537,7 +1569,7 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
   kb.add(1).add(x).add(w_hat).add(inv_norm).add(label).add(row_max).add(row_sum).add(dx).add(dw).add(workspace).add(n_rows).add(n_classes)
       .add(workspace_bytes).add(emb).add(accumulate_dw).add(s).add(m).add(inv_total_batch).add(g_fwd_bn).add(g_logits_pair).add(g_radial_mode)
       .add(g_dx_cluster).add(g_dw_cluster).add(make_bwd_plan(n_rows, n_classes, emb).chunk).add(g_pipe).add(g_ring).add(g_split[0])
-      .add(g_split[1]).add(g_split[2]);
+      .add(g_split[1]).add(g_split[2]).add(g_prefetch[0]).add(g_prefetch[1]).add(g_prefetch[2]);
   return run_cached_graph(kb, st, enqueue);
 }
 
@@ -1580,7 +1612,7 @@ static int tc_normalize_fwd_enqueue(const float* w, const int64_t* index, const 
     LogitsParams p{};
     p.label = label; p.n_rows = (int)n_rows; p.n_classes = (int)cc; p.class_base = (int)c0; p.emb = emb;
     p.n_rb = (int)((n_rows + BM - 1) / BM); p.n_ct = (int)((cc + bn - 1) / bn);
-    p.s = s; p.m = m; p.part_max = part_max; p.part_sum = part_sum; p.target_logit = target_logit; p.accumulate_stats = k > 0;
+    p.s = s; p.m = m; p.part_max = part_max; p.part_sum = part_sum; p.target_logit = target_logit; p.accumulate_stats = k > 0; p.prefetch = g_prefetch[0];
     if (has_next) {
       p.norm_w = index ? w : w + n0 * emb; p.norm_index = index ? index + n0 : nullptr; p.norm_rows = chunk_len(n0);
       p.norm_out = wh + n0 * emb; p.norm_inv = inv_norm + n0;
@@ -1608,7 +1640,7 @@ int tc_normalize_fwd(const float* w, const int64_t* index, const void* x, const 
   if (!graph_eligible(st)) return enqueue(st);
   KeyBuilder kb;
   kb.add(2).add(w).add(index).add(x).add(label).add(n_rows).add(n_classes).add(emb).add(s).add(m).add(w_hat).add(inv_norm).add(part_max)
-      .add(part_sum).add(target_logit).add(g_fwd_bn).add(g_logits_pair).add(g_fwd_chunks).add(g_norm_blocks_per_sm);
+      .add(part_sum).add(target_logit).add(g_fwd_bn).add(g_logits_pair).add(g_fwd_chunks).add(g_norm_blocks_per_sm).add(g_prefetch[0]);
   return run_cached_graph(kb, st, enqueue);
 }
 
@@ -1618,6 +1650,7 @@ void tc_set_fwd_overlap(int chunks, int norm_blocks_per_sm) {
 }
 
 void tc_set_graph(int on) { g_use_graph = on ? 1 : 0; }
+void tc_set_prefetch(int logits, int dx, int dw) { g_prefetch[0] = logits; g_prefetch[1] = dx; g_prefetch[2] = dw; }
 void tc_set_pipeline(int on, int sm_g, int sm_dx, int sm_dw, int ring) {
   g_pipe = on ? 1 : 0;
   if (sm_g > 0 && sm_dx > 0 && sm_dw > 0) { g_split[0] = sm_g; g_split[1] = sm_dx; g_split[2] = sm_dw; }
