@@ -124,6 +124,8 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
+    if args.workload == "c5":
+        raise SystemExit("--impl reference times the PartialFC path (c2/c3/c4); the FedAvg CPU baseline is the cpu_baseline of --workload c5")
     B, C, E, sr = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
     C_sample = 32768                 # bounded sample: ~0.3 s of host work per step
@@ -138,6 +140,156 @@ def run_reference(args):
             "config": {"workload": f"{args.workload}: PartialFC CosFace fwd+bwd, B={B}/GPU, {C} classes, E={E}, sample_rate={sr}, s={S}, m={M}"},
             "cpu_baseline": cpu, "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def iresnet50_shapes():
+    """(name, shape, is_float) with the layout of the reference's iresnet50 state_dict (backbones/iresnet.py:60-204, layers 3,4,14,3):
+    475 tensors, 43,629,071 elements, 79 of them int64 num_batches_tracked scalars."""
+    out = []
+
+    def bn(p, c):
+        out.extend([(p + ".weight", (c,), True), (p + ".bias", (c,), True), (p + ".running_mean", (c,), True), (p + ".running_var", (c,), True),
+                    (p + ".num_batches_tracked", (), False)])
+    out.append(("conv1.weight", (64, 3, 3, 3), True))
+    bn("bn1", 64)
+    out.append(("prelu.weight", (64,), True))
+    inpl = 64
+    for li, (planes, blocks) in enumerate(zip((64, 128, 256, 512), (3, 4, 14, 3)), 1):
+        for b in range(blocks):
+            p = f"layer{li}.{b}"
+            bn(p + ".bn1", inpl)
+            out.append((p + ".conv1.weight", (planes, inpl, 3, 3), True))
+            bn(p + ".bn2", planes)
+            out.append((p + ".prelu.weight", (planes,), True))
+            out.append((p + ".conv2.weight", (planes, planes, 3, 3), True))
+            bn(p + ".bn3", planes)
+            if b == 0:
+                out.append((p + ".downsample.0.weight", (planes, inpl, 1, 1), True))
+                bn(p + ".downsample.1", planes)
+            inpl = planes
+    bn("bn2", 512)
+    out.append(("fc.weight", (512, 512 * 7 * 7), True))
+    out.append(("fc.bias", (512,), True))
+    bn("features", 512)
+    out.append(("converter.weight", (512, 512), True))        # the transformation layer (client.py:29-36), BASELINE configs[4]
+    out.append(("converter.bias", (512,), True))
+    return out
+
+
+def run_fedavg(args):
+    """--workload c5: server.py FedPavg over 40 client state_dicts (iresnet50 + transformation layer), BASELINE configs[4].
+    value = algorithmic GB/s ((K+1) * N * 4 bytes per call) with the dicts resident in HBM; clients are sharded over the
+    ranks (K/W each) and the partial sums meet in one all-reduce."""
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as G
+    G.build()
+    import fedfr_b200
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    K = 40
+    shapes = iresnet50_shapes()
+    mine = list(range(rank, K, world))
+    torch.manual_seed(100)
+    base = {n: (torch.randn(sh, device=dev) if f else torch.zeros(sh, dtype=torch.int64, device=dev)) for n, sh, f in shapes}
+    models = [{n: (v + 0.01 * torch.randn_like(v)) if v.dtype == torch.float32 else v + i for n, v in base.items()} for i in mine]
+    weights = [6000 + 37 * i for i in mine]
+    n_elem = sum(v.numel() for v in base.values())
+    alg_bytes = (K + 1) * n_elem * 4.0
+
+    def step():
+        if world == 1:
+            return fedfr_b200.FedPavg(models, weights)
+        return fedfr_b200.FedPavg_sharded(models, weights)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    from fedfr_b200 import _native as N
+    l0 = N.lib.pfc_launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = N.lib.pfc_launch_count() - l0
+    # the C-ABI call alone (table upload + the one kernel), re-launched from the tables the last call staged
+    from fedfr_b200 import fedavg as FA
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        FA.relaunch_last()
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / args.steps
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    # end to end: the dicts start in pinned HOST memory (where FedFR keeps them, client.py:469), result read back
+    e2e_ms = None
+    if world == 1:
+        host_models = [{n: v.cpu().pin_memory() for n, v in m.items()} for m in models[:8]]      # bounded: 8 of the 40 clients
+        fedfr_b200.FedPavg(host_models, weights[:8])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        o = fedfr_b200.FedPavg(host_models, weights[:8])
+        _ = {n: v.cpu() for n, v in o.items()}
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import partial_fc_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        cm = [{n: v.cpu().numpy() for n, v in m.items()} for m in models[:8]]
+        t0 = time.perf_counter()
+        O.fedpavg(cm, weights[:8])
+        t = time.perf_counter() - t0
+        cpu = {"value": 9 * n_elem * 4.0 / t / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+               "sample": "oracle port of server.FedPavg (numpy, sequential fp32 mul+add), 8 of the 40 clients"}
+    line = {"metric": "FedPavg weighted average, algorithmic GB/s ((K+1)*N*4 bytes)", "value": gbs, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"c5: FedPavg of {K} client state_dicts (iresnet50 475 tensors + transformation layer, {n_elem} elements each), "
+                                   f"clients sharded over {world} GPU(s)", "l2": "inputs larger than L2 (7 GB of client tensors)"},
+            "e2e": None if e2e_ms is None else {"value": 9 * n_elem * 4.0 / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_ms,
+                                                "h2d_bytes_per_step": 8 * n_elem * 4, "d2h_bytes_per_step": n_elem * 4,
+                                                "sample": "8 of the 40 clients from pinned host memory, result copied back"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "fedavg_kernel (fedavg_weighted_sum call: table upload + one launch)",
+                         "achieved": (len(mine) + 1) * n_elem * 4.0 / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": (len(mine) + 1) * n_elem * 4.0 / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                         "ms_per_launch": kernel_ms, "peak_source": peaks["source"] + " copy bandwidth",
+                         "note": "value is the whole FedPavg(state_dicts) call, bound by per-tensor Python work over K x 477 tensors"},
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def run_ours(args):
@@ -304,7 +456,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c5"])
     ap.add_argument("--logits-tile", type=int, default=0)
     ap.add_argument("--radial-mode", type=int, default=2)
     ap.add_argument("--logits-pair", type=int, default=-1)
@@ -319,6 +471,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_fedavg(args)
     else:
         run_ours(args)
 

@@ -1,8 +1,8 @@
 """fedfr_b200 -- B200-native (sm_100a) PartialFC CosFace head + FedAvg, drop-in for jackie840129/FedFR's
 ``partial_fc.PartialFC`` / ``losses.CosFace`` / ``server.FedPavg`` hot path.  See DESIGN.md."""
 from . import _native  # noqa: F401  (fails loudly when the CUDA extension has not been built)
-from .fedavg import FedAvg_on_FC, FedPavg
+from .fedavg import FedAvg_on_FC, FedPavg, FedPavg_sharded
 from .losses import CosFace
 from .partial_fc import PartialFC
 
-__all__ = ["PartialFC", "CosFace", "FedPavg", "FedAvg_on_FC"]
+__all__ = ["PartialFC", "CosFace", "FedPavg", "FedAvg_on_FC", "FedPavg_sharded"]

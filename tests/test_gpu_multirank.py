@@ -75,3 +75,38 @@ def test_two_gpu_matches_reference(name, port, check_mode):
     for r in (0, 1):
         for k, v in ret[r].items():
             assert v < tol, (r, k, v, dict(ret[r]))
+
+
+def _fedavg_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import fedfr_b200
+        dev = torch.device("cuda", rank)
+        g = torch.Generator().manual_seed(11)
+        K = 6
+        base = {"a.weight": torch.randn(300, 77, generator=g), "bn.num_batches_tracked": torch.tensor(5, dtype=torch.int64),
+                "b.bias": torch.randn(1003, generator=g)}
+        models = [{n: (v + 0.01 * torch.randn(v.shape, generator=g)) if v.dtype == torch.float32 else v + i for n, v in base.items()}
+                  for i in range(K)]
+        weights = [100 + 7 * i for i in range(K)]
+        mine = list(range(rank, K, world))
+        out = fedfr_b200.FedPavg_sharded([{n: v.to(dev) for n, v in models[i].items()} for i in mine], [weights[i] for i in mine])
+        full = fedfr_b200.FedPavg([{n: v.to(dev) for n, v in m.items()} for m in models], weights)      # sequential order, one GPU
+        ret[rank] = max(float((out[n] - full[n]).abs().max() / full[n].abs().max().clamp_min(1e-20)) for n in full)
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_fedavg():
+    import __graft_entry__ as g
+    g.build()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_fedavg_worker, args=(2, 29761, ret), nprocs=2, join=True)
+    assert max(ret.values()) < 5e-6, dict(ret)
