@@ -714,6 +714,7 @@ struct DxParams {
   float* dx_part;          // [ksplit, n_rows, emb]
   int accumulate;
   int prefetch;            // > 0: TMA L2 prefetch distance in k-blocks
+  int strided;             // 1: k-blocks ks, ks + ksplit, ... instead of a contiguous slice
 };
 
 template <int BN, int STAGES, int CS>
@@ -736,7 +737,11 @@ __global__ void __launch_bounds__(kThreads, 1) dx_kernel(const __grid_constant__
   const int ks = grp % p.ksplit, eh = (grp / p.ksplit) % p.n_eh, rb = (grp / (p.ksplit * p.n_eh)) * CS + (int)crank;
   constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1);
   const int n_kb_total = (p.n_classes + BK - 1) / BK;
-  const int kb0 = (int)((int64_t)n_kb_total * ks / p.ksplit), kb1 = (int)((int64_t)n_kb_total * (ks + 1) / p.ksplit);
+  // k-blocks of this CTA: a contiguous slice, or (p.strided) every ksplit-th block so that all CTAs sweep the class axis
+  // together -- in step with a dw kernel running beside it, whose reads of the same G / w_hat tiles then hit L2
+  const int kstep = p.strided ? p.ksplit : 1;
+  const int kb0 = p.strided ? ks : (int)((int64_t)n_kb_total * ks / p.ksplit);
+  const int kb1 = p.strided ? n_kb_total : (int)((int64_t)n_kb_total * (ks + 1) / p.ksplit);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CS); }
@@ -753,9 +758,9 @@ __global__ void __launch_bounds__(kThreads, 1) dx_kernel(const __grid_constant__
   if (warp == 4) {
     if (lane == 0) {
       PipeState ps;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        if (p.prefetch && kb + p.prefetch < kb1) {          // k-block (kb + distance) -> L2 while the ring is still busy with kb
-          const int pk = kb + p.prefetch;
+      for (int kb = kb0; kb < kb1; kb += kstep) {
+        if (p.prefetch && kb + p.prefetch * kstep < kb1) {  // k-block (kb + distance) -> L2 while the ring is still busy with kb
+          const int pk = kb + p.prefetch * kstep;
           tma_prefetch_2d(&tmap_g, 0, (pk * p.n_rb + rb) * BM);
           if (CS == 1) {
 #pragma unroll
@@ -789,7 +794,7 @@ __global__ void __launch_bounds__(kThreads, 1) dx_kernel(const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, true);
       PipeState ps;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      for (int kb = kb0; kb < kb1; kb += kstep) {
         mbar_wait(&full[ps.stage], ps.phase);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + ps.stage * kStageBytes);
@@ -1194,16 +1199,16 @@ struct BwdPlan {
 };
 
 static int64_t g_chunk_budget_mb;                   // 0 = default
-static int g_pipe = 0;                              // 1 = concurrent chains (see pfc_set_pipeline)
-static int g_split[3] = {56, 32, 60};               // SMs for the G / dx / dw chains in pipelined mode
-static int g_ring = 3;
+static int g_pipe = 1;                              // 1 = concurrent chains (see pfc_set_pipeline)
+static int g_split[3] = {148, 64, 84};              // SMs for the G / dx / dw chains in pipelined mode
+static int g_ring = 1;                              // G buffers; 1 = G alone on every SM, then dx || dw sweep the chunk in step
 
 static BwdPlan make_bwd_plan(int64_t n_rows, int64_t n_classes, int emb) {
   BwdPlan pl{};
   const int64_t n_rb = (n_rows + BM - 1) / BM;
   const int64_t c_pad = (n_classes + 255) / 256 * 256;
   const int64_t row_bytes = n_rb * BM * 2;           // bytes of G scratch per class
-  int64_t budget_seq = 256ll << 20, budget_pipe = 32ll << 20;
+  int64_t budget_seq = 512ll << 20, budget_pipe = 32ll << 20;
   if (const char* e = getenv("FEDFR_G_CHUNK_MB")) { long v = atol(e); if (v > 0) budget_seq = budget_pipe = (int64_t)v << 20; }
   if (g_chunk_budget_mb > 0) budget_seq = budget_pipe = g_chunk_budget_mb << 20;
   auto chunk_for = [&](int64_t budget) {
@@ -1427,7 +1432,7 @@ static int tc_bwd_enqueue(const void* x, const void* w_hat, const float* inv_nor
     if (int rc = make_tmap_bf16_2d(&tw_mn, wh + c0 * emb, cc, emb, emb, 64)) return rc;     // B MN-major boxes [64 classes x 64 e]
     DxParams dp{};
     dp.n_rows = (int)n_rows; dp.n_classes = (int)cc; dp.emb = emb; dp.n_rb = n_rb; dp.n_eh = pl.n_eh; dp.ksplit = pl.ksplit;
-    dp.dx_part = dx_part; dp.accumulate = chunk_idx > 0; dp.prefetch = g_prefetch[1];
+    dp.dx_part = dx_part; dp.accumulate = chunk_idx > 0; dp.prefetch = g_prefetch[1]; dp.strided = pl.pipelined ? 1 : 0;
     int dcs = g_dx_cluster;
     if (pl.dx_bn < 128) dcs = 1;
     if (pl.dx_bn == 128 && dcs > 2) dcs = 2;
