@@ -329,6 +329,8 @@ def run_ours(args):
     if args.prefetch:
         v = [int(t) for t in args.prefetch.split(",")]
         N.lib.pfc_set_prefetch(v[0], v[1], v[2])
+    if args.dx_pair >= 0:
+        N.lib.pfc_set_dx_pair(args.dx_pair)
     if args.pipe:
         v = [int(t) for t in args.pipe.split(",")] + [0, 0, 0, 0]
         N.lib.pfc_set_pipeline(v[0], v[1], v[2], v[3], v[4])
@@ -467,6 +469,7 @@ def main():
     ap.add_argument("--pipe", default="", help="backward chain pipeline: 'on,smG,smDx,smDw,ring' (e.g. 1,56,32,60,3) or 0")
     ap.add_argument("--fwd-overlap", default="", help="fused forward: 'chunks,normalize_blocks_per_sm' (e.g. 6,2)")
     ap.add_argument("--prefetch", default="", help="TMA L2 prefetch: 'logits,dx_distance,dw' (e.g. 1,6,1)")
+    ap.add_argument("--dx-pair", type=int, default=-1, help="1/0: CTA-pair dx kernel")
     ap.add_argument("--chunk-mb", type=int, default=0, help="bf16 G scratch per backward chunk in MiB (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":

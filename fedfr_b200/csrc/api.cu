@@ -21,6 +21,7 @@ void tc_set_debug(long long* p);
 void tc_set_radial_mode(int m);
 void tc_set_logits_pair(int on);
 void tc_set_graph(int on);
+void tc_set_dx_pair(int on);
 void tc_set_prefetch(int logits, int dx, int dw);
 void tc_set_chunk_mb(int mb);
 void tc_set_pipeline(int on, int sm_g, int sm_dx, int sm_dw, int ring);
@@ -130,6 +131,11 @@ int pfc_set_pipeline(int on, int sm_g, int sm_dx, int sm_dw, int ring) {   /* co
 
 int pfc_set_prefetch(int logits, int dx_distance, int dw) {   /* TMA L2 prefetch ahead of the smem rings */
   tc_set_prefetch(logits, dx_distance, dw);
+  return 0;
+}
+
+int pfc_set_dx_pair(int on) {   /* 1 = CTA-pair dx kernel when Bt % 512 == 0 (default), 0 = single-CTA kernel */
+  tc_set_dx_pair(on);
   return 0;
 }
 

@@ -847,6 +847,132 @@ __global__ void __launch_bounds__(kThreads, 1) dx_kernel(const __grid_constant__
   if (warp == 5) tmem_dealloc<BN>(tmem_base);
 }
 
+// ================================================================================================
+// dx kernel, CTA-pair version (cta_group::2), used when the gathered batch is a multiple of 512 rows.
+//   A pair owns a row quad (4 row blocks = 512 rows), one e-half (N = 256) and a set of k-blocks (64 classes each).
+//   Two accumulators live in TMEM for the whole kernel: acc 0 = row blocks (4q, 4q+1), acc 1 = (4q+2, 4q+3); CTA r of
+//   the pair holds rows of blocks 4q + r and 4q + 2 + r.  Per k-block a CTA receives its two G boxes (2 x 16 KB) and
+//   HALF of the w_hat tile (its 128 e-columns, 16 KB): 48 KB per 1024 MMA cycles, half of what the single-CTA kernel
+//   needs -- that kernel is bound by L2 -> SM delivery -- and every w_hat byte is fetched once per row quad.
+// ================================================================================================
+template <int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) dx2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_w,
+                                                          const DxParams p) {
+  constexpr int BN = 256;
+  constexpr int kABytes = 2 * kChunkBytes;          // two G boxes [128 rows x 64 classes]
+  constexpr int kBBytes = 2 * kBoxBytes;            // w_hat [64 classes x 128 e] = two boxes
+  constexpr int kStageBytes = kABytes + kBBytes;    // 48 KB
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* full = bars;                 // leader only: both CTAs' TMA bytes land here
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int ks = pair % p.ksplit, eh = (pair / p.ksplit) % p.n_eh, quad = pair / (p.ksplit * p.n_eh);
+  const int rb0 = quad * 4 + (int)crank, rb1 = rb0 + 2;
+  const int n_kb_total = (p.n_classes + BK - 1) / BK;
+  const int kstep = p.strided ? p.ksplit : 1;
+  const int kb0 = p.strided ? ks : (int)((int64_t)n_kb_total * ks / p.ksplit);
+  const int kb1 = p.strided ? n_kb_total : (int)((int64_t)n_kb_total * (ks + 1) / p.ksplit);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) { prefetch_tmap(&tmap_g); prefetch_tmap(&tmap_w); }
+  if (warp == 5) tmem_alloc_2cta<2 * BN>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      PipeState ps;
+      for (int kb = kb0; kb < kb1; kb += kstep) {
+        mbar_wait(&empty[ps.stage], ps.phase ^ 1);
+        uint8_t* sa = smem + ps.stage * kStageBytes;
+        uint8_t* sb = sa + kABytes;
+        const uint32_t full_leader = mapa_u32(smem_u32(&full[ps.stage]), 0);
+        if (leader) mbar_arrive_expect_tx(&full[ps.stage], 2 * kStageBytes);
+        tma_load_2d_2cta(sa, &tmap_g, full_leader, 0, (kb * p.n_rb + rb0) * BM);
+        tma_load_2d_2cta(sa + kChunkBytes, &tmap_g, full_leader, 0, (kb * p.n_rb + rb1) * BM);
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+          tma_load_2d_2cta(sb + nb * kBoxBytes, &tmap_w, full_leader, eh * BN + (int)crank * 128 + nb * 64, kb * BK);
+        ps.advance(STAGES);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, false, true);
+      PipeState ps;
+      for (int kb = kb0; kb < kb1; kb += kstep) {
+        mbar_wait(&full[ps.stage], ps.phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + ps.stage * kStageBytes);
+        const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+        for (int acc = 0; acc < 2; ++acc) {
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t da = make_desc_sw128(a_addr + acc * kChunkBytes + kk * 32, 0, 1024);
+            const uint64_t db = make_desc_sw128(b_addr + kk * 2048, kBoxBytes, 1024);
+            umma_bf16_ss_2cta(tmem_base + acc * BN, da, db, idesc, (kb != kb0) || (kk != 0));
+          }
+        }
+        umma_commit_2cta(&empty[ps.stage], 3);
+        ps.advance(STAGES);
+      }
+      umma_commit_2cta(tmem_full, 3);
+    }
+  } else {
+    const bool have = kb1 > kb0;
+    if (have) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+#pragma unroll 1
+    for (int acc = 0; acc < 2; ++acc) {
+      const int row = (acc == 0 ? rb0 : rb1) * BM + threadIdx.x;
+      const bool row_ok = row < p.n_rows;
+      float* out = p.dx_part + ((int64_t)ks * p.n_rows + row) * p.emb + eh * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        if (have) {
+          tmem_ld_x32(tmem_base + lane_base + acc * BN + c, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0;
+        }
+        if (row_ok) {
+          float4* o = reinterpret_cast<float4*>(out + c);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 r = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                   __uint_as_float(v[4 * q + 3]));
+            if (p.accumulate) { float4 old = o[q]; r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w; }
+            o[q] = r;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 5) tmem_dealloc_2cta<2 * BN>(tmem_base);
+}
+
 __global__ void reduce_dx_kernel(const float4* __restrict__ part, int ksplit, int64_t n_vec, float4* __restrict__ dx) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
     float4 a = part[i];
@@ -1195,12 +1321,14 @@ struct BwdPlan {
   bool pipelined;
   int sm_g, sm_dx, sm_dw;   // SMs (CTAs) per chain
   int ksplit, n_eh, dx_bn;
+  bool dx_pair;             // CTA-pair dx kernel (row count a multiple of 512)
   size_t g_bytes, g_buf_bytes, dxp_bytes, radial_bytes;
 };
 
 static int64_t g_chunk_budget_mb;                   // 0 = default
+static int g_dx_pair = 1;                           // 1: CTA-pair dx kernel when the row count allows it
 static int g_pipe = 1;                              // 1 = concurrent chains (see pfc_set_pipeline)
-static int g_split[3] = {148, 64, 84};              // SMs for the G / dx / dw chains in pipelined mode
+static int g_split[3] = {148, 48, 100};             // SMs for the G / dx / dw chains in pipelined mode
 static int g_ring = 1;                              // G buffers; 1 = G alone on every SM, then dx || dw sweep the chunk in step
 
 static BwdPlan make_bwd_plan(int64_t n_rows, int64_t n_classes, int emb) {
@@ -1240,7 +1368,8 @@ static BwdPlan make_bwd_plan(int64_t n_rows, int64_t n_classes, int emb) {
   pl.sm_g = pl.pipelined ? g_split[0] : sms;
   pl.sm_dx = pl.pipelined ? g_split[1] : sms;
   pl.sm_dw = pl.pipelined ? g_split[2] : sms;
-  int64_t units = n_rb * pl.n_eh;
+  pl.dx_pair = g_dx_pair && g_logits_pair && emb >= 256 && n_rb % 4 == 0;
+  int64_t units = pl.dx_pair ? (n_rb / 4) * pl.n_eh * 2 : n_rb * pl.n_eh;      // CTAs per k-split
   int64_t ks = pl.sm_dx / units;
   if (ks < 1) ks = 1;
   const int64_t min_kb = ((chunk < n_classes ? chunk : n_classes) + BK - 1) / BK;
@@ -1289,6 +1418,12 @@ static int launch_dx_cs(const CUtensorMap& tg, const CUtensorMap& tw, const DxPa
   constexpr int STAGES = BN == 256 ? 4 : 6;
   const size_t smem = (size_t)STAGES * (kChunkBytes + (BN / 64) * kBoxBytes) + 1024 + 256;
   return launch_cluster(dx_kernel<BN, STAGES, CS>, grid, CS, smem, st, tg, tw, p);
+}
+
+static int launch_dx2(const CUtensorMap& tg, const CUtensorMap& tw, const DxParams& p, int grid, cudaStream_t st) {
+  constexpr int STAGES = 4;
+  const size_t smem = (size_t)STAGES * (2 * kChunkBytes + 2 * kBoxBytes) + 1024 + 256;
+  return launch_cluster(dx2_kernel<STAGES>, grid, 2, smem, st, tg, tw, p);
 }
 
 template <int BN>
@@ -1440,7 +1575,8 @@ static int tc_bwd_enqueue(const void* x, const void* w_hat, const float* inv_nor
     const int dgrid = n_rbg * dcs * pl.n_eh * pl.ksplit;
     int rc = 0;
     prof_begin(PH_DX, sX);
-    switch (pl.dx_bn) {
+    if (pl.dx_pair) rc = launch_dx2(tg_k, tw_mn, dp, (n_rb / 4) * pl.n_eh * pl.ksplit * 2, sX);
+    else switch (pl.dx_bn) {
       case 256: rc = launch_dx<256>(tg_k, tw_mn, dp, dgrid, dcs, sX); break;
       case 128: rc = launch_dx<128>(tg_k, tw_mn, dp, dgrid, dcs, sX); break;
       default: rc = launch_dx<64>(tg_k, tw_mn, dp, dgrid, dcs, sX); break;
@@ -1574,7 +1710,7 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
   kb.add(1).add(x).add(w_hat).add(inv_norm).add(label).add(row_max).add(row_sum).add(dx).add(dw).add(workspace).add(n_rows).add(n_classes)
       .add(workspace_bytes).add(emb).add(accumulate_dw).add(s).add(m).add(inv_total_batch).add(g_fwd_bn).add(g_logits_pair).add(g_radial_mode)
       .add(g_dx_cluster).add(g_dw_cluster).add(make_bwd_plan(n_rows, n_classes, emb).chunk).add(g_pipe).add(g_ring).add(g_split[0])
-      .add(g_split[1]).add(g_split[2]).add(g_prefetch[0]).add(g_prefetch[1]).add(g_prefetch[2]);
+      .add(g_split[1]).add(g_split[2]).add(g_prefetch[0]).add(g_prefetch[1]).add(g_prefetch[2]).add(g_dx_pair);
   return run_cached_graph(kb, st, enqueue);
 }
 
@@ -1655,6 +1791,7 @@ void tc_set_fwd_overlap(int chunks, int norm_blocks_per_sm) {
 }
 
 void tc_set_graph(int on) { g_use_graph = on ? 1 : 0; }
+void tc_set_dx_pair(int on) { g_dx_pair = on ? 1 : 0; }
 void tc_set_prefetch(int logits, int dx, int dw) { g_prefetch[0] = logits; g_prefetch[1] = dx; g_prefetch[2] = dw; }
 void tc_set_pipeline(int on, int sm_g, int sm_dx, int sm_dw, int ring) {
   g_pipe = on ? 1 : 0;
