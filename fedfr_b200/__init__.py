@@ -2,7 +2,7 @@
 ``partial_fc.PartialFC`` / ``losses.CosFace`` / ``server.FedPavg`` hot path.  See DESIGN.md."""
 from . import _native  # noqa: F401  (fails loudly when the CUDA extension has not been built)
 from .fedavg import FedAvg_on_FC, FedPavg, FedPavg_sharded
-from .losses import CosFace
+from .losses import ArcFace, CosFace
 from .partial_fc import PartialFC
 
-__all__ = ["PartialFC", "CosFace", "FedPavg", "FedAvg_on_FC", "FedPavg_sharded"]
+__all__ = ["PartialFC", "CosFace", "ArcFace", "FedPavg", "FedAvg_on_FC", "FedPavg_sharded"]

@@ -37,12 +37,12 @@ SIGNATURES = {
     "pfc_sample_workspace_bytes": (_sz, [_i64]),
     "pfc_sample_index": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "pfc_fwd_num_partials": (_i32, [_i64, _i64, _i32, _i32]),
-    "pfc_fwd_stats": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _i32, _vp]),
-    "pfc_normalize_fwd_stats": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "pfc_fwd_stats": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "pfc_normalize_fwd_stats": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "pfc_merge_stats": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "pfc_finalize_stats": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "pfc_bwd_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
-    "pfc_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _f32, _vp, _vp, _i32, _vp, _sz, _i32, _vp]),
+    "pfc_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _i32, _f32, _vp, _vp, _i32, _vp, _sz, _i32, _vp]),
     "pfc_cosface_dense": (_i32, [_vp, _vp, _i64, _i64, _f32, _f32, _vp, _vp]),
     "fedavg_table_bytes": (_sz, [_i32, _i32]),
     "fedavg_weighted_sum": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _sz, _vp]),
@@ -72,6 +72,9 @@ lib.pfc_set_pipeline.argtypes = [_i32, _i32, _i32, _i32, _i32]
 for _knob in ("pfc_set_dx_pair", "pfc_set_graph", "pfc_set_chunk_mb", "pfc_set_logits_pair", "pfc_set_radial_mode"):
     getattr(lib, _knob).restype = _i32
     getattr(lib, _knob).argtypes = [_i32]
+
+
+MARGIN_COSFACE, MARGIN_ARCFACE = 0, 1
 
 
 def check(rc: int, what: str) -> None:

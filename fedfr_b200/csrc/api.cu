@@ -4,14 +4,14 @@
 
 namespace pfc {
 int tc_fwd_num_partials(int64_t n_rows, int64_t n_classes);
-int tc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m,
+int tc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m, int margin_kind,
                  float* part_max, float* part_sum, float* target_logit, cudaStream_t st);
 size_t tc_bwd_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb);
 int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_max, const float* row_sum,
-           int64_t n_rows, int64_t n_classes, int emb, float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
+           int64_t n_rows, int64_t n_classes, int emb, float s, float m, int margin_kind, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
            void* workspace, size_t workspace_bytes, cudaStream_t st);
 int tc_normalize_fwd(const float* w, const int64_t* index, const void* x, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb,
-                     float s, float m, void* w_hat, float* inv_norm, float* part_max, float* part_sum, float* target_logit, cudaStream_t st);
+                     float s, float m, int margin_kind, void* w_hat, float* inv_norm, float* part_max, float* part_sum, float* target_logit, cudaStream_t st);
 void tc_set_fwd_overlap(int chunks, int norm_blocks_per_sm);
 int launch_normalize_rows(const float* w, const int64_t* index, int64_t n_rows, int emb, __nv_bfloat16* ob, float* of, float* inv_norm,
                           int blocks_per_sm, cudaStream_t st);
@@ -26,11 +26,11 @@ void tc_set_prefetch(int logits, int dx, int dw);
 void tc_set_chunk_mb(int mb);
 void tc_set_pipeline(int on, int sm_g, int sm_dx, int sm_dw, int ring);
 int simt_fwd_num_partials(int64_t n_rows, int64_t n_classes);
-int simt_fwd_stats(const float* x, const float* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m,
+int simt_fwd_stats(const float* x, const float* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m, int margin_kind,
                    float* part_max, float* part_sum, float* target_logit, cudaStream_t st);
 size_t simt_bwd_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb);
 int simt_bwd(const float* x, const float* w_hat, const float* inv_norm, const int64_t* label, const float* row_max, const float* row_sum,
-             int64_t n_rows, int64_t n_classes, int emb, float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
+             int64_t n_rows, int64_t n_classes, int emb, float s, float m, int margin_kind, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
              void* workspace, size_t workspace_bytes, cudaStream_t st);
 }  // namespace pfc
 
@@ -44,21 +44,21 @@ int pfc_fwd_num_partials(int64_t n_rows, int64_t n_classes, int emb, int path) {
   return path == PFC_PATH_CHECK ? simt_fwd_num_partials(n_rows, n_classes) : tc_fwd_num_partials(n_rows, n_classes);
 }
 
-int pfc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m,
+int pfc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m, int margin_kind,
                   float* part_max, float* part_sum, float* target_logit, int path, void* stream) {
   if (int rc = require_sm100()) return rc;
   PFC_REQUIRE(x && w_hat && label && part_max && part_sum && target_logit, PFC_E_ARG, "pfc_fwd_stats: null argument");
   PFC_REQUIRE(n_rows > 0 && n_classes > 0 && emb > 0, PFC_E_ARG, "pfc_fwd_stats: empty shape (rows=%lld classes=%lld)", (long long)n_rows,
               (long long)n_classes);
   if (path == PFC_PATH_CHECK)
-    return simt_fwd_stats(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(w_hat), label, n_rows, n_classes, emb, s, m,
+    return simt_fwd_stats(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(w_hat), label, n_rows, n_classes, emb, s, m, margin_kind,
                           part_max, part_sum, target_logit, as_stream(stream));
   PFC_REQUIRE(path == PFC_PATH_TENSOR, PFC_E_ARG, "pfc_fwd_stats: unknown path %d", path);
-  return tc_fwd_stats(x, w_hat, label, n_rows, n_classes, emb, s, m, part_max, part_sum, target_logit, as_stream(stream));
+  return tc_fwd_stats(x, w_hat, label, n_rows, n_classes, emb, s, m, margin_kind, part_max, part_sum, target_logit, as_stream(stream));
 }
 
 int pfc_normalize_fwd_stats(const float* w, const int64_t* index, const void* x, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb,
-                            float s, float m, void* w_hat, float* inv_norm, float* part_max, float* part_sum, float* target_logit, int path,
+                            float s, float m, int margin_kind, void* w_hat, float* inv_norm, float* part_max, float* part_sum, float* target_logit, int path,
                             void* stream) {
   if (int rc = require_sm100()) return rc;
   PFC_REQUIRE(w && x && w_hat && inv_norm && label && part_max && part_sum && target_logit, PFC_E_ARG, "pfc_normalize_fwd_stats: null argument");
@@ -66,11 +66,11 @@ int pfc_normalize_fwd_stats(const float* w, const int64_t* index, const void* x,
               (long long)n_rows, (long long)n_classes);
   if (path == PFC_PATH_CHECK) {
     if (int rc = launch_normalize_rows(w, index, n_classes, emb, nullptr, reinterpret_cast<float*>(w_hat), inv_norm, 0, as_stream(stream))) return rc;
-    return simt_fwd_stats(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(w_hat), label, n_rows, n_classes, emb, s, m,
+    return simt_fwd_stats(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(w_hat), label, n_rows, n_classes, emb, s, m, margin_kind,
                           part_max, part_sum, target_logit, as_stream(stream));
   }
   PFC_REQUIRE(path == PFC_PATH_TENSOR, PFC_E_ARG, "pfc_normalize_fwd_stats: unknown path %d", path);
-  return tc_normalize_fwd(w, index, x, label, n_rows, n_classes, emb, s, m, w_hat, inv_norm, part_max, part_sum, target_logit, as_stream(stream));
+  return tc_normalize_fwd(w, index, x, label, n_rows, n_classes, emb, s, m, margin_kind, w_hat, inv_norm, part_max, part_sum, target_logit, as_stream(stream));
 }
 
 int pfc_set_fwd_overlap(int chunks, int norm_blocks_per_sm) {   /* class chunks of the fused forward, normalise blocks per SM */
@@ -84,16 +84,16 @@ size_t pfc_bwd_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb, int p
 }
 
 int pfc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_max, const float* row_sum,
-            int64_t n_rows, int64_t n_classes, int emb, float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
+            int64_t n_rows, int64_t n_classes, int emb, float s, float m, int margin_kind, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
             void* workspace, size_t workspace_bytes, int path, void* stream) {
   if (int rc = require_sm100()) return rc;
   PFC_REQUIRE(x && w_hat && inv_norm && label && row_max && row_sum && dx && dw && workspace, PFC_E_ARG, "pfc_bwd: null argument");
   PFC_REQUIRE(n_rows > 0 && n_classes > 0 && emb > 0, PFC_E_ARG, "pfc_bwd: empty shape");
   if (path == PFC_PATH_CHECK)
     return simt_bwd(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(w_hat), inv_norm, label, row_max, row_sum, n_rows,
-                    n_classes, emb, s, m, inv_total_batch, dx, dw, accumulate_dw, workspace, workspace_bytes, as_stream(stream));
+                    n_classes, emb, s, m, margin_kind, inv_total_batch, dx, dw, accumulate_dw, workspace, workspace_bytes, as_stream(stream));
   PFC_REQUIRE(path == PFC_PATH_TENSOR, PFC_E_ARG, "pfc_bwd: unknown path %d", path);
-  return tc_bwd(x, w_hat, inv_norm, label, row_max, row_sum, n_rows, n_classes, emb, s, m, inv_total_batch, dx, dw, accumulate_dw, workspace,
+  return tc_bwd(x, w_hat, inv_norm, label, row_max, row_sum, n_rows, n_classes, emb, s, m, margin_kind, inv_total_batch, dx, dw, accumulate_dw, workspace,
                 workspace_bytes, as_stream(stream));
 }
 

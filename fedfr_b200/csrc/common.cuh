@@ -80,6 +80,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// Margin applied to the target cosine (margin_kind: PFC_MARGIN_COSFACE / PFC_MARGIN_ARCFACE) and its slope
+//   CosFace  losses.py:23-29   c - m                  slope 1
+//   ArcFace  losses.py:38-45   cos(acos(c) + m)       slope sin(acos(c) + m) / sqrt(1 - c^2)   (autograd of acos_ / cos_)
+// The cosine is clamped to [-1, 1] first (the reference would produce NaN outside; features and centres are unit vectors).
+__device__ __forceinline__ float margin_cos(float c, float m, int kind) {
+  if (kind == PFC_MARGIN_COSFACE) return c - m;
+  c = fminf(fmaxf(c, -1.f), 1.f);
+  return cosf(acosf(c) + m);
+}
+__device__ __forceinline__ float margin_slope(float c, float m, int kind) {
+  if (kind == PFC_MARGIN_COSFACE) return 1.f;
+  c = fminf(fmaxf(c, -1.f), 1.f);
+  return sinf(acosf(c) + m) * rsqrtf(fmaxf(1.f - c * c, 1e-12f));
+}
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 

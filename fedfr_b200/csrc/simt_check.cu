@@ -52,7 +52,7 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int64_t a
 
 // grid (n_row_tiles, n_split): each block scans its slice of class tiles for 64 rows.
 __global__ void __launch_bounds__(256) fwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ w_hat, const int64_t* __restrict__ label,
-                                                        int n_rows, int n_classes, int emb, float s, float m, float* __restrict__ part_max,
+                                                        int n_rows, int n_classes, int emb, float s, float m, int margin_kind, float* __restrict__ part_max,
                                                         float* __restrict__ part_sum, float* __restrict__ target_logit) {
   __shared__ float sA[TK][TM + 1], sB[TK][TN + 1], sZ[TM][TN + 1];
   const int m0 = blockIdx.x * TM;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) fwd_stats_kernel(const float* __restrict_
         const int col = ct * TN + j;
         if (col >= n_classes) break;
         float cosv = sZ[threadIdx.x][j];
-        if (col == my_label) cosv -= m;                       // losses.py:27
+        if (col == my_label) cosv = margin_cos(cosv, m, margin_kind);   // losses.py:27 / :41-44
         const float z = cosv * s;                             // losses.py:28
         if (col == my_label) target_logit[my_row] = z;
         if (z > run_m) { run_l = run_l * expf(run_m - z) + 1.f; run_m = z; }
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) fwd_stats_kernel(const float* __restrict_
 // G[r, c] = s * (exp(z - M_r) / S_r - [c == y_r]) / Bt      (fp32 scratch [n_rows, ldg])
 __global__ void __launch_bounds__(256) grad_logits_kernel(const float* __restrict__ x, const float* __restrict__ w_hat, const int64_t* __restrict__ label,
                                                           const float* __restrict__ row_max, const float* __restrict__ row_sum, int n_rows,
-                                                          int n_classes, int class_base, int emb, float s, float m, float g_scale,
+                                                          int n_classes, int class_base, int emb, float s, float m, int margin_kind, float g_scale,
                                                           float* __restrict__ g, int64_t ldg) {
   __shared__ float sA[TK][TM + 1], sB[TK][TN + 1];
   const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
@@ -111,9 +111,9 @@ __global__ void __launch_bounds__(256) grad_logits_kernel(const float* __restric
       const int c = n0 + tx * 4 + j;
       if (c >= n_classes) continue;
       const bool hit = (y >= 0) && (y == (int64_t)class_base + c);
-      const float z = (t.acc[i][j] - (hit ? m : 0.f)) * s;
+      const float z = (hit ? margin_cos(t.acc[i][j], m, margin_kind) : t.acc[i][j]) * s;
       const float pr = expf(z - M) / S;
-      g[(int64_t)r * ldg + c] = (pr - (hit ? 1.f : 0.f)) * g_scale;
+      g[(int64_t)r * ldg + c] = (pr - (hit ? 1.f : 0.f)) * g_scale * (hit ? margin_slope(t.acc[i][j], m, margin_kind) : 1.f);
     }
   }
 }
@@ -168,13 +168,13 @@ static int check_splits(int64_t n_classes) {
 
 int simt_fwd_num_partials(int64_t n_rows, int64_t n_classes) { (void)n_rows; return check_splits(n_classes); }
 
-int simt_fwd_stats(const float* x, const float* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m,
+int simt_fwd_stats(const float* x, const float* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m, int margin_kind,
                    float* part_max, float* part_sum, float* target_logit, cudaStream_t st) {
   const int splits = check_splits(n_classes);
   PFC_CUDA(cudaMemsetAsync(part_sum, 0, sizeof(float) * (size_t)splits * n_rows, st));
   PFC_CUDA(cudaMemsetAsync(target_logit, 0, sizeof(float) * (size_t)n_rows, st));
   dim3 grid((unsigned)((n_rows + simt::TM - 1) / simt::TM), (unsigned)splits);
-  simt::fwd_stats_kernel<<<grid, 256, 0, st>>>(x, w_hat, label, (int)n_rows, (int)n_classes, emb, s, m, part_max, part_sum, target_logit);
+  simt::fwd_stats_kernel<<<grid, 256, 0, st>>>(x, w_hat, label, (int)n_rows, (int)n_classes, emb, s, m, margin_kind, part_max, part_sum, target_logit);
   PFC_LAUNCH_CHECK();
   return 0;
 }
@@ -193,7 +193,7 @@ size_t simt_bwd_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb) {
 }
 
 int simt_bwd(const float* x, const float* w_hat, const float* inv_norm, const int64_t* label, const float* row_max, const float* row_sum,
-             int64_t n_rows, int64_t n_classes, int emb, float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
+             int64_t n_rows, int64_t n_classes, int emb, float s, float m, int margin_kind, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
              void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const int64_t chunk = check_chunk(n_rows, n_classes);
   PFC_REQUIRE(workspace_bytes >= simt_bwd_workspace_bytes(n_rows, n_classes, emb) - 2048, PFC_E_WORKSPACE, "pfc_bwd(check): workspace too small");
@@ -203,7 +203,7 @@ int simt_bwd(const float* x, const float* w_hat, const float* inv_norm, const in
   for (int64_t c0 = 0; c0 < n_classes; c0 += chunk, ++idx) {
     const int64_t cc = n_classes - c0 < chunk ? n_classes - c0 : chunk;
     dim3 g1((unsigned)((n_rows + 63) / 64), (unsigned)((cc + 63) / 64));
-    simt::grad_logits_kernel<<<g1, 256, 0, st>>>(x, w_hat + c0 * emb, label, row_max, row_sum, (int)n_rows, (int)cc, (int)c0, emb, s, m,
+    simt::grad_logits_kernel<<<g1, 256, 0, st>>>(x, w_hat + c0 * emb, label, row_max, row_sum, (int)n_rows, (int)cc, (int)c0, emb, s, m, margin_kind,
                                                  s * inv_total_batch, g, chunk);
     PFC_LAUNCH_CHECK();
     // dx[r,e] (+)= sum_c G[r,c] w_hat[c,e]

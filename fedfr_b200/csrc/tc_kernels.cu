@@ -82,6 +82,7 @@ struct LogitsParams {
   int emb;
   int n_rb, n_ct;            // row blocks, class tiles
   float s, m;
+  int margin_kind;           // PFC_MARGIN_COSFACE / PFC_MARGIN_ARCFACE
   // MODE_STATS
   float* part_max;           // [gridDim.x, n_rows]   (log-e units)
   float* part_sum;
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(kLogitsThreads, 1) logits_kernel(const __grid_
     // warp w reads TMEM lanes [32 (w & 3), +32) and the column half (w >> 2) of every tile
     const int quad = warp & 3, chalf = warp >> 2;
     constexpr int CH = BN / 2;
-    const float s2 = p.s * kLog2e, ms2 = p.m * p.s * kLog2e;
+    const float s2 = p.s * kLog2e;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     int cur_rb = -1;
     constexpr int kNoLabel = -(1 << 30);
@@ -352,16 +353,19 @@ __global__ void __launch_bounds__(kLogitsThreads, 1) logits_kernel(const __grid_
         tmem_ld_wait();
         const int cb = col0 + c;
         float z[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) z[j] = __uint_as_float(v[j]) * s2;
         const int hit = my_label - cb;                   // in [0,32) iff the target class is in this column group
+        float c_hit = 0.f, slope = 1.f;                  // plain cosine / margin slope at the target
         if (hit >= 0 && hit < 32) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (j == hit) {
-            z[j] -= ms2;
-            if (MODE == MODE_STATS) p.target_logit[row] = p.s * (__uint_as_float(v[j]) - p.m);
+            c_hit = __uint_as_float(v[j]);
+            slope = margin_slope(c_hit, p.m, p.margin_kind);
+            v[j] = __float_as_uint(margin_cos(c_hit, p.m, p.margin_kind));
+            if (MODE == MODE_STATS) p.target_logit[row] = p.s * __uint_as_float(v[j]);
           }
         }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) z[j] = __uint_as_float(v[j]) * s2;
         if (MODE == MODE_STATS) {
           if (tile_has_oob) {
 #pragma unroll
@@ -383,9 +387,13 @@ __global__ void __launch_bounds__(kLogitsThreads, 1) logits_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             float g0 = fast_exp2(z[j] - M2) * rS, g1 = fast_exp2(z[j + 1] - M2) * rS;
-            if (j == hit) g0 -= 1.0f;
-            if (j + 1 == hit) g1 -= 1.0f;
+            if (j == hit) g0 = (g0 - 1.0f) * slope;
+            if (j + 1 == hit) g1 = (g1 - 1.0f) * slope;
             pk[j >> 1] = pack_bf16x2(g0 * p.g_scale, g1 * p.g_scale);
+          }
+          if (hit >= 0 && hit < 32) {                    // the projection below uses the plain cosine
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j == hit) v[j] = __float_as_uint(c_hit);
           }
           if (cb < p.ldg) {   // blocked scratch: [class block of 64][row block][128 rows][64 classes]; padded rows hold zeros
             uint4* dst = reinterpret_cast<uint4*>(p.g + ((int64_t)((cb >> 6) * p.n_rb + rb) * BM + quad * 32 + lane) * 64 + (cb & 32));
@@ -590,11 +598,14 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0),
         const int cb = col0 + c;
         const int hit = my_label - cb;                       // in [0,32) iff this row's target class is in this column group
         const bool has_hit = hit >= 0 && hit < 32;
-        if (has_hit) {                                       // rare: fold the margin into the cosine, v[hit] -= m
+        float c_hit = 0.f, slope = 1.f;                      // plain cosine / margin slope at the target
+        if (has_hit) {                                       // rare: fold the margin into the cosine
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (j == hit) {
-            if (MODE == MODE_STATS) p.target_logit[row] = p.s * (__uint_as_float(v[j]) - p.m);
-            v[j] = __float_as_uint(__uint_as_float(v[j]) - p.m);
+            c_hit = __uint_as_float(v[j]);
+            slope = margin_slope(c_hit, p.m, p.margin_kind);
+            v[j] = __float_as_uint(margin_cos(c_hit, p.m, p.margin_kind));
+            if (MODE == MODE_STATS) p.target_logit[row] = p.s * __uint_as_float(v[j]);
           }
         }
         if (MODE == MODE_STATS) {
@@ -633,8 +644,8 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0),
           if (has_hit) {
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-              if (2 * q == hit) g[q].x -= p.g_scale;
-              if (2 * q + 1 == hit) g[q].y -= p.g_scale;
+              if (2 * q == hit) g[q].x = (g[q].x - p.g_scale) * slope;
+              if (2 * q + 1 == hit) g[q].y = (g[q].y - p.g_scale) * slope;
             }
           }
           uint32_t pk[16];
@@ -660,7 +671,7 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0),
           if (p.radial_mode) {                              // radial_j += sum over this warp's 32 rows of G_ij cos_ij
             if (has_hit) {                                  // undo the margin: the projection uses the plain cosine
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (j == hit) v[j] = __float_as_uint(__uint_as_float(v[j]) + p.m);
+              for (int j = 0; j < 32; ++j) if (j == hit) v[j] = __float_as_uint(c_hit);
             }
             float2 h[16];
 #pragma unroll
@@ -1287,7 +1298,7 @@ int tc_fwd_num_partials(int64_t n_rows, int64_t n_classes) {
   return 2 * (g_logits_pair ? pair_grid(n_rows, n_classes) : fwd_grid(n_rows, n_classes, g_fwd_bn));
 }
 
-int tc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m,
+int tc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m, int margin_kind,
                  float* part_max, float* part_sum, float* target_logit, cudaStream_t st) {
   PFC_REQUIRE(tensor_emb_ok(emb), PFC_E_SHAPE, "tensor path supports emb in {64,128,256,512}, got %d (use PFC_PATH_CHECK)", emb);
   PFC_REQUIRE(n_rows > 0 && n_classes > 0 && n_classes < (1ll << 30) && n_rows < (1ll << 24), PFC_E_SHAPE, "pfc_fwd_stats: shape out of range");
@@ -1298,7 +1309,7 @@ int tc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t
   LogitsParams p{};
   p.label = label; p.n_rows = (int)n_rows; p.n_classes = (int)n_classes; p.class_base = 0; p.emb = emb;
   p.n_rb = (int)((n_rows + BM - 1) / BM); p.n_ct = (int)((n_classes + bn - 1) / bn);
-  p.s = s; p.m = m; p.part_max = part_max; p.part_sum = part_sum; p.target_logit = target_logit;
+  p.s = s; p.m = m; p.margin_kind = margin_kind; p.part_max = part_max; p.part_sum = part_sum; p.target_logit = target_logit;
   const int grid = g_logits_pair ? pair_grid(n_rows, n_classes) : fwd_grid(n_rows, n_classes, bn);
   PFC_CUDA(cudaMemsetAsync(part_sum, 0, sizeof(float) * (size_t)grid * 2 * n_rows, st));
   PFC_CUDA(cudaMemsetAsync(target_logit, 0, sizeof(float) * (size_t)n_rows, st));
@@ -1499,7 +1510,7 @@ struct EventPool {          // edge markers of one enqueue; destroying a recorde
   } while (0)
 
 static int tc_bwd_enqueue(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_max, const float* row_sum,
-                          int64_t n_rows, int64_t n_classes, int emb, float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
+                          int64_t n_rows, int64_t n_classes, int emb, float s, float m, int margin_kind, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
                           void* workspace, size_t workspace_bytes, cudaStream_t st) {
   PFC_REQUIRE(tensor_emb_ok(emb), PFC_E_SHAPE, "tensor path supports emb in {64,128,256,512}, got %d (use PFC_PATH_CHECK)", emb);
   PFC_REQUIRE(n_rows > 0 && n_classes > 0 && n_classes < (1ll << 30) && n_rows < (1ll << 24), PFC_E_SHAPE, "pfc_bwd: shape out of range");
@@ -1541,7 +1552,7 @@ static int tc_bwd_enqueue(const void* x, const void* w_hat, const float* inv_nor
     if (int rc = make_tmap_bf16_2d(&tw_k, wh + c0 * emb, cc, emb, emb, g_logits_pair ? 128 : bn)) return rc;
     LogitsParams lp{};
     lp.label = label; lp.n_rows = (int)n_rows; lp.n_classes = (int)cc; lp.class_base = (int)c0; lp.emb = emb;
-    lp.n_rb = n_rb; lp.n_ct = (int)((cc + bn - 1) / bn); lp.s = s; lp.m = m;
+    lp.n_rb = n_rb; lp.n_ct = (int)((cc + bn - 1) / bn); lp.s = s; lp.m = m; lp.margin_kind = margin_kind;
     lp.row_max = row_max; lp.row_sum = row_sum; lp.g = g; lp.ldg = pl.ldg; lp.g_scale = s * inv_total_batch; lp.radial = radial + c0; lp.radial_mode = g_radial_mode; lp.prefetch = g_prefetch[0];
     const uint64_t g_rows = (uint64_t)(pl.ldg / 64) * n_rb * BM;                              // rows of the blocked scratch viewed as [g_rows, 64]
     prof_begin(PH_GRAD, sG);
@@ -1699,16 +1710,16 @@ static int run_cached_graph(const KeyBuilder& kb, cudaStream_t st, Enqueue enque
 }
 
 int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_max, const float* row_sum,
-           int64_t n_rows, int64_t n_classes, int emb, float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
+           int64_t n_rows, int64_t n_classes, int emb, float s, float m, int margin_kind, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
            void* workspace, size_t workspace_bytes, cudaStream_t st) {
   auto enqueue = [&](cudaStream_t cs) {
-    return tc_bwd_enqueue(x, w_hat, inv_norm, label, row_max, row_sum, n_rows, n_classes, emb, s, m, inv_total_batch, dx, dw, accumulate_dw,
+    return tc_bwd_enqueue(x, w_hat, inv_norm, label, row_max, row_sum, n_rows, n_classes, emb, s, m, margin_kind, inv_total_batch, dx, dw, accumulate_dw,
                           workspace, workspace_bytes, cs);
   };
   if (!graph_eligible(st)) return enqueue(st);
   KeyBuilder kb;
   kb.add(1).add(x).add(w_hat).add(inv_norm).add(label).add(row_max).add(row_sum).add(dx).add(dw).add(workspace).add(n_rows).add(n_classes)
-      .add(workspace_bytes).add(emb).add(accumulate_dw).add(s).add(m).add(inv_total_batch).add(g_fwd_bn).add(g_logits_pair).add(g_radial_mode)
+      .add(workspace_bytes).add(emb).add(accumulate_dw).add(s).add(m).add(margin_kind).add(inv_total_batch).add(g_fwd_bn).add(g_logits_pair).add(g_radial_mode)
       .add(g_dx_cluster).add(g_dw_cluster).add(make_bwd_plan(n_rows, n_classes, emb).chunk).add(g_pipe).add(g_ring).add(g_split[0])
       .add(g_split[1]).add(g_split[2]).add(g_prefetch[0]).add(g_prefetch[1]).add(g_prefetch[2]).add(g_dx_pair);
   return run_cached_graph(kb, st, enqueue);
@@ -1723,7 +1734,7 @@ static int g_fwd_chunks = 4;
 static int g_norm_blocks_per_sm = 2;
 
 static int tc_normalize_fwd_enqueue(const float* w, const int64_t* index, const void* x, const int64_t* label, int64_t n_rows, int64_t n_classes,
-                                    int emb, float s, float m, void* w_hat, float* inv_norm, float* part_max, float* part_sum,
+                                    int emb, float s, float m, int margin_kind, void* w_hat, float* inv_norm, float* part_max, float* part_sum,
                                     float* target_logit, cudaStream_t st) {
   PFC_REQUIRE(tensor_emb_ok(emb), PFC_E_SHAPE, "tensor path supports emb in {64,128,256,512}, got %d (use PFC_PATH_CHECK)", emb);
   PFC_REQUIRE(n_rows > 0 && n_classes > 0 && n_classes < (1ll << 30) && n_rows < (1ll << 24), PFC_E_SHAPE, "pfc_normalize_fwd_stats: shape out of range");
@@ -1753,7 +1764,7 @@ static int tc_normalize_fwd_enqueue(const float* w, const int64_t* index, const 
     LogitsParams p{};
     p.label = label; p.n_rows = (int)n_rows; p.n_classes = (int)cc; p.class_base = (int)c0; p.emb = emb;
     p.n_rb = (int)((n_rows + BM - 1) / BM); p.n_ct = (int)((cc + bn - 1) / bn);
-    p.s = s; p.m = m; p.part_max = part_max; p.part_sum = part_sum; p.target_logit = target_logit; p.accumulate_stats = k > 0; p.prefetch = g_prefetch[0];
+    p.s = s; p.m = m; p.margin_kind = margin_kind; p.part_max = part_max; p.part_sum = part_sum; p.target_logit = target_logit; p.accumulate_stats = k > 0; p.prefetch = g_prefetch[0];
     if (has_next) {
       p.norm_w = index ? w : w + n0 * emb; p.norm_index = index ? index + n0 : nullptr; p.norm_rows = chunk_len(n0);
       p.norm_out = wh + n0 * emb; p.norm_inv = inv_norm + n0;
@@ -1774,13 +1785,13 @@ static int tc_normalize_fwd_enqueue(const float* w, const int64_t* index, const 
 }
 
 int tc_normalize_fwd(const float* w, const int64_t* index, const void* x, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb,
-                     float s, float m, void* w_hat, float* inv_norm, float* part_max, float* part_sum, float* target_logit, cudaStream_t st) {
+                     float s, float m, int margin_kind, void* w_hat, float* inv_norm, float* part_max, float* part_sum, float* target_logit, cudaStream_t st) {
   auto enqueue = [&](cudaStream_t cs) {
-    return tc_normalize_fwd_enqueue(w, index, x, label, n_rows, n_classes, emb, s, m, w_hat, inv_norm, part_max, part_sum, target_logit, cs);
+    return tc_normalize_fwd_enqueue(w, index, x, label, n_rows, n_classes, emb, s, m, margin_kind, w_hat, inv_norm, part_max, part_sum, target_logit, cs);
   };
   if (!graph_eligible(st)) return enqueue(st);
   KeyBuilder kb;
-  kb.add(2).add(w).add(index).add(x).add(label).add(n_rows).add(n_classes).add(emb).add(s).add(m).add(w_hat).add(inv_norm).add(part_max)
+  kb.add(2).add(w).add(index).add(x).add(label).add(n_rows).add(n_classes).add(emb).add(s).add(m).add(margin_kind).add(w_hat).add(inv_norm).add(part_max)
       .add(part_sum).add(target_logit).add(g_fwd_bn).add(g_logits_pair).add(g_fwd_chunks).add(g_norm_blocks_per_sm).add(g_prefetch[0]);
   return run_cached_graph(kb, st, enqueue);
 }

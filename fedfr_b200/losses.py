@@ -27,10 +27,29 @@ class CosFace(torch.nn.Module):
         return out
 
 
+class ArcFace(torch.nn.Module):
+    """losses.py:32-45 as a descriptor: ``s * cos(acos(cosine) + m)`` on the target column.  Fused into the same logits
+    epilogues as CosFace (the target cosine is clamped to [-1, 1] first); calling it on dense logits is not offered --
+    the reference's own dense path (client.py:133) goes through ``PartialFC`` here."""
+
+    def __init__(self, s=64.0, m=0.5):
+        super().__init__()
+        self.s = s
+        self.m = m
+
+    def forward(self, cosine, label):
+        raise NotImplementedError("fedfr_b200.ArcFace is a margin descriptor for PartialFC; it has no dense-logits kernel")
+
+
+_MARGIN_KINDS = {"CosFace": 0, "ArcFace": 1}      # PFC_MARGIN_COSFACE / PFC_MARGIN_ARCFACE
+
+
 def margin_params(margin_softmax):
-    """(s, m) of a CosFace-like object: this package's class or the reference's ``losses.CosFace``."""
-    if type(margin_softmax).__name__ != "CosFace" or not hasattr(margin_softmax, "s") or not hasattr(margin_softmax, "m"):
+    """(s, m, margin_kind) of a margin object: this package's classes or the reference's ``losses.CosFace`` /
+    ``losses.ArcFace`` (matched by class name, read as descriptors, never called)."""
+    name = type(margin_softmax).__name__
+    if name not in _MARGIN_KINDS or not hasattr(margin_softmax, "s") or not hasattr(margin_softmax, "m"):
         raise NotImplementedError(
-            f"margin_softmax of type {type(margin_softmax).__name__} is not supported by the fused kernels: "
-            "only CosFace(s, m) (losses.py:17-29) is implemented; there is no unfused fallback")
-    return float(margin_softmax.s), float(margin_softmax.m)
+            f"margin_softmax of type {name} is not supported by the fused kernels: CosFace(s, m) (losses.py:17-29) and "
+            "ArcFace(s, m) (losses.py:32-45) are implemented; there is no unfused fallback")
+    return float(margin_softmax.s), float(margin_softmax.m), _MARGIN_KINDS[name]

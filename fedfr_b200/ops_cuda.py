@@ -106,7 +106,7 @@ class CudaOps:
             self._ws[key] = w_hat
         return w_hat
 
-    def normalize_fwd_stats(self, sub_weight, x_hat, label, s, m):
+    def normalize_fwd_stats(self, sub_weight, x_hat, label, s, m, margin_kind=0):
         """normalize(sub_weight) fused with fwd_stats (one graph: the normalisation of class chunk k+1 runs under the
         logits kernel of chunk k).  -> (w_hat, inv_norm, stats [Bt, 3])."""
         n, emb = sub_weight.shape
@@ -117,7 +117,7 @@ class CudaOps:
         part = self._persist("part", (2, n_part, bt), torch.float32)
         tz = self._persist("target_logit", (bt,), torch.float32)
         st = _stream(self.device)
-        N.check(N.lib.pfc_normalize_fwd_stats(N.ptr(sub_weight), None, N.ptr(x_hat), N.ptr(label), bt, n, emb, float(s), float(m), N.ptr(w_hat),
+        N.check(N.lib.pfc_normalize_fwd_stats(N.ptr(sub_weight), None, N.ptr(x_hat), N.ptr(label), bt, n, emb, float(s), float(m), int(margin_kind), N.ptr(w_hat),
                                               N.ptr(inv), N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), self.path, st), "pfc_normalize_fwd_stats")
         stats = self._persist("stats", (bt, 3), torch.float32)
         N.check(N.lib.pfc_merge_stats(N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), n_part, bt, N.ptr(stats), st), "pfc_merge_stats")
@@ -131,7 +131,7 @@ class CudaOps:
                                          _stream(self.device)), "pfc_cast_rows_bf16")
         return x
 
-    def fwd_stats(self, x_hat, w_hat, label, s, m):
+    def fwd_stats(self, x_hat, w_hat, label, s, m, margin_kind=0):
         """-> stats [Bt, 3] = (row max, sum-exp at that max, target logit) of this shard."""
         bt, emb = x_hat.shape
         cs = w_hat.shape[0]
@@ -139,7 +139,7 @@ class CudaOps:
         part = self._persist("part", (2, n_part, bt), torch.float32)
         tz = self._persist("target_logit", (bt,), torch.float32)
         st = _stream(self.device)
-        N.check(N.lib.pfc_fwd_stats(N.ptr(x_hat), N.ptr(w_hat), N.ptr(label), bt, cs, emb, float(s), float(m), N.ptr(part[0]), N.ptr(part[1]),
+        N.check(N.lib.pfc_fwd_stats(N.ptr(x_hat), N.ptr(w_hat), N.ptr(label), bt, cs, emb, float(s), float(m), int(margin_kind), N.ptr(part[0]), N.ptr(part[1]),
                                     N.ptr(tz), self.path, st), "pfc_fwd_stats")
         stats = torch.empty((bt, 3), dtype=torch.float32, device=self.device)
         N.check(N.lib.pfc_merge_stats(N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), n_part, bt, N.ptr(stats), st), "pfc_merge_stats")
@@ -155,7 +155,7 @@ class CudaOps:
                 "pfc_finalize_stats")
         return row_max, row_sum, loss
 
-    def bwd(self, x_hat, w_hat, inv_norm, label, row_max, row_sum, s, m, inv_total_batch, dw, accumulate):
+    def bwd(self, x_hat, w_hat, inv_norm, label, row_max, row_sum, s, m, inv_total_batch, dw, accumulate, margin_kind=0):
         """Writes/accumulates ``dw`` [Cs, E]; returns this shard's partial ``dx`` [Bt, E] (library-owned scratch,
         overwritten by the next step: callers hand out a copy)."""
         bt, emb = x_hat.shape
@@ -165,6 +165,6 @@ class CudaOps:
         ws = self._buf("bwd", nbytes + 1024)
         off = (-ws.data_ptr()) % 1024
         N.check(N.lib.pfc_bwd(N.ptr(x_hat), N.ptr(w_hat), N.ptr(inv_norm), N.ptr(label), N.ptr(row_max), N.ptr(row_sum), bt, cs, emb, float(s),
-                              float(m), float(inv_total_batch), N.ptr(dx), N.ptr(dw), 1 if accumulate else 0, ws.data_ptr() + off,
+                              float(m), int(margin_kind), float(inv_total_batch), N.ptr(dx), N.ptr(dw), 1 if accumulate else 0, ws.data_ptr() + off,
                               ws.numel() - off, self.path, _stream(self.device)), "pfc_bwd")
         return dx

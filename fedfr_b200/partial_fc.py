@@ -10,8 +10,8 @@ arguments, attributes (``weight``, ``weight_mom``, ``sub_weight``, ``sub_weight_
   epilogue of a tcgen05 GEMM, and the backward recomputes them (``libfedfr_b200.so``);
 * the three row-statistic all-reduces of partial_fc.py:142,147,161 are one all-gather of
   ``(max, sum-exp, target logit)`` triples followed by a local merge (mathematically identical);
-* ``margin_softmax`` must be a ``CosFace(s, m)`` object (this package's or the reference's); it is read as a
-  descriptor, never called.
+* ``margin_softmax`` must be a ``CosFace(s, m)`` or ``ArcFace(s, m)`` object (this package's or the reference's); it
+  is read as a descriptor, never called.
 
 There is no PyTorch/CPU fallback: construction fails without an sm_100 device.
 """
@@ -37,7 +37,7 @@ class PartialFC(Module):
         self.world_size: int = world_size
         self.batch_size: int = batch_size
         self.margin_softmax = margin_softmax
-        self._s, self._m = margin_params(margin_softmax)
+        self._s, self._m, self._margin_kind = margin_params(margin_softmax)
         self.sample_rate: float = sample_rate
         self.embedding_size: int = embedding_size
         self.prefix: str = prefix
@@ -176,11 +176,11 @@ class PartialFC(Module):
 
         # forward: per-shard (max, sum-exp, target logit), then one exchange instead of three all-reduces
         if fused:       # normalize(sub_weight) chunk k+1 runs underneath the logits kernel of chunk k
-            w_hat, inv_norm, stats = ops.normalize_fwd_stats(self.sub_weight.data, x_hat, total_label, self._s, self._m)
+            w_hat, inv_norm, stats = ops.normalize_fwd_stats(self.sub_weight.data, x_hat, total_label, self._s, self._m, self._margin_kind)
             self._norm = (w_hat, inv_norm)
         else:
             inv_norm = self._norm[1]
-            stats = ops.fwd_stats(x_hat, w_hat, total_label, self._s, self._m)
+            stats = ops.fwd_stats(x_hat, w_hat, total_label, self._s, self._m, self._margin_kind)
         if W == 1:
             gathered = stats.unsqueeze(0)
         else:
@@ -193,7 +193,7 @@ class PartialFC(Module):
         if not accumulate:
             self.sub_weight.grad = torch.empty_like(self.sub_weight.data)
         dx_total = ops.bwd(x_hat, w_hat, inv_norm, total_label, row_max, row_sum, self._s, self._m, 1.0 / (B * W),
-                           self.sub_weight.grad, accumulate)
+                           self.sub_weight.grad, accumulate, self._margin_kind)
 
         if W == 1:
             x_grad = dx_total.clone()               # dx_total is step scratch with a stable address

@@ -30,6 +30,10 @@ extern "C" {
 #define PFC_E_ARCH        (-3)   /* device is not compute capability 10.x */
 #define PFC_E_WORKSPACE   (-4)   /* workspace too small */
 
+/* margin applied to the target cosine in the logits epilogues */
+#define PFC_MARGIN_COSFACE 0     /* s * (cos - m)                 losses.py:17-29 */
+#define PFC_MARGIN_ARCFACE 1     /* s * cos(acos(cos) + m)        losses.py:32-45 */
+
 /* kernel path selectors for the GEMM-shaped entries */
 #define PFC_PATH_TENSOR   0      /* bf16 operands, tcgen05/TMEM fp32 accumulate (the product path) */
 #define PFC_PATH_CHECK    1      /* fp32 operands, fp32 SIMT accumulate ("check mode", slow) */
@@ -98,7 +102,7 @@ int pfc_fwd_num_partials(int64_t n_rows, int64_t n_classes, int emb, int path);
  *   part_max/part_sum  fp32 [pfc_fwd_num_partials(...), n_rows]
  *   target_logit fp32 [n_rows], must be zero-filled by the caller (only owning rows are written) */
 int pfc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes,
-                  int emb, float s, float m, float* part_max, float* part_sum, float* target_logit,
+                  int emb, float s, float m, int margin_kind, float* part_max, float* part_sum, float* target_logit,
                   int path, void* stream);
 
 /* prepare + forward in one call: norm_weight = normalize(sub_weight[index]) (partial_fc.py:105,127) fused with
@@ -108,7 +112,7 @@ int pfc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_
  *   w_hat  out: bf16 (PFC_PATH_TENSOR) / fp32 (PFC_PATH_CHECK) [n_classes, emb];  inv_norm out: fp32 [n_classes]
  *   the remaining arguments are those of pfc_fwd_stats; target_logit / part_sum are zero-filled here. */
 int pfc_normalize_fwd_stats(const float* w, const int64_t* index, const void* x, const int64_t* label,
-                            int64_t n_rows, int64_t n_classes, int emb, float s, float m, void* w_hat,
+                            int64_t n_rows, int64_t n_classes, int emb, float s, float m, int margin_kind, void* w_hat,
                             float* inv_norm, float* part_max, float* part_sum, float* target_logit,
                             int path, void* stream);
 
@@ -135,7 +139,7 @@ size_t pfc_bwd_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb, int p
  * w_hat_f32 is only read in PFC_PATH_CHECK (then x / w_hat are fp32 too). */
 int pfc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label,
             const float* row_max, const float* row_sum, int64_t n_rows, int64_t n_classes, int emb,
-            float s, float m, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
+            float s, float m, int margin_kind, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
             void* workspace, size_t workspace_bytes, int path, void* stream);
 
 /* losses.CosFace.forward on materialised logits (dense twin, client.py:430): in place

@@ -97,12 +97,31 @@ def normalize_rows(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return w / n, n
 
 
-def margin_logits(x: torch.Tensor, w_hat: torch.Tensor, label: torch.Tensor, s: float, m: float) -> torch.Tensor:
-    """z = s * (x @ w_hat.T - m * onehot(label)), rows with label -1 get no margin (losses.py:23-29)."""
+def margin_logits(x: torch.Tensor, w_hat: torch.Tensor, label: torch.Tensor, s: float, m: float, margin: str = "cosface") -> torch.Tensor:
+    """CosFace (losses.py:23-29): z = s * (x @ w_hat.T - m * onehot(label)).
+    ArcFace (losses.py:38-45): z = s * cos(acos(x @ w_hat.T) + m * onehot(label)); the reference runs acos/cos over the
+    whole matrix, which is the identity off the target column (to fp32 rounding), so only targets are touched here.
+    Rows with label -1 get no margin."""
     z = x @ w_hat.t()
     rows = torch.nonzero(label >= 0, as_tuple=True)[0]
-    z[rows, label[rows]] -= m
+    if margin == "cosface":
+        z[rows, label[rows]] -= m
+    elif margin == "arcface":
+        z[rows, label[rows]] = torch.cos(torch.acos(z[rows, label[rows]]) + m)
+    else:
+        raise ValueError(margin)
     return z * s
+
+
+def target_slope(x: torch.Tensor, w_hat: torch.Tensor, label: torch.Tensor, m: float, margin: str = "cosface") -> torch.Tensor:
+    """d(margin(cos)) / d(cos) at the target column, per row (1 where the row has no target here).
+    CosFace: 1.  ArcFace: d cos(acos(c) + m) / dc = sin(acos(c) + m) / sqrt(1 - c^2)  (autograd of acos_ / cos_)."""
+    f = torch.ones(x.shape[0], dtype=x.dtype)
+    if margin == "arcface":
+        rows = torch.nonzero(label >= 0, as_tuple=True)[0]
+        c = (x[rows] * w_hat[label[rows]]).sum(dim=1)
+        f[rows] = torch.sin(torch.acos(c) + m) / torch.sqrt(1.0 - c * c)
+    return f
 
 
 @dataclass
@@ -114,14 +133,14 @@ class ShardOut:
     row_sumexp: torch.Tensor
 
 
-def shard_forward_stats(x, w, label, s, m):
+def shard_forward_stats(x, w, label, s, m, margin="cosface"):
     """Local (row max, logits) of one shard; the caller reduces max/sum over shards."""
     w_hat, n = normalize_rows(w)
-    z = margin_logits(x, w_hat, label, s, m)
+    z = margin_logits(x, w_hat, label, s, m, margin)
     return z, w_hat, n
 
 
-def shard_backward(x, z, w_hat, n, label, gmax, gsum, s, total_batch) -> ShardOut:
+def shard_backward(x, z, w_hat, n, label, gmax, gsum, s, total_batch, slope=None) -> ShardOut:
     """Hand-written backward of partial_fc.py:140-168 for one shard given the *global* max / sum-exp."""
     p = torch.exp(z - gmax[:, None]) / gsum[:, None]
     rows = torch.nonzero(label >= 0, as_tuple=True)[0]
@@ -131,6 +150,8 @@ def shard_backward(x, z, w_hat, n, label, gmax, gsum, s, total_batch) -> ShardOu
     g[rows, label[rows]] -= 1.0
     g /= total_batch
     g *= s                                        # d z / d cos
+    if slope is not None:                         # ArcFace: the target column carries d cos(theta + m) / d cos(theta)
+        g[rows, label[rows]] *= slope[rows]
     dx = g @ w_hat                                # [Bt,E]
     dw_hat = g.t() @ x                            # [Cs,E]
     radial = (w_hat * dw_hat).sum(dim=1, keepdim=True)
@@ -153,7 +174,7 @@ class StepOut:
 def forward_backward(features: Sequence[torch.Tensor], labels: Sequence[torch.Tensor],
                      weights: Sequence[torch.Tensor], num_classes: int, s: float = 64.0, m: float = 0.4,
                      sample_rate: float = 1.0, perms: Optional[Sequence[np.ndarray]] = None,
-                     dtype: torch.dtype = torch.float32) -> StepOut:
+                     dtype: torch.dtype = torch.float32, margin: str = "cosface") -> StepOut:
     """One ``PartialFC.forward_backward`` over ``W = len(weights)`` simulated ranks.
 
     ``features[r]`` [B,E] and ``labels[r]`` [B] are rank r's local batch, ``weights[r]`` its full shard
@@ -178,13 +199,13 @@ def forward_backward(features: Sequence[torch.Tensor], labels: Sequence[torch.Te
             y = relabel_to_sample(y, index)
             w = w[torch.from_numpy(index)]
         yt = torch.from_numpy(y)
-        z, w_hat, n = shard_forward_stats(x, w, yt, s, m)
-        per_rank.append((yt, index, z, w_hat, n))
+        z, w_hat, n = shard_forward_stats(x, w, yt, s, m, margin)
+        per_rank.append((yt, index, z, w_hat, n, target_slope(x, w_hat, yt, m, margin)))
 
     gmax = torch.stack([pr[2].max(dim=1)[0] for pr in per_rank]).max(dim=0)[0]        # all_reduce MAX :142
     gsum = sum(torch.exp(pr[2] - gmax[:, None]).sum(dim=1) for pr in per_rank)         # all_reduce SUM :147
 
-    outs = [shard_backward(x, z, w_hat, n, yt, gmax, gsum, s, Bt) for (yt, _, z, w_hat, n) in per_rank]
+    outs = [shard_backward(x, z, w_hat, n, yt, gmax, gsum, s, Bt, slope) for (yt, _, z, w_hat, n, slope) in per_rank]
     p_true = sum(o.loss_rows for o in outs)                                            # all_reduce SUM :161
     loss = -(p_true.clamp_min(PROB_FLOOR).log().mean())                                # :162
     dx_sum = sum(o.dx for o in outs)                                                   # reduce_scatter :173

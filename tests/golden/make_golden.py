@@ -56,7 +56,7 @@ def _import_reference():
     return partial_fc, losses
 
 
-def _build_module(partial_fc, losses, rank, world_size, batch_size, num_classes, sample_rate, emb, weight, s, m):
+def _build_module(partial_fc, losses, rank, world_size, batch_size, num_classes, sample_rate, emb, weight, s, m, loss="cosface"):
     """Field-for-field what partial_fc.py:24-69 sets, with device=cpu and a caller supplied shard."""
     from torch.nn import Module
     from torch.nn.parameter import Parameter
@@ -65,7 +65,7 @@ def _build_module(partial_fc, losses, rank, world_size, batch_size, num_classes,
     mod.num_classes, mod.rank, mod.local_rank = num_classes, rank, rank
     mod.device = torch.device("cpu")
     mod.world_size, mod.batch_size = world_size, batch_size
-    mod.margin_softmax = losses.CosFace(s=s, m=m)
+    mod.margin_softmax = (losses.ArcFace if loss == "arcface" else losses.CosFace)(s=s, m=m)
     mod.sample_rate, mod.embedding_size, mod.prefix = sample_rate, emb, "./"
     mod.num_local = num_classes // world_size + int(rank < num_classes % world_size)
     mod.class_start = num_classes // world_size * rank + min(rank, num_classes % world_size)
@@ -115,7 +115,7 @@ def _worker(rank, world_size, cfg, feats, labels, weights, port, ret):
         return t
     torch.rand = rand_spy
     mod = _build_module(partial_fc, losses, rank, world_size, cfg["batch"], cfg["num_classes"],
-                        cfg["sample_rate"], cfg["emb"], weights[rank], cfg["s"], cfg["m"])
+                        cfg["sample_rate"], cfg["emb"], weights[rank], cfg["s"], cfg["m"], cfg.get("loss", "cosface"))
     opt = torch.optim.SGD([{"params": mod.parameters()}], lr=cfg["lr"], momentum=0.9, weight_decay=5e-4)
     steps = []
     for step in range(cfg["steps"]):
@@ -169,6 +169,9 @@ CASES = {
     "w1_sr_pos_overflow": dict(seed=4, world_size=1, batch=64, num_classes=300, emb=64, sample_rate=0.1, s=64.0, m=0.4, lr=0.002, steps=1, store_inputs=True),
     "w2_sr1_ragged": dict(seed=5, world_size=2, batch=16, num_classes=301, emb=128, sample_rate=1.0, s=64.0, m=0.4, lr=0.002, steps=1, store_inputs=True),
     "w2_sr03": dict(seed=6, world_size=2, batch=16, num_classes=401, emb=128, sample_rate=0.3, s=64.0, m=0.4, lr=0.002, steps=2, store_inputs=True),
+    # ArcFace (losses.py:32-45), the second margin of the same boundary (--loss ArcFace, client.py:133)
+    "w1_arc_small": dict(seed=7, world_size=1, batch=16, num_classes=200, emb=128, sample_rate=1.0, s=64.0, m=0.5, lr=0.002, steps=2, store_inputs=True, loss="arcface"),
+    "w2_arc_sr03": dict(seed=8, world_size=2, batch=16, num_classes=401, emb=128, sample_rate=0.3, s=30.0, m=0.5, lr=0.002, steps=1, store_inputs=True, loss="arcface"),
     "c1_b128_c10k": dict(seed=100, world_size=1, batch=128, num_classes=10000, emb=512, sample_rate=1.0, s=64.0, m=0.4, lr=0.002, steps=1, store_inputs=False),
 }
 
@@ -217,7 +220,10 @@ def fedavg_golden():
 
 
 def main():
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]       # optional: regenerate just these cases
     for name, cfg in CASES.items():
+        if only and name not in only:
+            continue
         pool = None
         if name == "w1_sr_pos_overflow":      # 64 samples over 60 distinct ids > num_sample=30 -> index = positives
             pool = torch.arange(0, 300, 5)
@@ -244,7 +250,8 @@ def main():
                     pass
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **store)
         print(name, "loss", [float(res[r][0]["loss"]) for r in range(cfg["world_size"])])
-    fedavg_golden()
+    if not only:
+        fedavg_golden()
 
 
 if __name__ == "__main__":

@@ -54,4 +54,10 @@ class Case:
         return self.z[f"r{r}/s{step}/{key}"]
 
 
-SMALL_CASES = ["w1_sr1_small", "w1_sr1_s30", "w1_sr01", "w1_sr_pos_overflow", "w2_sr1_ragged", "w2_sr03"]
+SMALL_CASES = ["w1_sr1_small", "w1_sr1_s30", "w1_sr01", "w1_sr_pos_overflow", "w2_sr1_ragged", "w2_sr03", "w1_arc_small", "w2_arc_sr03"]
+
+
+def margin_of(pkg, cfg):
+    """The margin object of a golden case: pkg.ArcFace for cfg['loss'] == 'arcface', else pkg.CosFace."""
+    cls = pkg.ArcFace if cfg.get("loss", "cosface") == "arcface" else pkg.CosFace
+    return cls(s=cfg["s"], m=cfg["m"])

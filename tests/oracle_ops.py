@@ -32,8 +32,10 @@ class OracleOps:
     def cast_features(self, x):
         return x
 
-    def fwd_stats(self, x, w_hat, label, s, m):
-        z = O.margin_logits(x, w_hat, label, s, m)
+    _KIND = {0: "cosface", 1: "arcface"}
+
+    def fwd_stats(self, x, w_hat, label, s, m, margin_kind=0):
+        z = O.margin_logits(x, w_hat, label, s, m, self._KIND[margin_kind])
         mx = z.max(dim=1)[0]
         se = torch.exp(z - mx[:, None]).sum(dim=1)
         tz = torch.zeros_like(mx)
@@ -48,9 +50,10 @@ class OracleOps:
         p = torch.exp(tz - M) / S
         return M, S, -(p.clamp_min(O.PROB_FLOOR).log().mean())
 
-    def bwd(self, x, w_hat, inv_norm, label, row_max, row_sum, s, m, inv_total_batch, dw, accumulate):
-        z = O.margin_logits(x, w_hat, label, s, m)
-        out = O.shard_backward(x, z, w_hat, (1.0 / inv_norm)[:, None], label, row_max, row_sum, s, round(1.0 / inv_total_batch))
+    def bwd(self, x, w_hat, inv_norm, label, row_max, row_sum, s, m, inv_total_batch, dw, accumulate, margin_kind=0):
+        z = O.margin_logits(x, w_hat, label, s, m, self._KIND[margin_kind])
+        slope = O.target_slope(x, w_hat, label, m, self._KIND[margin_kind])
+        out = O.shard_backward(x, z, w_hat, (1.0 / inv_norm)[:, None], label, row_max, row_sum, s, round(1.0 / inv_total_batch), slope)
         if accumulate:
             dw += out.dw
         else:

@@ -52,12 +52,16 @@ def test_no_gpu_fails_loudly(native):
 
 def test_unsupported_margin_is_an_error():
     from fedfr_b200.losses import margin_params, CosFace
-    assert margin_params(CosFace(s=30.0, m=0.4)) == (30.0, pytest.approx(0.4))
+    assert margin_params(CosFace(s=30.0, m=0.4)) == (30.0, pytest.approx(0.4), 0)
 
-    class ArcFace:
+    class ArcFace:                    # the reference's class is matched by name and read as a descriptor
+        s, m = 64.0, 0.5
+    assert margin_params(ArcFace()) == (64.0, 0.5, 1)
+
+    class CurricularFace:
         s, m = 64.0, 0.5
     with pytest.raises(NotImplementedError):
-        margin_params(ArcFace())
+        margin_params(CurricularFace())
 
 
 def test_product_never_imports_oracle():

@@ -29,11 +29,11 @@ def _worker(rank, world, name, check_mode, port, ret):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         import fedfr_b200
-        from golden_util import Case
+        from golden_util import Case, margin_of
         case = Case(name)
         cfg = case.cfg
         dev = torch.device("cuda", rank)
-        head = fedfr_b200.PartialFC(rank, rank, world, cfg["batch"], False, fedfr_b200.CosFace(s=cfg["s"], m=cfg["m"]), cfg["num_classes"],
+        head = fedfr_b200.PartialFC(rank, rank, world, cfg["batch"], False, margin_of(fedfr_b200, cfg), cfg["num_classes"],
                                     sample_rate=cfg["sample_rate"], embedding_size=cfg["emb"], prefix="/tmp", check_mode=check_mode)
         head.weight.copy_(case.weights[rank].to(dev))
         head.weight_mom.zero_()
@@ -64,7 +64,7 @@ def _worker(rank, world, name, check_mode, port, ret):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("check_mode", [True, False])
-@pytest.mark.parametrize("name,port", [("w2_sr1_ragged", 29741), ("w2_sr03", 29742)])
+@pytest.mark.parametrize("name,port", [("w2_sr1_ragged", 29741), ("w2_sr03", 29742), ("w2_arc_sr03", 29743)])
 def test_two_gpu_matches_reference(name, port, check_mode):
     import __graft_entry__ as g
     g.build()

@@ -31,6 +31,9 @@ def pkg():
     return fedfr_b200
 
 
+from golden_util import margin_of  # noqa: E402  (tests/ is on sys.path via conftest)
+
+
 def rel(a, b):
     """Relative L2 error with an absolute floor (1e-7 rms) so vanishing gradients do not divide by ~0."""
     a = torch.as_tensor(a, dtype=torch.float64).cpu()
@@ -39,7 +42,7 @@ def rel(a, b):
 
 
 def _make_head(pkg, cfg, weight, check_mode, rank=0, world=1):
-    head = pkg.PartialFC(rank, 0, world, cfg["batch"], False, pkg.CosFace(s=cfg["s"], m=cfg["m"]), cfg["num_classes"],
+    head = pkg.PartialFC(rank, 0, world, cfg["batch"], False, margin_of(pkg, cfg), cfg["num_classes"],
                          sample_rate=cfg["sample_rate"], embedding_size=cfg["emb"], prefix="/tmp", check_mode=check_mode)
     head.weight.copy_(weight.to(head.device))
     head.weight_mom.zero_()
@@ -47,9 +50,9 @@ def _make_head(pkg, cfg, weight, check_mode, rank=0, world=1):
 
 
 @pytest.mark.parametrize("check_mode", [True, False])
-@pytest.mark.parametrize("name", ["w1_sr1_small", "w1_sr1_s30", "w1_sr01", "w1_sr_pos_overflow"])
+@pytest.mark.parametrize("name", ["w1_sr1_small", "w1_sr1_s30", "w1_sr01", "w1_sr_pos_overflow", "w1_arc_small"])
 def test_golden_single_rank(pkg, name, check_mode, monkeypatch):
-    from golden_util import Case
+    from golden_util import Case, margin_of
     case = Case(name)
     cfg = case.cfg
     if not check_mode and cfg["emb"] not in (64, 128, 256, 512):
@@ -86,7 +89,7 @@ def test_golden_single_rank(pkg, name, check_mode, monkeypatch):
 @pytest.mark.parametrize("check_mode", [True, False])
 def test_c1_config_vs_golden(pkg, check_mode):
     """BASELINE.json configs[0]: B=128, C=10k, E=512, sample_rate=1 (reference run on CPU gloo)."""
-    from golden_util import Case
+    from golden_util import Case, margin_of
     case = Case("c1_b128_c10k")
     head = _make_head(pkg, case.cfg, case.weights[0], check_mode)
     dev = head.device
@@ -120,6 +123,27 @@ def test_vs_oracle(pkg, B, C, E, s, check_mode):
     # second call without zero_grad accumulates into .grad (torch semantics of logits.backward, partial_fc.py:168)
     head.forward_backward(y.to(head.device), x.to(head.device), opt)
     assert rel(head.sub_weight.grad, 2 * ref.dw[0]) < tol
+
+
+@pytest.mark.parametrize("check_mode", [True, False])
+@pytest.mark.parametrize("B,C,E,s", [(200, 4097, 256, 30.0), (512, 20000, 512, 64.0)])
+def test_arcface_vs_oracle(pkg, B, C, E, s, check_mode):
+    """ArcFace margin (losses.py:32-45) through the same fused kernels; labels drawn from few classes so that trained-like
+    (large) target cosines occur: the slope sin(theta + m) / sin(theta) is exercised away from theta = pi / 2."""
+    from oracle import partial_fc_oracle as O
+    g = torch.Generator().manual_seed(B * 11 + C)
+    w = torch.randn(C, E, generator=g) * 0.01
+    y = torch.randint(0, C, (B,), generator=g)
+    x = torch.nn.functional.normalize(torch.randn(B, E, generator=g) + 3.0 * torch.nn.functional.normalize(w[y]) * (torch.arange(B) % 3 == 0)[:, None])
+    ref = O.forward_backward([x], [y], [w], C, s, 0.5, margin="arcface")
+    cfg = dict(batch=B, num_classes=C, emb=E, s=s, m=0.5, sample_rate=1.0, loss="arcface")
+    head = _make_head(pkg, cfg, w, check_mode)
+    opt = torch.optim.SGD([{"params": head.parameters()}], lr=0.1, momentum=0.9)
+    x_grad, loss = head.forward_backward(y.to(head.device), x.to(head.device), opt)
+    tol = TOL[check_mode]
+    assert abs(float(loss) - float(ref.loss)) <= tol * float(ref.loss)
+    assert rel(x_grad, ref.x_grad[0]) < tol
+    assert rel(head.sub_weight.grad, ref.dw[0]) < tol
 
 
 def test_hard_sample_clamp(pkg):

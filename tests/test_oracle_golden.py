@@ -16,7 +16,7 @@ def _run_steps(case, dtype=torch.float32):
     for step in range(cfg["steps"]):
         perms = [case.get(r, step, "perm") if case.has(r, step, "perm") else None for r in range(W)]
         out = O.forward_backward(case.features, case.labels, weights, cfg["num_classes"], cfg["s"], cfg["m"],
-                                 cfg["sample_rate"], perms, dtype=dtype)
+                                 cfg["sample_rate"], perms, dtype=dtype, margin=cfg.get("loss", "cosface"))
         yield step, out, weights, moms
         for r in range(W):          # optimizer.step() + update()  (partial_fc.py:113-116,124-126)
             if out.index[r] is None:
@@ -32,11 +32,14 @@ def _run_steps(case, dtype=torch.float32):
 def test_oracle_matches_reference(name):
     case = Case(name)
     W = case.cfg["world_size"]
+    # ArcFace: the reference pushes EVERY logit through acos_/cos_ (losses.py:43-44), an identity that costs ~1e-7 of
+    # rounding per element before the x s scale; the oracle only touches the target column -> a wider absolute floor
+    atol = 1e-5 if case.cfg.get("loss", "cosface") == "arcface" else 2e-6
     for step, out, weights, moms in _run_steps(case):
         for r in range(W):
             assert abs(float(out.loss) - float(case.get(r, step, "loss"))) <= 2e-5 * max(1.0, abs(float(out.loss)))
-            np.testing.assert_allclose(out.x_grad[r].numpy(), case.get(r, step, "x_grad"), rtol=2e-4, atol=2e-6)
-            np.testing.assert_allclose(out.dw[r].numpy(), case.get(r, step, "dw"), rtol=2e-4, atol=2e-6)
+            np.testing.assert_allclose(out.x_grad[r].numpy(), case.get(r, step, "x_grad"), rtol=2e-4, atol=atol)
+            np.testing.assert_allclose(out.dw[r].numpy(), case.get(r, step, "dw"), rtol=2e-4, atol=atol)
             if case.has(r, step, "index"):
                 np.testing.assert_array_equal(out.index[r], case.get(r, step, "index"))      # bit exact
 
