@@ -30,6 +30,7 @@ SIGNATURES = {
     "pfc_last_error": (C.c_char_p, []),
     "pfc_query_device": (_i32, [_i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "pfc_normalize_rows": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "pfc_sgd_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _i32, _vp, _vp, _vp]),
     "pfc_cast_rows_bf16": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "pfc_gather_rows2": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "pfc_scatter_rows2": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),

@@ -64,6 +64,75 @@ __global__ void scale_kernel(const float* __restrict__ in, float s, int64_t n, f
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i] * s;
 }
 
+// Fused optimizer.step() + update() for the head: torch.optim.SGD (momentum, weight decay, dampening,
+// nesterov) on the rows of the shard named by `index` (all rows when NULL), written in place -- for a sampled step this is
+// `weight[index]`, `weight_mom[index]`, i.e. PartialFC.update() (partial_fc.py:113-116) never has to run.  The arithmetic
+// follows torch's foreach kernels operation by operation (a + alpha * b is one fma):
+//     g   = fma(wd, w, grad)            _foreach_add(grads, params, alpha = weight_decay)
+//     buf = buf * momentum              _foreach_mul_(bufs, momentum)
+//     buf = fma(1 - dampening, g, buf)  _foreach_add_(bufs, grads, alpha = 1 - dampening)
+//     g   = fma(momentum, buf, g)       (nesterov only)
+//     w   = fma(-lr, buf or g, w)       _foreach_add_(params, grads, alpha = -lr)
+// Optionally emits the bf16 normalised rows + 1/norm of the UPDATED weights, which is what the next forward needs
+// (saves that step's separate normalize pass over the shard).  One warp per row; HBM bound: 5 x 4E bytes per row.
+template <int kVecPerLane>
+__global__ void __launch_bounds__(256) sgd_rows_kernel(float* __restrict__ weight, float* __restrict__ mom, const float* __restrict__ grad,
+                                                       const int64_t* __restrict__ index, int64_t n_rows, int emb, float lr, float momentum,
+                                                       float one_minus_damp, float wd, int nesterov, __nv_bfloat16* __restrict__ w_hat,
+                                                       float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int nvec = emb >> 2;
+  for (int64_t r = warp; r < n_rows; r += n_warps) {
+    const int64_t dst = index ? index[r] : r;
+    float4* pw = reinterpret_cast<float4*>(weight + dst * emb);
+    float4* pm = reinterpret_cast<float4*>(mom + dst * emb);
+    const float4* pg = reinterpret_cast<const float4*>(grad + r * emb);
+    float4 w[kVecPerLane], b[kVecPerLane], g[kVecPerLane];
+#pragma unroll
+    for (int i = 0; i < kVecPerLane; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) { w[i] = ld_stream_f4(pw + c); b[i] = ld_stream_f4(pm + c); g[i] = ld_stream_f4(pg + c); }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVecPerLane; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        float* wf = reinterpret_cast<float*>(&w[i]);
+        float* bf = reinterpret_cast<float*>(&b[i]);
+        float* gf = reinterpret_cast<float*>(&g[i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float gg = wd != 0.f ? __fmaf_rn(wd, wf[k], gf[k]) : gf[k];
+          float bb = __fmul_rn(bf[k], momentum);
+          bb = __fmaf_rn(one_minus_damp, gg, bb);
+          const float step = nesterov ? __fmaf_rn(momentum, bb, gg) : bb;
+          wf[k] = __fmaf_rn(-lr, step, wf[k]);
+          bf[k] = bb;
+          ss += wf[k] * wf[k];
+        }
+        st_stream_f4(pw + c, w[i]);
+        st_stream_f4(pm + c, b[i]);
+      }
+    }
+    if (w_hat != nullptr || inv_norm != nullptr) {
+      ss = warp_sum(ss);
+      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+      if (lane == 0 && inv_norm) inv_norm[r] = inv;
+      if (w_hat) {
+#pragma unroll
+        for (int i = 0; i < kVecPerLane; ++i) {
+          const int c = lane + i * 32;
+          if (c < nvec)
+            *reinterpret_cast<uint2*>(w_hat + r * emb + c * 4) = make_uint2(pack_bf16x2(w[i].x * inv, w[i].y * inv), pack_bf16x2(w[i].z * inv, w[i].w * inv));
+        }
+      }
+    }
+  }
+}
+
 static int row_grid(int64_t n_rows) {
   int64_t blocks = (n_rows + 7) / 8;            // 8 warps per block
   int64_t cap = (int64_t)sm_count() * 8;        // 8 resident blocks of 256 threads per SM
@@ -114,6 +183,29 @@ int pfc_normalize_rows(const float* w, const int64_t* index, int64_t n_rows, int
   prof_begin(PH_NORMALIZE, st);
   if (int rc = launch_normalize_rows(w, index, n_rows, emb, reinterpret_cast<__nv_bfloat16*>(w_hat_bf16), w_hat_f32, inv_norm, 0, st)) return rc;
   prof_end(PH_NORMALIZE, st);
+  return 0;
+}
+
+int pfc_sgd_step(float* weight, float* weight_mom, const float* grad, const int64_t* index, int64_t n_rows, int emb, float lr, float momentum,
+                 float dampening, float weight_decay, int nesterov, void* w_hat_bf16, float* inv_norm, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  PFC_REQUIRE(weight && weight_mom && grad && n_rows >= 0 && emb > 0, PFC_E_ARG, "pfc_sgd_step: bad argument");
+  PFC_REQUIRE(emb % 4 == 0 && emb <= 2048, PFC_E_SHAPE, "pfc_sgd_step: emb=%d must be a multiple of 4 and <= 2048", emb);
+  PFC_REQUIRE(!(index && (w_hat_bf16 || inv_norm)), PFC_E_ARG, "pfc_sgd_step: the normalised output is for unsampled steps (index == NULL)");
+  if (n_rows == 0) return 0;
+  const int vec_per_lane = (emb / 4 + 31) / 32;
+  const int grid = row_grid(n_rows);
+  cudaStream_t st = as_stream(stream);
+  auto* wh = reinterpret_cast<__nv_bfloat16*>(w_hat_bf16);
+  const float omd = 1.0f - dampening;
+#define PFC_SGD(V) sgd_rows_kernel<V><<<grid, 256, 0, st>>>(weight, weight_mom, grad, index, n_rows, emb, lr, momentum, omd, weight_decay, nesterov, wh, inv_norm)
+  if (vec_per_lane <= 1) PFC_SGD(1);
+  else if (vec_per_lane <= 2) PFC_SGD(2);
+  else if (vec_per_lane <= 4) PFC_SGD(4);
+  else if (vec_per_lane <= 8) PFC_SGD(8);
+  else PFC_SGD(16);
+#undef PFC_SGD
+  PFC_LAUNCH_CHECK();
   return 0;
 }
 

@@ -75,6 +75,19 @@ class CudaOps:
         N.check(N.lib.pfc_scatter_rows2(N.ptr(weight), N.ptr(weight_mom), N.ptr(index), index.numel(), weight.shape[1], N.ptr(sub_w),
                                         N.ptr(sub_m), _stream(self.device)), "pfc_scatter_rows2")
 
+    def sgd_step(self, weight, weight_mom, grad, index, lr, momentum, dampening, weight_decay, nesterov, prenormalize):
+        """In place torch.optim.SGD step on weight[index] / weight_mom[index] (all rows when index is None).
+        Returns (w_hat, inv_norm) of the updated rows when ``prenormalize`` (unsampled, tensor path), else None."""
+        n, emb = grad.shape
+        w_hat = inv = None
+        if prenormalize and index is None and self.path == N.PATH_TENSOR:
+            w_hat = self._w_hat_buffer(n, emb)
+            inv = self._persist("inv_norm", (n,), torch.float32)
+        N.check(N.lib.pfc_sgd_step(N.ptr(weight), N.ptr(weight_mom), N.ptr(grad), N.ptr(index), n, emb, float(lr), float(momentum),
+                                   float(dampening), float(weight_decay), 1 if nesterov else 0, N.ptr(w_hat), N.ptr(inv), _stream(self.device)),
+                "pfc_sgd_step")
+        return (w_hat, inv) if w_hat is not None else None
+
     # ------------------------------------------------------------------ floating point side
     def normalize(self, sub_weight):
         """-> (w_hat operand, inv_norm).  bf16 on the tensor path, fp32 in check mode."""

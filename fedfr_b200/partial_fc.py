@@ -88,6 +88,7 @@ class PartialFC(Module):
         else:
             self.sub_weight = Parameter(torch.empty((0, 0), device=self.device))
         self._norm = None       # (w_hat, inv_norm) of the current step
+        self._prenorm = None    # (w_hat, inv_norm, weight ptr, weight version) left behind by step(prenormalize=True)
         self._label_buf = None
 
     # ------------------------------------------------------------------ shard I/O (partial_fc.py:71-87)
@@ -132,6 +133,32 @@ class PartialFC(Module):
         """Write the sampled rows back (partial_fc.py:113-116); replaced by a no-op when sample_rate == 1."""
         self._ops.scatter_rows2(self.weight, self.weight_mom, self.index, self.sub_weight.data, self.sub_weight_mom)
 
+    @torch.no_grad()
+    def step(self, optimizer, prenormalize=True):
+        """``optimizer.step()`` + ``self.update()`` for the head in ONE pass over the shard (the step either
+        side of the path).  Reads lr / momentum / dampening / weight_decay / nesterov from the optimizer's last param
+        group -- the one ``prepare`` wired ``sub_weight`` and its momentum buffer into (partial_fc.py:124-126) -- and
+        applies torch.optim.SGD's arithmetic in place to ``weight[index]`` / ``weight_mom[index]`` (so the scatter of
+        partial_fc.py:113-116 never runs).  Use it INSTEAD of ``optimizer.step(); module.update()`` for an optimizer
+        that holds only the head.  With ``sample_rate == 1`` and ``prenormalize`` the same pass also emits
+        normalize(weight) of the updated shard, and the next ``forward_backward`` skips its normalisation pass."""
+        group = optimizer.param_groups[-1]
+        if len(optimizer.param_groups) != 1 or len(group["params"]) != 1 or group["params"][0] is not self.sub_weight:
+            raise ValueError("PartialFC.step needs an optimizer whose only parameter is this module's sub_weight "
+                             "(call forward_backward first; use optimizer.step() + update() otherwise)")
+        if group.get("maximize", False) or float(group.get("momentum", 0.0)) == 0.0:
+            raise NotImplementedError("PartialFC.step implements SGD with momentum (config.py:8), minimising")
+        grad = self.sub_weight.grad
+        if grad is None:
+            return
+        sampled = int(self.sample_rate) != 1
+        pre = self._ops.sgd_step(self.weight, self.weight_mom, grad, self.index if sampled else None, group["lr"], group["momentum"],
+                                 group.get("dampening", 0.0), group.get("weight_decay", 0.0), group.get("nesterov", False),
+                                 prenormalize and not sampled)
+        self._prenorm = None
+        if pre is not None:
+            self._prenorm = (pre[0], pre[1], self.weight.data_ptr(), self.weight._version)
+
     # ------------------------------------------------------------------ collectives
     def _all_gather(self, out, inp):
         if self.world_size == 1:
@@ -175,7 +202,13 @@ class PartialFC(Module):
         x_hat = ops.cast_features(total_features)
 
         # forward: per-shard (max, sum-exp, target logit), then one exchange instead of three all-reduces
-        if fused:       # normalize(sub_weight) chunk k+1 runs underneath the logits kernel of chunk k
+        pre = self._prenorm
+        self._prenorm = None
+        if pre is not None and int(self.sample_rate) == 1 and pre[2] == self.weight.data_ptr() and pre[3] == self.weight._version:
+            w_hat, inv_norm = pre[0], pre[1]        # step() already normalised the updated shard
+            self._norm = (w_hat, inv_norm)
+            stats = ops.fwd_stats(x_hat, w_hat, total_label, self._s, self._m, self._margin_kind)
+        elif fused:     # normalize(sub_weight) chunk k+1 runs underneath the logits kernel of chunk k
             w_hat, inv_norm, stats = ops.normalize_fwd_stats(self.sub_weight.data, x_hat, total_label, self._s, self._m, self._margin_kind)
             self._norm = (w_hat, inv_norm)
         else:

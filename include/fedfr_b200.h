@@ -65,6 +65,15 @@ int pfc_gather_rows2(const float* weight, const float* weight_mom, const int64_t
 int pfc_scatter_rows2(float* weight, float* weight_mom, const int64_t* index, int64_t n_index, int emb,
                       const float* sub_weight, const float* sub_weight_mom, void* stream);
 
+/* optimizer.step() + update() for the head in one pass (the step either side of the path):
+ * torch.optim.SGD (momentum buffer always present, as injected at partial_fc.py:126) applied in place to the rows
+ * weight[index[r]] / weight_mom[index[r]] with gradient row r (index == NULL: row r itself), operation by operation as
+ * torch's foreach kernels do it (config.py:8-9: momentum 0.9, weight_decay 5e-4).  When index == NULL, w_hat_bf16 /
+ * inv_norm (either may be NULL) receive normalize() of the UPDATED rows -- the operands of the next step's forward. */
+int pfc_sgd_step(float* weight, float* weight_mom, const float* grad, const int64_t* index, int64_t n_rows,
+                 int emb, float lr, float momentum, float dampening, float weight_decay, int nesterov,
+                 void* w_hat_bf16, float* inv_norm, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Sampling (integer exact)                                              partial_fc.py:89-106
  * ---------------------------------------------------------------------------------------------- */

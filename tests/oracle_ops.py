@@ -29,6 +29,14 @@ class OracleOps:
         w_hat, n = O.normalize_rows(sub_weight)
         return w_hat, 1.0 / n.squeeze(1)
 
+    def sgd_step(self, weight, weight_mom, grad, index, lr, momentum, dampening, weight_decay, nesterov, prenormalize):
+        assert dampening == 0 and not nesterov
+        rows = slice(None) if index is None else index
+        w, m = O.sgd_momentum_step(weight[rows], weight_mom[rows], grad, lr, momentum, weight_decay)
+        weight[rows] = w
+        weight_mom[rows] = m
+        return None
+
     def cast_features(self, x):
         return x
 

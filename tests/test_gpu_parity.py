@@ -324,3 +324,43 @@ def test_full_size_c3_properties(pkg):
         dx += (Gc * (s / B)) @ wb[c0:c0 + 65536].double()
     assert rel(x_grad, dx) < 1e-2
     assert head.sub_weight.grad.shape == (C, E) and bool(torch.isfinite(head.sub_weight.grad).all())
+
+
+@pytest.mark.parametrize("sample_rate", [1.0, 0.25])
+@pytest.mark.parametrize("nesterov,dampening", [(False, 0.0), (True, 0.0), (False, 0.1)])
+def test_fused_step_matches_torch_sgd(pkg, sample_rate, nesterov, dampening, monkeypatch):
+    """PartialFC.step(opt) vs torch.optim.SGD.step() + update() on identical state: same weights and momentum (the
+    kernel mirrors torch's foreach arithmetic), and the pre-normalised operands it leaves behind give the same next
+    forward_backward as the ordinary path."""
+    B, C, E = 64, 3000, 256
+    g = torch.Generator().manual_seed(99)
+    w = torch.randn(C, E, generator=g) * 0.01
+    x = torch.nn.functional.normalize(torch.randn(B, E, generator=g))
+    y = torch.randint(0, C, (B,), generator=g)
+    cfg = dict(batch=B, num_classes=C, emb=E, s=64.0, m=0.4, sample_rate=sample_rate)
+    heads = [_make_head(pkg, cfg, w, False) for _ in range(2)]
+    dev = heads[0].device
+    opts = [torch.optim.SGD([{"params": h.parameters()}], lr=0.05, momentum=0.9, weight_decay=5e-4, nesterov=nesterov, dampening=dampening)
+            for h in heads]
+    perm = torch.rand(C, generator=g).to(dev)
+    real_rand = torch.rand
+    outs = []
+    for it in range(3):
+        for k, (h, o) in enumerate(zip(heads, opts)):
+            monkeypatch.setattr(torch, "rand", lambda *a, **kw: perm.clone())
+            xg, loss = h.forward_backward(y.to(dev), x.to(dev), o)
+            monkeypatch.setattr(torch, "rand", real_rand)
+            if k == 0:
+                o.step()
+                h.update()
+            else:
+                h.step(o)
+            o.zero_grad()
+            outs.append((xg.clone(), float(loss)))
+        torch.cuda.synchronize()
+        a, b = heads
+        assert rel(b.weight, a.weight) < 1e-6 and rel(b.weight_mom, a.weight_mom) < 1e-6, (it, rel(b.weight, a.weight))
+        assert abs(outs[-1][1] - outs[-2][1]) <= 1e-5 * abs(outs[-2][1])
+        assert rel(outs[-1][0], outs[-2][0]) < 1e-3
+    if sample_rate == 1.0 and not nesterov and dampening == 0.0:
+        assert torch.equal(heads[0].weight, heads[1].weight), "same arithmetic as torch's foreach SGD -> same bits"

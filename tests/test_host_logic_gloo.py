@@ -96,3 +96,27 @@ def test_single_rank_host_logic_matches_reference(name):
         opt.zero_grad()
         np.testing.assert_allclose(head.weight.numpy(), case.get(0, step, "weight_after"), rtol=3e-4, atol=3e-6)
         np.testing.assert_allclose(head.weight_mom.numpy(), case.get(0, step, "mom_after"), rtol=3e-4, atol=3e-6)
+
+
+@pytest.mark.parametrize("name", ["w1_sr1_small", "w1_sr01"])
+def test_fused_step_host_logic_matches_reference(name):
+    """PartialFC.step(optimizer) == optimizer.step() + update() of the reference run (weights and momentum after each step)."""
+    import __graft_entry__ as g
+    g.build()
+    sys.path.insert(0, HERE)
+    import fedfr_b200
+    from golden_util import Case, margin_of
+    from oracle_ops import OracleOps
+    case = Case(name)
+    cfg = case.cfg
+    head = fedfr_b200.PartialFC(0, 0, 1, cfg["batch"], False, margin_of(fedfr_b200, cfg), cfg["num_classes"],
+                                sample_rate=cfg["sample_rate"], embedding_size=cfg["emb"], prefix="/tmp", _ops=OracleOps())
+    head.weight.copy_(case.weights[0])
+    opt = torch.optim.SGD([{"params": head.parameters()}], lr=cfg["lr"], momentum=0.9, weight_decay=5e-4)
+    torch.manual_seed(cfg["seed"] * 1000)
+    for step in range(cfg["steps"]):
+        head.forward_backward(case.labels[0], case.features[0], opt)
+        head.step(opt)                          # instead of opt.step(); head.update()
+        opt.zero_grad()
+        np.testing.assert_allclose(head.weight.numpy(), case.get(0, step, "weight_after"), rtol=3e-4, atol=3e-6)
+        np.testing.assert_allclose(head.weight_mom.numpy(), case.get(0, step, "mom_after"), rtol=3e-4, atol=3e-6)
