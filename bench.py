@@ -390,6 +390,48 @@ def run_ours(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps) / args.steps
 
+    # the step either side of the path (reported separately): optimizer.step() + update(), torch vs fused
+    def opt_time(fn, n=5):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    def torch_opt():
+        opt.step()
+        head.update()
+
+    def train_step_torch():
+        head.sub_weight.grad = None
+        head.forward_backward(label, feats, opt)
+        opt.step()
+        head.update()
+
+    def train_step_fused():
+        head.sub_weight.grad = None
+        head.forward_backward(label, feats, opt)
+        head.step(opt)
+
+    step_resident()
+    extras = {}
+    try:
+        opt_time(torch_opt, 2)
+        extras["optimizer_step_update_torch_ms"] = opt_time(torch_opt)
+        step_resident()
+        opt_time(lambda: head.step(opt, prenormalize=False), 2)
+        extras["optimizer_step_update_fused_ms"] = opt_time(lambda: head.step(opt, prenormalize=False))
+        opt_time(train_step_torch, 2)
+        extras["train_step_torch_optimizer_ms"] = opt_time(train_step_torch, 10)
+        opt_time(train_step_fused, 2)
+        extras["train_step_fused_optimizer_ms"] = opt_time(train_step_fused, 10)
+    except Exception as e:           # noqa: BLE001  (extras never fail the bench line)
+        extras["error"] = repr(e)
+    head._prenorm = None
+
     # per-phase device times (events on the launch stream inside the library) for the roofline of the dominant kernel
     import ctypes as CT
     N.lib.pfc_profile_enable(1)
@@ -445,7 +487,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (weight shard fp32+bf16 streamed every step)", "parallelism": f"class-shard x{world}"},
             "e2e": {"value": Bt / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": B * E * 4 + B * 8, "d2h_bytes_per_step": B * E * 4 + 4,
                     "ms_per_step": ms_e2e},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extras": extras}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
