@@ -317,8 +317,6 @@ def run_ours(args):
         N.check(N.lib.pfc_set_logits_tile(args.logits_tile), "pfc_set_logits_tile")
     if args.logits_pair >= 0:
         N.lib.pfc_set_logits_pair(args.logits_pair)
-    if args.radial_mode != 2:
-        N.lib.pfc_set_radial_mode(args.radial_mode)
     if args.graph >= 0:
         N.lib.pfc_set_graph(args.graph)
     if args.chunk_mb:
@@ -334,6 +332,9 @@ def run_ours(args):
     if args.pipe:
         v = [int(t) for t in args.pipe.split(",")] + [0, 0, 0, 0]
         N.lib.pfc_set_pipeline(v[0], v[1], v[2], v[3], v[4])
+    if args.prob_split:
+        v = args.prob_split.split(",")
+        N.lib.pfc_set_prob_split(int(v[0]), float(v[1]) if len(v) > 1 else 0.0, int(v[2]) if len(v) > 2 else -1)
     if args.dx_cluster or args.dw_cluster:
         N.lib.pfc_set_clusters(args.dx_cluster, args.dw_cluster)
     torch.manual_seed(100 + rank)
@@ -502,7 +503,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c5"])
     ap.add_argument("--logits-tile", type=int, default=0)
-    ap.add_argument("--radial-mode", type=int, default=2)
     ap.add_argument("--logits-pair", type=int, default=-1)
     ap.add_argument("--dx-cluster", type=int, default=0)
     ap.add_argument("--dw-cluster", type=int, default=0)
@@ -512,6 +512,7 @@ def main():
     ap.add_argument("--fwd-overlap", default="", help="fused forward: 'chunks,normalize_blocks_per_sm' (e.g. 6,2)")
     ap.add_argument("--prefetch", default="", help="TMA L2 prefetch: 'logits,dx_distance,dw' (e.g. 1,6,1)")
     ap.add_argument("--dx-pair", type=int, default=-1, help="1/0: CTA-pair dx kernel")
+    ap.add_argument("--prob-split", default="", help="stored-probability backward: 'dx_sms[,dw_rate[,sweep_lead]]' (SM budget of the dx kernel, dx/dw pacing)")
     ap.add_argument("--chunk-mb", type=int, default=0, help="bf16 G scratch per backward chunk in MiB (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":

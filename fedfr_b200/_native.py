@@ -44,6 +44,10 @@ SIGNATURES = {
     "pfc_finalize_stats": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "pfc_bwd_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "pfc_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _i32, _f32, _vp, _vp, _i32, _vp, _sz, _i32, _vp]),
+    "pfc_prob_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "pfc_normalize_fwd_prob": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pfc_bwd_prob_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "pfc_bwd_prob": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _i32, _f32, _vp, _vp, _i32, _vp, _sz, _vp, _sz, _vp]),
     "pfc_cosface_dense": (_i32, [_vp, _vp, _i64, _i64, _f32, _f32, _vp, _vp]),
     "fedavg_table_bytes": (_sz, [_i32, _i32]),
     "fedavg_weighted_sum": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _sz, _vp]),
@@ -70,7 +74,9 @@ lib.pfc_set_fwd_overlap.restype = _i32
 lib.pfc_set_fwd_overlap.argtypes = [_i32, _i32]
 lib.pfc_set_pipeline.restype = _i32
 lib.pfc_set_pipeline.argtypes = [_i32, _i32, _i32, _i32, _i32]
-for _knob in ("pfc_set_dx_pair", "pfc_set_graph", "pfc_set_chunk_mb", "pfc_set_logits_pair", "pfc_set_radial_mode"):
+lib.pfc_set_prob_split.restype = _i32
+lib.pfc_set_prob_split.argtypes = [_i32, _f32, _i32]
+for _knob in ("pfc_set_dx_pair", "pfc_set_graph", "pfc_set_chunk_mb", "pfc_set_logits_pair"):
     getattr(lib, _knob).restype = _i32
     getattr(lib, _knob).argtypes = [_i32]
 

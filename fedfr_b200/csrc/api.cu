@@ -12,13 +12,21 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
            void* workspace, size_t workspace_bytes, cudaStream_t st);
 int tc_normalize_fwd(const float* w, const int64_t* index, const void* x, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb,
                      float s, float m, int margin_kind, void* w_hat, float* inv_norm, float* part_max, float* part_sum, float* target_logit, cudaStream_t st);
+size_t tc_prob_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb);
+int tc_normalize_fwd_prob(const float* w, const int64_t* index, const void* x, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb,
+                          float s, float m, int margin_kind, void* w_hat, float* inv_norm, float* part_max, float* part_sum, float* target_logit,
+                          void* prob_ws, size_t prob_ws_bytes, cudaStream_t st);
+size_t tc_bwd_prob_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb);
+int tc_bwd_prob(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_sum, int64_t n_rows, int64_t n_classes,
+                int emb, float s, float m, int margin_kind, float inv_total_batch, float* dx, float* dw, int accumulate_dw, void* prob_ws,
+                size_t prob_ws_bytes, void* workspace, size_t workspace_bytes, cudaStream_t st);
+void tc_set_prob_split(int dx_sms, float dw_rate, int sweep_lead);
 void tc_set_fwd_overlap(int chunks, int norm_blocks_per_sm);
 int launch_normalize_rows(const float* w, const int64_t* index, int64_t n_rows, int emb, __nv_bfloat16* ob, float* of, float* inv_norm,
                           int blocks_per_sm, cudaStream_t st);
 void tc_set_fwd_bn(int bn);
 void tc_set_clusters(int dx_cs, int dw_cs);
 void tc_set_debug(long long* p);
-void tc_set_radial_mode(int m);
 void tc_set_logits_pair(int on);
 void tc_set_graph(int on);
 void tc_set_dx_pair(int on);
@@ -73,6 +81,46 @@ int pfc_normalize_fwd_stats(const float* w, const int64_t* index, const void* x,
   return tc_normalize_fwd(w, index, x, label, n_rows, n_classes, emb, s, m, margin_kind, w_hat, inv_norm, part_max, part_sum, target_logit, as_stream(stream));
 }
 
+/* ---- stored-probability variant of the two calls above (tensor path only) ----------------------------------------
+ * The forward keeps P_ij = exp2(s log2e cos_ij - a_i) in a bf16 workspace (a_i: a per-row upper bound of the logits),
+ * so the backward needs no third logits GEMM.  w == NULL: w_hat / inv_norm are already valid.                       */
+size_t pfc_prob_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb) {
+  if (n_rows <= 0 || n_classes <= 0 || emb <= 0) return 0;
+  return tc_prob_workspace_bytes(n_rows, n_classes, emb);
+}
+
+int pfc_normalize_fwd_prob(const float* w, const int64_t* index, const void* x, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb,
+                           float s, float m, int margin_kind, void* w_hat, float* inv_norm, float* part_max, float* part_sum, float* target_logit,
+                           void* prob_ws, size_t prob_ws_bytes, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  PFC_REQUIRE(x && w_hat && inv_norm && label && part_max && part_sum && target_logit && prob_ws, PFC_E_ARG, "pfc_normalize_fwd_prob: null argument");
+  PFC_REQUIRE(n_rows > 0 && n_classes > 0 && emb > 0, PFC_E_ARG, "pfc_normalize_fwd_prob: empty shape (rows=%lld classes=%lld)", (long long)n_rows,
+              (long long)n_classes);
+  return tc_normalize_fwd_prob(w, index, x, label, n_rows, n_classes, emb, s, m, margin_kind, w_hat, inv_norm, part_max, part_sum, target_logit, prob_ws,
+                               prob_ws_bytes, as_stream(stream));
+}
+
+size_t pfc_bwd_prob_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb) {
+  if (n_rows <= 0 || n_classes <= 0 || emb <= 0) return 0;
+  return tc_bwd_prob_workspace_bytes(n_rows, n_classes, emb);
+}
+
+int pfc_bwd_prob(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_sum, int64_t n_rows, int64_t n_classes,
+                 int emb, float s, float m, int margin_kind, float inv_total_batch, float* dx, float* dw, int accumulate_dw, void* prob_ws,
+                 size_t prob_ws_bytes, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  PFC_REQUIRE(x && w_hat && inv_norm && label && row_sum && dx && dw && prob_ws && workspace, PFC_E_ARG, "pfc_bwd_prob: null argument");
+  PFC_REQUIRE(n_rows > 0 && n_classes > 0 && emb > 0, PFC_E_ARG, "pfc_bwd_prob: empty shape");
+  return tc_bwd_prob(x, w_hat, inv_norm, label, row_sum, n_rows, n_classes, emb, s, m, margin_kind, inv_total_batch, dx, dw, accumulate_dw, prob_ws,
+                     prob_ws_bytes, workspace, workspace_bytes, as_stream(stream));
+}
+
+/* tuning: SM budget of the dx kernel (0 = from the shape), dw/dx per-SM rate (<= 0 = keep), classes dx / dw may drift apart (< 0 = keep, 0 = unpaced) */
+int pfc_set_prob_split(int dx_sms, float dw_rate, int sweep_lead) {
+  tc_set_prob_split(dx_sms, dw_rate, sweep_lead);
+  return 0;
+}
+
 int pfc_set_fwd_overlap(int chunks, int norm_blocks_per_sm) {   /* class chunks of the fused forward, normalise blocks per SM */
   tc_set_fwd_overlap(chunks, norm_blocks_per_sm);
   return 0;
@@ -106,11 +154,6 @@ int pfc_set_logits_tile(int bn) {
 
 int pfc_set_logits_pair(int on) {   /* 1 = CTA-pair (cta_group::2) logits kernels (default), 0 = single-CTA */
   tc_set_logits_pair(on);
-  return 0;
-}
-
-int pfc_set_radial_mode(int m) {   /* timing experiment only: anything but 2 gives wrong dw */
-  tc_set_radial_mode(m);
   return 0;
 }
 

@@ -111,15 +111,16 @@ __global__ void __launch_bounds__(256) sgd_rows_kernel(float* __restrict__ weigh
           const float step = nesterov ? __fmaf_rn(momentum, bb, gg) : bb;
           wf[k] = __fmaf_rn(-lr, step, wf[k]);
           bf[k] = bb;
-          ss += wf[k] * wf[k];
         }
+        ss += w[i].x * w[i].x + w[i].y * w[i].y + w[i].z * w[i].z + w[i].w * w[i].w;      // same expression as normalize_rows_warp: same bits
         st_stream_f4(pw + c, w[i]);
         st_stream_f4(pm + c, b[i]);
       }
     }
     if (w_hat != nullptr || inv_norm != nullptr) {
       ss = warp_sum(ss);
-      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+      const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+      const float inv = 1.0f / nrm;
       if (lane == 0 && inv_norm) inv_norm[r] = inv;
       if (w_hat) {
 #pragma unroll

@@ -64,7 +64,6 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 namespace tc {
 
 constexpr int kThreads = 192;          // dx / dw kernels: 4 epilogue warps + TMA warp + MMA warp
-constexpr int kEpiWarps = 4;
 constexpr int kLogitsEpiWarps = 8;     // logits kernels: two warps per TMEM lane quadrant, each takes half of the tile's columns
 constexpr int kLogitsThreads = (kLogitsEpiWarps + 2) * 32;
 constexpr int BM = 128;
@@ -72,7 +71,7 @@ constexpr int BK = 64;
 constexpr int kChunkBytes = BM * BK * 2;      // one [128 x 64] bf16 K-major tile = 16 KB
 constexpr int kBoxBytes = 64 * BK * 2;        // one [64 x 64] bf16 box = 8 KB
 
-enum { MODE_STATS = 0, MODE_GRAD = 1 };
+enum { MODE_STATS = 0, MODE_GRAD = 1, MODE_PROB = 2 };
 
 struct LogitsParams {
   const int64_t* label;      // [n_rows] shard-local id or -1
@@ -100,9 +99,10 @@ struct LogitsParams {
   __nv_bfloat16* g;          // [n_rows, ldg]
   int64_t ldg;
   float g_scale;             // s / total_batch
-  float* radial;             // [n_classes] += sum_i G_ij cos_ij  (= w_hat_j . dwh_j, the normalize-backward projection)
-  int radial_mode;           // 2 = on (default); 0/1 are timing experiments (skip / no atomics)
   int prefetch;              // 1: TMA L2 prefetch of the next class tile
+  // MODE_PROB (forward that keeps the unnormalised probabilities): P_ij = exp2(s2 cos_ij - row_bound_i) -> bf16 scratch
+  const float* row_bound;    // [n_rows] log2 units: an upper bound of every logit of the row minus a fixed headroom
+  float* target_cos;         // [n_rows] plain cosine at the target column (the backward's fp32 fix-up needs it)
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -391,24 +391,10 @@ __global__ void __launch_bounds__(kLogitsThreads, 1) logits_kernel(const __grid_
             if (j + 1 == hit) g1 = (g1 - 1.0f) * slope;
             pk[j >> 1] = pack_bf16x2(g0 * p.g_scale, g1 * p.g_scale);
           }
-          if (hit >= 0 && hit < 32) {                    // the projection below uses the plain cosine
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j == hit) v[j] = __float_as_uint(c_hit);
-          }
           if (cb < p.ldg) {   // blocked scratch: [class block of 64][row block][128 rows][64 classes]; padded rows hold zeros
             uint4* dst = reinterpret_cast<uint4*>(p.g + ((int64_t)((cb >> 6) * p.n_rb + rb) * BM + quad * 32 + lane) * 64 + (cb & 32));
 #pragma unroll
             for (int q = 0; q < 4; ++q) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          }
-          if (p.radial_mode) {   // radial_j += sum over this warp's 32 rows of bf16(G_ij) * cos_ij   (rows past n_rows hold G = 0)
-            float h[32];
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              h[j] = __uint_as_float(pk[j >> 1] << 16) * __uint_as_float(v[j]);
-              h[j + 1] = __uint_as_float(pk[j >> 1] & 0xffff0000u) * __uint_as_float(v[j + 1]);
-            }
-            const float cs = warp_colsum32(h, lane);
-            if (p.radial_mode > 1 && cb + lane < p.n_classes) atomicAdd(p.radial + cb + lane, cs);
           }
         }
       }
@@ -434,9 +420,12 @@ __global__ void __launch_bounds__(kLogitsThreads, 1) logits_kernel(const __grid_
 //   tcgen05.commit is multicast to the barriers of both CTAs; every CTA runs its own epilogue on its own TMEM rows.
 //   MODE_GRAD stores G through per-warp swizzled staging boxes and TMA stores into the blocked scratch.
 // ================================================================================================
-constexpr int kNormWarps = 8;          // extra HBM-streaming warps of the NORM variant
+// extra HBM-streaming warps of the NORM variant.  MODE_PROB: 6 of them make a 512-thread CTA = 128 registers per thread,
+// which its epilogue (two 32-column groups in flight + the packed bf16 staging) needs to stay spill-free; a setmaxnreg
+// split (epilogue warpgroups up, the rest down) made ptxas spill in the reduced half and was dropped.
+__host__ __device__ constexpr int norm_warps(int mode) { return mode == MODE_PROB ? 6 : 8; }
 template <int STAGES, int MODE, bool NORM>
-__global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0), 1)
+__global__ void __launch_bounds__(kLogitsThreads + (NORM ? norm_warps(MODE) * 32 : 0), 1)
     logits2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                    const __grid_constant__ CUtensorMap tmap_g, const LogitsParams p) {
   constexpr int BN = 256;                 // classes per pair tile
@@ -449,7 +438,7 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0),
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + n_kb * kChunkBytes;
   uint8_t* smem_g = smem_b + STAGES * kBStage;                                   // [8 warps] staging (MODE_GRAD only)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_g + (MODE == MODE_GRAD ? kLogitsEpiWarps * kGBox : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_g + (MODE != MODE_STATS ? kLogitsEpiWarps * kGBox : 0));
   uint64_t* full = bars;                          // [STAGES]  used in the leader only (both CTAs' TMA bytes land here)
   uint64_t* empty = bars + STAGES;                // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;        // [2]
@@ -466,6 +455,7 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0),
   const int64_t n_items = (int64_t)n_rp * p.n_ct;
   const int64_t t0 = n_items * pair / n_pairs, t1 = n_items * (pair + 1) / n_pairs;
   constexpr int kProducerWarp = kLogitsEpiWarps, kMmaWarp = kLogitsEpiWarps + 1;
+  constexpr int kNormWarps = norm_warps(MODE);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -474,7 +464,7 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0),
     mbar_init(a_empty, 1);
     fence_barrier_init();
   }
-  if (warp == kProducerWarp && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); if (MODE == MODE_GRAD) prefetch_tmap(&tmap_g); }
+  if (warp == kProducerWarp && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); if (MODE != MODE_STATS) prefetch_tmap(&tmap_g); }
   if (warp == kMmaWarp) tmem_alloc_2cta<2 * BN>(tmem_slot);
   tc_fence_before();
   cluster_sync_all();
@@ -567,8 +557,8 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0),
     for (int64_t t = t0; t < t1; ++t, ++it) {
       const int rp = (int)(t / p.n_ct), ct = (int)(t % p.n_ct);
       if (rp != cur_rp) {
-        if (MODE == MODE_STATS && cur_rp >= 0 && row_ok) {
-          p.part_max[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = run_m * kLn2;
+        if (MODE != MODE_GRAD && cur_rp >= 0 && row_ok) {
+          p.part_max[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = (MODE == MODE_PROB ? M2 : run_m) * kLn2;
           p.part_sum[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = run_l;
         }
         cur_rp = rp;
@@ -587,6 +577,10 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0),
         }
         M2 = 0.f; rS = 0.f;
         if (MODE == MODE_GRAD && row_ok) { M2 = p.row_max[row] * kLog2e; rS = 1.0f / p.row_sum[row]; }
+        if (MODE == MODE_PROB) {                           // rows past n_rows: exp2(-inf) = 0, nothing stored or summed
+          M2 = row_ok ? p.row_bound[row] : INFINITY;
+          if (p.accumulate_stats && row_ok) run_l = p.part_sum[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row];
+        }
       }
       const int acc = (int)(it & 1);
       mbar_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1));
@@ -605,10 +599,59 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0),
             c_hit = __uint_as_float(v[j]);
             slope = margin_slope(c_hit, p.m, p.margin_kind);
             v[j] = __float_as_uint(margin_cos(c_hit, p.m, p.margin_kind));
-            if (MODE == MODE_STATS) p.target_logit[row] = p.s * __uint_as_float(v[j]);
+            if (MODE != MODE_GRAD) p.target_logit[row] = p.s * __uint_as_float(v[j]);
+            if (MODE == MODE_PROB) p.target_cos[row] = c_hit;
           }
         }
-        if (MODE == MODE_STATS) {
+        if (MODE == MODE_PROB) {
+          // P = exp2(s2 cos - bound): summed in fp32 (the softmax denominator, target included), stored as bf16 with the
+          // target column zeroed -- the backward writes that one element from fp32 statistics (no p - 1 cancellation).
+          const float2 s2v = make_float2(s2, s2), m2v = make_float2(-M2, -M2);
+          float2 g[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float2 zz = __ffma2_rn(make_float2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), s2v, m2v);
+            g[q] = make_float2(fast_exp2(zz.x), fast_exp2(zz.y));
+          }
+          if (tile_has_oob) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              if (cb + 2 * q >= p.n_classes) g[q].x = 0.f;
+              if (cb + 2 * q + 1 >= p.n_classes) g[q].y = 0.f;
+            }
+          }
+          float2 sum = g[0];
+#pragma unroll
+          for (int q = 1; q < 16; ++q) sum = __fadd2_rn(sum, g[q]);
+          run_l += sum.x + sum.y;
+          if (has_hit) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              if (2 * q == hit) g[q].x = 0.f;
+              if (2 * q + 1 == hit) g[q].y = 0.f;
+            }
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) pk[q] = pack_bf16x2(g[q].x, g[q].y);
+          const int half = (c >> 5) & 1;
+          if (half == 0) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(gbuf + sw128_off(lane, half * 4 + q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          if (half == 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            const int cbg = p.class_base + cb;               // the scratch spans the whole shard
+            if (lane == 0 && cbg < p.ldg && rb < p.n_rb) {
+              tma_store_2d(&tmap_g, gbuf, 0, ((cbg >> 6) * p.n_rb + rb) * BM + quad * 32);
+              tma_store_commit();
+            }
+          }
+        } else if (MODE == MODE_STATS) {
           if (tile_has_oob) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (cb + j >= p.n_classes) v[j] = __float_as_uint(-INFINITY);
@@ -668,17 +711,6 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0),
               tma_store_commit();
             }
           }
-          if (p.radial_mode) {                              // radial_j += sum over this warp's 32 rows of G_ij cos_ij
-            if (has_hit) {                                  // undo the margin: the projection uses the plain cosine
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (j == hit) v[j] = __float_as_uint(c_hit);
-            }
-            float2 h[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) h[q] = __fmul2_rn(g[q], make_float2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])));
-            const float cs = warp_colsum32_x2(h, lane);
-            if (p.radial_mode > 1 && cb + lane < p.n_classes) atomicAdd(p.radial + cb + lane, cs);
-          }
         }
       };
       {
@@ -704,11 +736,11 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0),
         else mbar_arrive_cluster_addr_relaxed(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
       }
     }
-    if (MODE == MODE_STATS && cur_rp >= 0 && row_ok) {
-      p.part_max[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = run_m * kLn2;
+    if (MODE != MODE_GRAD && cur_rp >= 0 && row_ok) {
+      p.part_max[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = (MODE == MODE_PROB ? M2 : run_m) * kLn2;
       p.part_sum[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = run_l;
     }
-    if (MODE == MODE_GRAD && lane == 0) tma_store_wait_all();
+    if (MODE != MODE_STATS && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   cluster_sync_all();
@@ -719,7 +751,25 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? kNormWarps * 32 : 0),
 // dx kernel: D[128 rows x BN e] = sum over a class slice of G[rows, classes] * w_hat[classes, e]
 //   A = G (K-major, K = classes), B = w_hat (MN-major: N = e contiguous, K = classes)
 // ================================================================================================
+// dx and dw run side by side and both walk the class axis upwards, reading the same G (or P) and w_hat tiles.  Each
+// publishes the furthest class it has requested; whoever is more than `lead` classes ahead of the other waits, so the
+// second reader of a tile finds it in L2 (the phase is HBM bound: a tile fetched twice costs as much as the dw write).
+// Purely a pacing hint: the wait gives up after a bounded number of polls, and a finished kernel leaves its counter
+// at the end of the class axis.
+struct SweepSync {
+  int* self;            // device counters (nullptr = not paced)
+  const int* other;
+  int lead;
+};
+__device__ __forceinline__ void sweep_pace(const SweepSync& sw, int pos) {
+  if (sw.self == nullptr) return;
+  atomicMax(sw.self, pos);
+  int polls = 0;
+  while (pos > *reinterpret_cast<const volatile int*>(sw.other) + sw.lead && ++polls < (1 << 14)) __nanosleep(200);
+}
+
 struct DxParams {
+  SweepSync sweep;
   int n_rows, n_classes, emb;
   int n_rb, n_eh, ksplit;
   float* dx_part;          // [ksplit, n_rows, emb]
@@ -769,6 +819,7 @@ __global__ void __launch_bounds__(kThreads, 1) dx_kernel(const __grid_constant__
   if (warp == 4) {
     if (lane == 0) {
       PipeState ps;
+      int n_issued = 0;
       for (int kb = kb0; kb < kb1; kb += kstep) {
         if (p.prefetch && kb + p.prefetch * kstep < kb1) {  // k-block (kb + distance) -> L2 while the ring is still busy with kb
           const int pk = kb + p.prefetch * kstep;
@@ -782,6 +833,7 @@ __global__ void __launch_bounds__(kThreads, 1) dx_kernel(const __grid_constant__
             for (int q = 0; q < kPer; ++q) tma_prefetch_2d(&tmap_w, eh * BN + ((int)crank * kPer + q) * 64, pk * BK);
           }
         }
+        if (crank == 0 && (n_issued++ & 3) == 0) sweep_pace(p.sweep, kb * BK);
         mbar_wait(&empty[ps.stage], ps.phase ^ 1);
         uint8_t* sa = smem + ps.stage * kStageBytes;
         uint8_t* sb = sa + kChunkBytes;
@@ -907,7 +959,9 @@ __global__ void __launch_bounds__(kThreads, 1) dx2_kernel(const __grid_constant_
   if (warp == 4) {
     if (lane == 0) {
       PipeState ps;
-      for (int kb = kb0; kb < kb1; kb += kstep) {
+      int n_issued = 0;
+      for (int kb = kb0; kb < kb1; kb += kstep, ++n_issued) {
+        if (leader && (n_issued & 3) == 0) sweep_pace(p.sweep, kb * BK);
         mbar_wait(&empty[ps.stage], ps.phase ^ 1);
         uint8_t* sa = smem + ps.stage * kStageBytes;
         uint8_t* sb = sa + kABytes;
@@ -998,109 +1052,132 @@ __global__ void reduce_dx_kernel(const float4* __restrict__ part, int ksplit, in
 // ================================================================================================
 // dw kernel: D[128 classes x EN e] = G^T[classes, rows] * x_hat[rows, e-slice], epilogue = normalize backward
 //   A = G^T (MN-major: M = classes contiguous in a G row), B = x_hat (MN-major: N = e contiguous), K = rows
+//   (G is either the gradient scratch of logits_kernel<MODE_GRAD> or the stored probabilities of MODE_PROB, in which
+//   case B is the row-scaled x_hat.)
 //   Work item = (class tile, e-slice of EN = min(E, 256) columns): the accumulator is EN TMEM columns, two of them
 //   are allocated so the epilogue of item k overlaps the MMAs of item k+1.
-//   The radial term t_j = w_hat_j . dwh_j of the normalize backward was accumulated by the G kernel
-//   (LogitsParams::radial), so the epilogue is a single pass:
-//       dw_j[e] = (acc[e] - w_hat_j[e] * t_j) * inv_norm_j
+//   Epilogue = normalize backward,   dw_j[e] = (acc[e] - w_hat_j[e] * t_j) * inv_norm_j,   t_j = w_hat_j . acc_j:
+//   two passes over the accumulator (dot, then output); thread = class row, so the dot is thread-local.
+//     E <= 256: one item holds the whole row; a cluster of CS CTAs = CS class tiles in lock step sharing the x_hat
+//               stream by TMA multicast.
+//     E == 512: the row spans two e-slices.  A cluster of 2 CTAs owns ONE class tile, CTA r computes slice r; the G^T
+//               tile is fetched once and multicast to both, and the two partial dots are exchanged through distributed
+//               shared memory (st.shared::cluster + a cluster-scope mbarrier per warp) between the passes.
 //   Each epilogue warp owns 32 classes: its w_hat rows arrive by its own TMA loads into swizzled smem (issued one
 //   item ahead), the result leaves through swizzled staging boxes and its own TMA stores / reduce-adds.
-//   Cluster of CS CTAs = CS class tiles in lock step sharing the x_hat stream by TMA multicast.
 // ================================================================================================
 struct DwParams {
-  int n_rows, n_classes, emb;     // n_classes = classes in this chunk
+  SweepSync sweep;
+  int n_rows, n_classes, emb;     // n_classes = classes in this launch
   int n_ct, n_rb;
   const float* inv_norm;          // [n_classes]
-  const float* radial;            // [n_classes]
   int accumulate;
   int prefetch;                   // 1: TMA L2 prefetch of the next tile's G / w_hat boxes
   long long* dbg;                 // optional cycle counters of CTA 0 (developer instrumentation), else nullptr
 };
 
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+
+constexpr int kDwEpiWarps = 8;                 // two warps per TMEM lane quadrant, each takes half of the slice's columns
+constexpr int kDwThreads = (kDwEpiWarps + 2) * 32;
+
 template <int EMB, int STAGES, int CS>
-__global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
-                                                         const __grid_constant__ CUtensorMap tmap_wh, const __grid_constant__ CUtensorMap tmap_dw,
-                                                         const DwParams p) {
+__global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                                                           const __grid_constant__ CUtensorMap tmap_wh, const __grid_constant__ CUtensorMap tmap_dw,
+                                                           const DwParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int EN = EMB < 256 ? EMB : 256;              // accumulator width = N of one MMA
   constexpr int NH = EMB / EN;                           // e-slices per class tile
+  constexpr bool ES = NH == 2;                           // e-split cluster: both CTAs work on the same class tile
+  static_assert(!ES || CS == 2, "the e-split arrangement is a cluster of exactly two CTAs");
   constexpr int NBOX = EN / 64;                          // 64-wide boxes per e-slice
+  constexpr int CW = EN / 2;                             // columns per epilogue warp
+  constexpr int NG = CW / 32;                            // 32-column groups per epilogue warp (1, 2 or 4)
+  constexpr int kContrib = ES ? 4 : 2;                   // partial dots per class row: (cluster rank x) column half
   constexpr int kABytes = 2 * kBoxBytes;                 // 128 classes x 64 rows
   constexpr int kBBytes = NBOX * kBoxBytes;              // EN x 64 rows
   constexpr int kStageBytes = kABytes + kBBytes;
-  constexpr int kWBox = 32 * 128;                        // per-warp w_hat box: 32 classes x 64 e bf16 = 4 KB
-  constexpr int kWWarp = NBOX * kWBox;                   // per-warp w_hat slice
-  constexpr int kOBox = 32 * 128;                        // per-warp staging box: 32 classes x 32 e fp32 = 4 KB
-  uint8_t* smem_w = smem + STAGES * kStageBytes;         // [4 warps][NBOX] w_hat boxes
-  uint8_t* smem_o = smem_w + 4 * kWWarp;                 // [4 warps] staging
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + 4 * kOBox);
+  constexpr int kWBox = 32 * 128;                        // w_hat box: 32 classes x 64 e bf16 = 4 KB = one fp32 staging box [32 x 32]
+  constexpr int kWWarp = (NG + 1) / 2 * kWBox;           // per-warp w_hat columns (a warp with 32 columns still loads a 64-e box)
+  constexpr int kSBox = NG == 1 ? 2 : 0;                 // extra staging boxes for the warps that own a single w_hat box
+  uint8_t* smem_w = smem + STAGES * kStageBytes;         // [8 warps] w_hat boxes, reused as output staging
+  uint8_t* smem_s = smem_w + kDwEpiWarps * kWWarp;       // [8 warps][kSBox] staging (EN = 64 only)
+  float* tpart = reinterpret_cast<float*>(smem_s + kDwEpiWarps * kSBox * kWBox);   // [2][kContrib][128] partial dots
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tpart + 2 * 4 * 128);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;               // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;          // [2]
-  uint64_t* wfull = bars + 2 * STAGES + 4;               // [4 warps]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+  uint64_t* wfull = bars + 2 * STAGES + 4;               // [8 warps]
+  uint64_t* tbar = bars + 2 * STAGES + 12;               // [2][4 quadrants] all partial dots of the quadrant's rows have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kb = (p.n_rows + BK - 1) / BK;
   const uint32_t crank = CS > 1 ? cluster_ctarank() : 0;
   const int n_clusters = gridDim.x / CS, cid = blockIdx.x / CS;
   constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1);
-  // item i -> class tile ((i / NH) * n_clusters + cid) * CS + crank, e-slice i % NH.  Every CTA of a cluster runs the
-  // same number of items (tiles past n_ct are phantoms: TMA zero-fills their loads and clips their stores).
-  auto tile_of = [&](int i) { return ((i / NH) * n_clusters + cid) * CS + (int)crank; };
-  auto more = [&](int i) { return ((i / NH) * n_clusters + cid) * CS < p.n_ct; };
+  constexpr int kProducerWarp = kDwEpiWarps, kMmaWarp = kDwEpiWarps + 1;
+  // ES:   item i -> class tile i * n_clusters + cid (both CTAs), e-slice = cluster rank.
+  // else: item i -> class tile (i * n_clusters + cid) * CS + crank, the only e-slice.  Every CTA of a cluster runs the
+  //       same number of items (tiles past n_ct are phantoms: TMA zero-fills their loads and clips their stores).
+  auto tile_of = [&](int i) { return ES ? i * n_clusters + cid : (i * n_clusters + cid) * CS + (int)crank; };
+  auto more = [&](int i) { return ES ? i * n_clusters + cid < p.n_ct : (i * n_clusters + cid) * CS < p.n_ct; };
+  const int hs = ES ? (int)crank : 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CS); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
-    for (int i = 0; i < 4; ++i) mbar_init(&wfull[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kDwEpiWarps); }
+    for (int i = 0; i < kDwEpiWarps; ++i) mbar_init(&wfull[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&tbar[i], kContrib);
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) { prefetch_tmap(&tmap_g); prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_wh); prefetch_tmap(&tmap_dw); }
-  if (warp == 5) tmem_alloc<2 * EN>(tmem_slot);
+  if (warp == kProducerWarp && lane == 0) { prefetch_tmap(&tmap_g); prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_wh); prefetch_tmap(&tmap_dw); }
+  if (warp == kMmaWarp) tmem_alloc<2 * EN>(tmem_slot);
   tc_fence_before();
   if (CS > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == kProducerWarp) {
     if (lane == 0) {
       PipeState ps;
       for (int i = 0; more(i); ++i) {
-        const int ct = tile_of(i), hs = i % NH;
-        if (p.prefetch && hs == 0 && more(i + NH)) {          // G boxes of the next class tile -> L2 (HBM latency off the smem ring)
-          const int nt = tile_of(i + NH);
-          for (int kb = 0; kb < n_kb; ++kb) {
-            tma_prefetch_2d(&tmap_g, 0, ((2 * nt) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64);
-            tma_prefetch_2d(&tmap_g, 0, ((2 * nt + 1) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64);
-          }
-        }
+        const int ct = tile_of(i);
+        if (crank == 0) sweep_pace(p.sweep, ct * BM);
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&empty[ps.stage], ps.phase ^ 1);
           uint8_t* sa = smem + ps.stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
           mbar_arrive_expect_tx(&full[ps.stage], kStageBytes);
           // G scratch blocks (2 ct, kb / 2) and (2 ct + 1, kb / 2): 64 rows x 64 classes each, contiguous 8 KB
-          tma_load_2d(sa, &tmap_g, &full[ps.stage], 0, ((2 * ct) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64);
-          tma_load_2d(sa + kBoxBytes, &tmap_g, &full[ps.stage], 0, ((2 * ct + 1) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64);
-          if (CS == 1) {
+          if (ES) {                               // this CTA fetches class half `crank` for both CTAs of the cluster
+            tma_load_2d_mc(sa + crank * kBoxBytes, &tmap_g, &full[ps.stage], 0, ((2 * ct + (int)crank) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64, kMask);
 #pragma unroll
             for (int nb = 0; nb < NBOX; ++nb) tma_load_2d(sb + nb * kBoxBytes, &tmap_x, &full[ps.stage], hs * EN + nb * 64, kb * BK);
-          } else {                                // 1/CS of the x_hat boxes, delivered to every CTA of the cluster
-            constexpr int kPer = NBOX / CS;
+          } else {
+            tma_load_2d(sa, &tmap_g, &full[ps.stage], 0, ((2 * ct) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64);
+            tma_load_2d(sa + kBoxBytes, &tmap_g, &full[ps.stage], 0, ((2 * ct + 1) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64);
+            if (CS == 1) {
 #pragma unroll
-            for (int q = 0; q < kPer; ++q) {
-              const int nb = (int)crank * kPer + q;
-              tma_load_2d_mc(sb + nb * kBoxBytes, &tmap_x, &full[ps.stage], hs * EN + nb * 64, kb * BK, kMask);
+              for (int nb = 0; nb < NBOX; ++nb) tma_load_2d(sb + nb * kBoxBytes, &tmap_x, &full[ps.stage], nb * 64, kb * BK);
+            } else {                              // 1/CS of the x_hat boxes, delivered to every CTA of the cluster
+              constexpr int kPer = NBOX / CS > 0 ? NBOX / CS : 1;
+#pragma unroll
+              for (int q = 0; q < kPer; ++q) {
+                const int nb = (int)crank * kPer + q;
+                if (nb < NBOX) tma_load_2d_mc(sb + nb * kBoxBytes, &tmap_x, &full[ps.stage], nb * 64, kb * BK, kMask);
+              }
             }
           }
           ps.advance(STAGES);
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, EN, true, true);
       PipeState ps;
@@ -1133,32 +1210,39 @@ __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__
       if (p.dbg && blockIdx.x == 0) { p.dbg[0] = t_we; p.dbg[1] = t_wf; p.dbg[2] = clock64() - t_all; }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: warp w owns classes [32w, 32w+32) of the tile
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // ------------------------------------------------------------------ epilogue: warp (quad, chalf) owns classes [32 quad, +32) of
+    // the tile and columns [chalf * CW, +CW) of the slice.  thread = class row.
+    const int quad = warp & 3, chalf = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    constexpr int kNW = (NG + 1) / 2;                     // w_hat boxes of this warp
     uint8_t* wbuf = smem_w + warp * kWWarp;
-    uint8_t* obuf = smem_o + warp * kOBox;
+    uint8_t* sbuf = smem_s + warp * kSBox * kWBox;
     uint64_t* wbar = &wfull[warp];
-    long long t_wfull = 0, t_ww = 0, t_ep = 0;
+    const uint32_t peer = crank ^ 1u;
+    const int contrib = (ES ? (int)crank * 2 : 0) + chalf;
+    const int e_warp = hs * EN + chalf * CW;              // first e column of this warp
+    long long t_wfull = 0, t_ww = 0, t_ep = 0, t_p1 = 0, t_ex = 0, t_p2 = 0;
     auto issue_w = [&](int i) {                           // this warp's w_hat rows of item i (lane 0 only)
-      const int cls0 = tile_of(i) * BM + warp * 32, hs = i % NH;
-      mbar_arrive_expect_tx(wbar, kWWarp);
+      const int cls0 = tile_of(i) * BM + quad * 32;
+      mbar_arrive_expect_tx(wbar, kNW * kWBox);
 #pragma unroll
-      for (int nb = 0; nb < NBOX; ++nb) tma_load_2d(wbuf + nb * kWBox, &tmap_wh, wbar, hs * EN + nb * 64, cls0);
-      if (p.prefetch && more(i + 1)) {                    // and the rows of the item after that -> L2
-        const int n0 = tile_of(i + 1) * BM + warp * 32, nh = (i + 1) % NH;
+      for (int nb = 0; nb < kNW; ++nb) tma_load_2d(wbuf + nb * kWBox, &tmap_wh, wbar, (e_warp & ~63) + nb * 64, cls0);
+      if (more(i + 1)) {                                  // and the rows of the item after that -> L2, so this load only pays the L2 latency
+        const int n0 = tile_of(i + 1) * BM + quad * 32;
 #pragma unroll
-        for (int nb = 0; nb < NBOX; ++nb) tma_prefetch_2d(&tmap_wh, nh * EN + nb * 64, n0);
+        for (int nb = 0; nb < kNW; ++nb) tma_prefetch_2d(&tmap_wh, (e_warp & ~63) + nb * 64, n0);
       }
     };
+    constexpr int kSub = NG == 1 ? 4 : 0;                 // 32-column warps read the upper / lower half of their 64-e box
+    const int sub0 = NG == 1 ? ((e_warp >> 5) & 1) * kSub : 0;
     if (lane == 0 && more(0)) issue_w(0);
     for (int it = 0; more(it); ++it) {
-      const int ct = tile_of(it), hs = it % NH;
+      const int ct = tile_of(it);
       const int acc = it & 1;
-      const int cls0 = ct * BM + warp * 32;
+      const int cls0 = ct * BM + quad * 32;
       const int cls = cls0 + lane;
       const bool ok = cls < p.n_classes;
       const float inv_n = ok ? p.inv_norm[cls] : 0.f;
-      const float nr = ok ? -p.radial[cls] : 0.f;
       long long c0 = clock64();
       mbar_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1));
       t_wfull += clock64() - c0;
@@ -1167,60 +1251,189 @@ __global__ void __launch_bounds__(kThreads, 1) dw_kernel(const __grid_constant__
       t_ww += clock64() - c0;
       c0 = clock64();
       tc_fence_after();
-#pragma unroll 1
-      for (int nb = 0; nb < NBOX; ++nb) {                 // one 64-e w_hat box = two 32-column groups
-        uint4 wq[8];
+      const uint32_t t_base = tmem_base + lane_base + acc * EN + chalf * CW;
+      // ---- pass 1: partial dot t = w_hat_j . acc_j over this warp's columns (thread-local: lane = class row)
+      float2 dot2 = make_float2(0.f, 0.f);
+      {
+        uint32_t va[32], vb[32];
+        auto dot_group = [&](const uint32_t (&v)[32], int g) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) wq[q] = *reinterpret_cast<const uint4*>(wbuf + nb * kWBox + sw128_off(lane, q));
-        __syncwarp();                                     // the box is dead now: it doubles as the second staging buffer
+          for (int q = 0; q < 4; ++q) {
+            const uint4 w16 = *reinterpret_cast<const uint4*>(wbuf + (g >> 1) * kWBox + sw128_off(lane, sub0 + (g & 1) * 4 + q));
+            const uint32_t w4[4] = {w16.x, w16.y, w16.z, w16.w};
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          tmem_ld_x32(tmem_base + lane_base + acc * EN + nb * 64 + h * 32, v);
+            for (int k = 0; k < 4; ++k)
+              dot2 = __ffma2_rn(make_float2(__uint_as_float(w4[k] << 16), __uint_as_float(w4[k] & 0xffff0000u)),
+                                make_float2(__uint_as_float(v[q * 8 + 2 * k]), __uint_as_float(v[q * 8 + 2 * k + 1])), dot2);
+          }
+        };
+        tmem_ld_x32(t_base, va);
+#pragma unroll
+        for (int g = 0; g < NG; g += 2) {
           tmem_ld_wait();
-          uint8_t* orow = h == 0 ? obuf : wbuf + nb * kWBox;
-          if (h == 0 && lane == 0) tma_store_wait_read<1>();   // the previous store out of obuf has been read
+          if (g + 1 < NG) tmem_ld_x32(t_base + (g + 1) * 32, vb);
+          dot_group(va, g);
+          if (g + 1 < NG) {
+            tmem_ld_wait();
+            if (g + 2 < NG) tmem_ld_x32(t_base + (g + 2) * 32, va);
+            dot_group(vb, g + 1);
+          }
+        }
+      }
+      t_p1 += clock64() - c0;
+      // ---- exchange: every contributor (column half x cluster rank) publishes its partial to each CTA that needs it
+      float t;
+      {
+        const int buf = it & 1;
+        float* slot = tpart + (buf * 4 + contrib) * 128 + quad * 32 + lane;
+        *slot = dot2.x + dot2.y;
+        if (ES) st_cluster_f32(mapa_u32(smem_u32(slot), peer), dot2.x + dot2.y);
+        __syncwarp();                                     // one release per warp covers the 32 lanes' stores (not 32 cluster fences)
+        if (lane == 0) {
+          mbar_arrive(&tbar[buf * 4 + quad]);
+          if (ES) mbar_arrive_remote(&tbar[buf * 4 + quad], peer);
+        }
+        if (ES) mbar_wait_cluster(&tbar[buf * 4 + quad], (uint32_t)((it >> 1) & 1));
+        else mbar_wait(&tbar[buf * 4 + quad], (uint32_t)((it >> 1) & 1));
+        const float* all = tpart + buf * 4 * 128 + quad * 32 + lane;
+        t = all[0] + all[128];                            // fixed order: every warp (and both CTAs) get the same bits
+        if (ES) t = (t + all[256]) + all[384];
+      }
+      t_ex += clock64() - c0;
+      const float c1 = ok ? -t * inv_n : 0.f;
+      const float2 c1v = make_float2(c1, c1), inv2 = make_float2(inv_n, inv_n);
+      // ---- pass 2: dw = acc * inv_norm - w_hat * (t * inv_norm); the w_hat boxes become the fp32 staging boxes
+      uint4 wq[NG * 4];
+#pragma unroll
+      for (int g = 0; g < NG; ++g)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) wq[g * 4 + q] = *reinterpret_cast<const uint4*>(wbuf + (g >> 1) * kWBox + sw128_off(lane, sub0 + (g & 1) * 4 + q));
+      __syncwarp();                                       // every lane holds its w_hat row: the boxes are free
+      {
+        uint32_t va[32];
+        auto out_group = [&](const uint32_t (&v)[32], int g) {
+          uint8_t* orow = NG == 1 ? sbuf + (it & 1) * kWBox : wbuf + (g & (kNW - 1)) * kWBox;
+          // the store issued two groups ago (same box) must have been read; stores are committed one group each
+          if (lane == 0) { if (NG == 1) tma_store_wait_read<1>(); else tma_store_wait_read<kNW - 1>(); }
           __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 w8 = wq[h * 4 + q];
-            float4 r0, r1;
-            r0.x = fmaf(__uint_as_float(w8.x << 16), nr, __uint_as_float(v[q * 8 + 0])) * inv_n;
-            r0.y = fmaf(__uint_as_float(w8.x & 0xffff0000u), nr, __uint_as_float(v[q * 8 + 1])) * inv_n;
-            r0.z = fmaf(__uint_as_float(w8.y << 16), nr, __uint_as_float(v[q * 8 + 2])) * inv_n;
-            r0.w = fmaf(__uint_as_float(w8.y & 0xffff0000u), nr, __uint_as_float(v[q * 8 + 3])) * inv_n;
-            r1.x = fmaf(__uint_as_float(w8.z << 16), nr, __uint_as_float(v[q * 8 + 4])) * inv_n;
-            r1.y = fmaf(__uint_as_float(w8.z & 0xffff0000u), nr, __uint_as_float(v[q * 8 + 5])) * inv_n;
-            r1.z = fmaf(__uint_as_float(w8.w << 16), nr, __uint_as_float(v[q * 8 + 6])) * inv_n;
-            r1.w = fmaf(__uint_as_float(w8.w & 0xffff0000u), nr, __uint_as_float(v[q * 8 + 7])) * inv_n;
-            *reinterpret_cast<float4*>(orow + sw128_off(lane, 2 * q)) = r0;
-            *reinterpret_cast<float4*>(orow + sw128_off(lane, 2 * q + 1)) = r1;
+            const uint4 w8 = wq[g * 4 + q];
+            const uint32_t w4[4] = {w8.x, w8.y, w8.z, w8.w};
+            float2 r[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              r[k] = __ffma2_rn(make_float2(__uint_as_float(w4[k] << 16), __uint_as_float(w4[k] & 0xffff0000u)), c1v,
+                                __fmul2_rn(make_float2(__uint_as_float(v[q * 8 + 2 * k]), __uint_as_float(v[q * 8 + 2 * k + 1])), inv2));
+            *reinterpret_cast<float4*>(orow + sw128_off(lane, 2 * q)) = make_float4(r[0].x, r[0].y, r[1].x, r[1].y);
+            *reinterpret_cast<float4*>(orow + sw128_off(lane, 2 * q + 1)) = make_float4(r[2].x, r[2].y, r[3].x, r[3].y);
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (p.accumulate) tma_reduce_add_2d(&tmap_dw, orow, hs * EN + nb * 64 + h * 32, cls0);
-            else tma_store_2d(&tmap_dw, orow, hs * EN + nb * 64 + h * 32, cls0);
+            if (p.accumulate) tma_reduce_add_2d(&tmap_dw, orow, e_warp + g * 32, cls0);
+            else tma_store_2d(&tmap_dw, orow, e_warp + g * 32, cls0);
             tma_store_commit();
           }
+        };
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {                    // (one group in flight: the 16 w_hat registers leave no room for two)
+          tmem_ld_x32(t_base + g * 32, va);
+          tmem_ld_wait();
+          out_group(va, g);
         }
       }
+      t_p2 += clock64() - c0;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&tmem_empty[acc]);
-        tma_store_wait_read<0>();                         // every staging box (incl. the reused w_hat boxes) has been read
+        if (NG > 1) tma_store_wait_read<0>();             // the staging boxes are this warp's w_hat boxes: all reads done before the reload
         if (more(it + 1)) issue_w(it + 1);
       }
       __syncwarp();
       t_ep += clock64() - c0;
     }
     if (lane == 0) tma_store_wait_all();
-    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[3] = t_wfull; p.dbg[4] = t_ww; p.dbg[5] = t_ep; }
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[3] = t_wfull; p.dbg[4] = t_ww; p.dbg[5] = t_ep; p.dbg[6] = t_p1; p.dbg[7] = t_ex; p.dbg[8] = t_p2; }
   }
   tc_fence_before();
   if (CS > 1) cluster_sync_all(); else __syncthreads();     // peers may still multicast into / arrive on this CTA
-  if (warp == 5) tmem_dealloc<2 * EN>(tmem_base);
+  if (warp == kMmaWarp) tmem_dealloc<2 * EN>(tmem_base);
+}
+
+// ================================================================================================
+// Stored-probability backward (MODE_PROB forward): the forward kept P_ij = exp2(s2 cos_ij - a_i) (bf16, blocked
+// scratch, target column zero), so   G_ij = scale_i P_ij   with   scale_i = s / (S_i Bt)   (S_i = global sum of P_i.)
+// and no logits are recomputed:
+//     dx_i  = scale_i  sum_j P_ij w_hat_j                      (dx kernels on P, row scale in the slab reduction)
+//     dwh_j = sum_i P_ij (scale_i x_hat_i)                      (dw kernel on P^T and the pre-scaled x_hat)
+//     t_j   = w_hat_j . dwh_j                                    (dw epilogue, from its accumulator)
+// The target element G_iy = s (p_iy - 1) slope / Bt is formed in fp32 from the row statistics and written into the
+// scratch as v = (p_iy - 1) slope S_i by prob_prep_kernel (bf16 rounding of the difference, not of p_iy).
+// ================================================================================================
+constexpr float kProbHeadroom = 58.f;      // log2 units: P <= 2^58, so a row sum over < 2^30 classes stays below 2^88
+
+// a_i = s2 |x_hat_i| (1 + 2^-7) - headroom.  |x.w_hat| <= |x| |w_hat| and bf16 rounding leaves |w_hat| <= 1 + 2^-8.
+__global__ void __launch_bounds__(256) row_bound_kernel(const __nv_bfloat16* __restrict__ x, int64_t n_rows, int emb, float s2,
+                                                        float* __restrict__ bound) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(x + r * emb);
+  float ss = 0.f;
+  for (int c = lane; c < emb / 2; c += 32) {
+    const uint32_t u = p[c];
+    const float a = __uint_as_float(u << 16), b = __uint_as_float(u & 0xffff0000u);
+    ss = fmaf(a, a, fmaf(b, b, ss));
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) bound[r] = s2 * sqrtf(ss) * 1.0078125f - kProbHeadroom;
+}
+
+// One warp per row: x_scaled_i = bf16(x_hat_i * scale_i), row_scale_i, and the target element of the row (if this
+// shard owns it): scratch[i, y] = bf16((p_iy - 1) slope S_i).  With the target in place the dx / dw GEMMs and the radial
+// term the dw epilogue takes from its accumulator need no further special case.
+__global__ void __launch_bounds__(256) prob_prep_kernel(const __nv_bfloat16* __restrict__ x, const int64_t* __restrict__ label,
+                                                        const float* __restrict__ row_sum, const float* __restrict__ row_bound,
+                                                        const float* __restrict__ target_cos, int64_t n_rows, int emb, int n_rb, int64_t n_classes,
+                                                        float s, float m, int margin_kind, float g_scale, __nv_bfloat16* __restrict__ x_scaled,
+                                                        float* __restrict__ row_scale, __nv_bfloat16* __restrict__ scratch) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  const float S = row_sum[r];
+  const float sc = (S > 0.f && S < INFINITY) ? g_scale / S : 0.f;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(x + r * emb);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(x_scaled + r * emb);
+  for (int c = lane; c < emb / 2; c += 32) {
+    const uint32_t u = src[c];
+    dst[c] = pack_bf16x2(__uint_as_float(u << 16) * sc, __uint_as_float(u & 0xffff0000u) * sc);
+  }
+  if (lane == 0) {
+    row_scale[r] = sc;
+    const int64_t y = label[r];
+    if (y >= 0 && y < n_classes) {
+      const float c = target_cos[r];
+      const float pS = exp2f(s * kLog2e * margin_cos(c, m, margin_kind) - row_bound[r]);       // p_iy S_i
+      const float v = (pS - S) * margin_slope(c, m, margin_kind);
+      scratch[(((y >> 6) * n_rb + (r >> 7)) * BM + (r & 127)) * 64 + (y & 63)] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// dx = row_scale_i * sum of the split-K slabs
+__global__ void reduce_dx_scaled_kernel(const float4* __restrict__ part, int ksplit, int64_t n_vec, int vec_per_row, const float* __restrict__ row_scale,
+                                        float4* __restrict__ dx) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = part[i];
+    for (int k = 1; k < ksplit; ++k) {
+      const float4 b = part[(int64_t)k * n_vec + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    const float sc = row_scale[i / vec_per_row];
+    dx[i] = make_float4(a.x * sc, a.y * sc, a.z * sc, a.w * sc);
+  }
 }
 
 }  // namespace tc
@@ -1253,12 +1466,12 @@ static int g_logits_pair = 1;      // 1: CTA-pair (cta_group::2) logits kernels,
 
 template <int STAGES, int MODE, bool NORM = false>
 static int launch_logits2(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tg, const LogitsParams& p, int grid, cudaStream_t st) {
-  const size_t smem = (size_t)(p.emb / BK) * kChunkBytes + (size_t)STAGES * 128 * BK * 2 + (MODE == MODE_GRAD ? kLogitsEpiWarps * 4096 : 0) + 1024 + 256;
+  const size_t smem = (size_t)(p.emb / BK) * kChunkBytes + (size_t)STAGES * 128 * BK * 2 + (MODE != MODE_STATS ? kLogitsEpiWarps * 4096 : 0) + 1024 + 256;
   auto kern = logits2_kernel<STAGES, MODE, NORM>;
   PFC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kLogitsThreads + (NORM ? kNormWarps * 32 : 0));
+  cfg.blockDim = dim3(kLogitsThreads + (NORM ? norm_warps(MODE) * 32 : 0));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1333,7 +1546,7 @@ struct BwdPlan {
   int sm_g, sm_dx, sm_dw;   // SMs (CTAs) per chain
   int ksplit, n_eh, dx_bn;
   bool dx_pair;             // CTA-pair dx kernel (row count a multiple of 512)
-  size_t g_bytes, g_buf_bytes, dxp_bytes, radial_bytes;
+  size_t g_bytes, g_buf_bytes, dxp_bytes;
 };
 
 static int64_t g_chunk_budget_mb;                   // 0 = default
@@ -1390,26 +1603,24 @@ static BwdPlan make_bwd_plan(int64_t n_rows, int64_t n_classes, int emb) {
   pl.g_buf_bytes = (size_t)n_rb * BM * pl.ldg * 2;      // blocked: [ldg / 64][n_rb][128][64] bf16
   pl.g_bytes = pl.g_buf_bytes * pl.ring;
   pl.dxp_bytes = ((size_t)pl.ksplit * n_rows * emb * 4 + 1023) / 1024 * 1024;
-  pl.radial_bytes = ((size_t)n_classes * 4 + 1023) / 1024 * 1024;
   return pl;
 }
 
 size_t tc_bwd_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb) {
   BwdPlan pl = make_bwd_plan(n_rows, n_classes, emb);
-  return pl.g_bytes + pl.dxp_bytes + pl.radial_bytes + 1024;
+  return pl.g_bytes + pl.dxp_bytes + 1024;
 }
 
-static int g_radial_mode = 2;
 static int g_prefetch[3] = {0, 0, 0};               // TMA L2 prefetch knobs: logits (0/1), dx (k-block distance), dw (0/1); measured slower, off
 static long long* g_dbg = nullptr;                   // developer instrumentation buffer (device), see pfc_set_debug_buffer
 static int g_dx_cluster = 2, g_dw_cluster = 2;      // cluster sizes (1, 2 or 4); tuning knobs
 
 template <class Kern, class... Args>
-static int launch_cluster(Kern kern, int grid, int cs, size_t smem, cudaStream_t st, Args... args) {
+static int launch_cluster_threads(Kern kern, int threads, int grid, int cs, size_t smem, cudaStream_t st, Args... args) {
   PFC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3((unsigned)threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1422,6 +1633,10 @@ static int launch_cluster(Kern kern, int grid, int cs, size_t smem, cudaStream_t
   PFC_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
   PFC_LAUNCH_CHECK();
   return 0;
+}
+template <class Kern, class... Args>
+static int launch_cluster(Kern kern, int grid, int cs, size_t smem, cudaStream_t st, Args... args) {
+  return launch_cluster_threads(kern, kThreads, grid, cs, smem, st, args...);
 }
 
 template <int BN, int CS>
@@ -1453,11 +1668,13 @@ static int launch_dw_cs(const CUtensorMap& tg, const CUtensorMap& tx, const CUte
                         cudaStream_t st) {
   constexpr int EN = EMB < 256 ? EMB : 256;
   constexpr int kStage = 2 * kBoxBytes + (EN / 64) * kBoxBytes;
-  constexpr int kEpi = 4 * (EN / 64) * 4096 + 4 * 4096;          // per-warp w_hat boxes + staging
-  constexpr int STAGES = (232448 - 1280 - kEpi) / kStage > 8 ? 8 : (232448 - 1280 - kEpi) / kStage;
+  constexpr int NG = EN / 64;                                    // 32-column groups per epilogue warp
+  constexpr int kEpi = kDwEpiWarps * ((NG + 1) / 2) * 4096 + (NG == 1 ? kDwEpiWarps * 2 * 4096 : 0);   // w_hat boxes (= staging) [+ staging]
+  constexpr int kFixed = 4096 /* partial dots */ + 1024 /* alignment */ + 512 /* barriers */;
+  constexpr int STAGES = (232448 - kFixed - kEpi) / kStage > 8 ? 8 : (232448 - kFixed - kEpi) / kStage;
   static_assert(STAGES >= 2, "dw kernel smem budget");
-  const size_t smem = (size_t)STAGES * kStage + kEpi + 1024 + 256;
-  return launch_cluster(dw_kernel<EMB, STAGES, CS>, grid, CS, smem, st, tg, tx, twh, tdw, p);
+  const size_t smem = (size_t)STAGES * kStage + kEpi + kFixed;
+  return launch_cluster_threads(dw_kernel<EMB, STAGES, CS>, kDwThreads, grid, CS, smem, st, tg, tx, twh, tdw, p);
 }
 
 template <int EMB>
@@ -1465,17 +1682,22 @@ static int launch_dw(const CUtensorMap& tg, const CUtensorMap& tx, const CUtenso
                      int cs, int sms, cudaStream_t st) {
   if (EMB < 128) cs = 1;
   if (EMB == 128 && cs > 2) cs = 2;
-  int n_groups = (n_ct + cs - 1) / cs;
+  if (EMB > 256) cs = 2;                                   // e-split pair: one class tile per cluster, e-slice = cluster rank
+  const int n_groups = EMB > 256 ? n_ct : (n_ct + cs - 1) / cs;
   int max_clusters = sms / cs;
   if (cs == 4) max_clusters = max_clusters * 9 / 10;     // GPCs of 18 SMs strand 2 SMs per GPC with 4-CTA clusters
   if (max_clusters < 1) max_clusters = 1;
   const int clusters = n_groups < max_clusters ? n_groups : max_clusters;
   const int grid = clusters * cs;
-  if constexpr (EMB >= 128) {
-    if (cs == 4) { if constexpr (EMB >= 256) return launch_dw_cs<EMB, 4>(tg, tx, twh, tdw, p, grid, st); }
-    if (cs == 2) return launch_dw_cs<EMB, 2>(tg, tx, twh, tdw, p, grid, st);
+  if constexpr (EMB > 256) {
+    return launch_dw_cs<EMB, 2>(tg, tx, twh, tdw, p, grid, st);
+  } else {
+    if constexpr (EMB >= 128) {
+      if (cs == 4) { if constexpr (EMB >= 256) return launch_dw_cs<EMB, 4>(tg, tx, twh, tdw, p, grid, st); }
+      if (cs == 2) return launch_dw_cs<EMB, 2>(tg, tx, twh, tdw, p, grid, st);
+    }
+    return launch_dw_cs<EMB, 1>(tg, tx, twh, tdw, p, grid, st);
   }
-  return launch_dw_cs<EMB, 1>(tg, tx, twh, tdw, p, grid, st);
 }
 
 // side streams of the pipelined backward (per device)
@@ -1515,12 +1737,11 @@ static int tc_bwd_enqueue(const void* x, const void* w_hat, const float* inv_nor
   PFC_REQUIRE(tensor_emb_ok(emb), PFC_E_SHAPE, "tensor path supports emb in {64,128,256,512}, got %d (use PFC_PATH_CHECK)", emb);
   PFC_REQUIRE(n_rows > 0 && n_classes > 0 && n_classes < (1ll << 30) && n_rows < (1ll << 24), PFC_E_SHAPE, "pfc_bwd: shape out of range");
   const BwdPlan pl = make_bwd_plan(n_rows, n_classes, emb);
-  PFC_REQUIRE(workspace_bytes >= pl.g_bytes + pl.dxp_bytes + pl.radial_bytes, PFC_E_WORKSPACE, "pfc_bwd: workspace too small (%zu < %zu)",
-              workspace_bytes, pl.g_bytes + pl.dxp_bytes + pl.radial_bytes);
+  PFC_REQUIRE(workspace_bytes >= pl.g_bytes + pl.dxp_bytes, PFC_E_WORKSPACE, "pfc_bwd: workspace too small (%zu < %zu)",
+              workspace_bytes, pl.g_bytes + pl.dxp_bytes);
   PFC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, PFC_E_ARG, "pfc_bwd: workspace must be 1024-byte aligned");
   char* g_base = reinterpret_cast<char*>(workspace);
   float* dx_part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.g_bytes);
-  float* radial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.g_bytes + pl.dxp_bytes);
   const auto* wh = reinterpret_cast<const __nv_bfloat16*>(w_hat);
   const int bn = g_logits_pair ? 256 : g_fwd_bn;
   const int n_rb = (int)((n_rows + BM - 1) / BM);
@@ -1531,7 +1752,6 @@ static int tc_bwd_enqueue(const void* x, const void* w_hat, const float* inv_nor
   // chains: G on the caller's stream, dx and dw on side streams when pipelined
   cudaStream_t sG = st, sX = st, sW = st;
   EventPool pool;
-  PFC_CUDA(cudaMemsetAsync(radial, 0, (size_t)n_classes * 4, st));
   if (pl.pipelined) {
     if (int rc = side_streams(&sX, &sW)) return rc;
     PFC_EDGE(st, sX);
@@ -1553,7 +1773,7 @@ static int tc_bwd_enqueue(const void* x, const void* w_hat, const float* inv_nor
     LogitsParams lp{};
     lp.label = label; lp.n_rows = (int)n_rows; lp.n_classes = (int)cc; lp.class_base = (int)c0; lp.emb = emb;
     lp.n_rb = n_rb; lp.n_ct = (int)((cc + bn - 1) / bn); lp.s = s; lp.m = m; lp.margin_kind = margin_kind;
-    lp.row_max = row_max; lp.row_sum = row_sum; lp.g = g; lp.ldg = pl.ldg; lp.g_scale = s * inv_total_batch; lp.radial = radial + c0; lp.radial_mode = g_radial_mode; lp.prefetch = g_prefetch[0];
+    lp.row_max = row_max; lp.row_sum = row_sum; lp.g = g; lp.ldg = pl.ldg; lp.g_scale = s * inv_total_batch; lp.prefetch = g_prefetch[0];
     const uint64_t g_rows = (uint64_t)(pl.ldg / 64) * n_rb * BM;                              // rows of the blocked scratch viewed as [g_rows, 64]
     prof_begin(PH_GRAD, sG);
     if (g_logits_pair) {
@@ -1603,7 +1823,7 @@ static int tc_bwd_enqueue(const void* x, const void* w_hat, const float* inv_nor
     if (int rc2 = make_tmap_bf16_2d(&tg_mn, g, g_rows, 64, 64, 64)) return rc2;              // A MN-major boxes [64 rows x 64 classes] = half a block
     DwParams wp{};
     wp.n_rows = (int)n_rows; wp.n_classes = (int)cc; wp.emb = emb; wp.n_ct = (int)((cc + BM - 1) / BM); wp.n_rb = n_rb;
-    wp.inv_norm = inv_norm + c0; wp.radial = radial + c0; wp.accumulate = accumulate_dw; wp.dbg = g_dbg; wp.prefetch = g_prefetch[2];
+    wp.inv_norm = inv_norm + c0; wp.accumulate = accumulate_dw; wp.dbg = g_dbg; wp.prefetch = g_prefetch[2];
     CUtensorMap twh_e, tdw_e;
     if (int rc3 = make_tmap_bf16_2d(&twh_e, wh + c0 * emb, cc, emb, emb, 32)) return rc3;      // epilogue: per-warp [32 classes x 64 e]
     if (int rc3 = make_tmap_f32_2d(&tdw_e, dw + c0 * emb, cc, emb, emb, 32)) return rc3;       // epilogue: per-warp [32 classes x 32 e] fp32
@@ -1719,7 +1939,7 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
   if (!graph_eligible(st)) return enqueue(st);
   KeyBuilder kb;
   kb.add(1).add(x).add(w_hat).add(inv_norm).add(label).add(row_max).add(row_sum).add(dx).add(dw).add(workspace).add(n_rows).add(n_classes)
-      .add(workspace_bytes).add(emb).add(accumulate_dw).add(s).add(m).add(margin_kind).add(inv_total_batch).add(g_fwd_bn).add(g_logits_pair).add(g_radial_mode)
+      .add(workspace_bytes).add(emb).add(accumulate_dw).add(s).add(m).add(margin_kind).add(inv_total_batch).add(g_fwd_bn).add(g_logits_pair)
       .add(g_dx_cluster).add(g_dw_cluster).add(make_bwd_plan(n_rows, n_classes, emb).chunk).add(g_pipe).add(g_ring).add(g_split[0])
       .add(g_split[1]).add(g_split[2]).add(g_prefetch[0]).add(g_prefetch[1]).add(g_prefetch[2]).add(g_dx_pair);
   return run_cached_graph(kb, st, enqueue);
@@ -1733,38 +1953,76 @@ int launch_normalize_rows(const float* w, const int64_t* index, int64_t n_rows, 
 static int g_fwd_chunks = 4;
 static int g_norm_blocks_per_sm = 2;
 
+// layout of the stored-probability workspace (MODE_PROB forward -> tc_bwd_prob)
+struct ProbLayout {
+  int n_rb;
+  int64_t c_pad;                    // classes rounded up to the 256-class pair tile
+  size_t off_bound, off_tcos, off_scale, off_xs, total;      // scratch (bf16, blocked [c_pad/64][n_rb][128][64]) sits at offset 0
+};
+static ProbLayout prob_layout(int64_t n_rows, int64_t n_classes, int emb) {
+  ProbLayout L{};
+  L.n_rb = (int)((n_rows + BM - 1) / BM);
+  L.c_pad = (n_classes + 255) / 256 * 256;
+  auto up = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+  size_t off = up((size_t)L.n_rb * BM * L.c_pad * 2);
+  L.off_bound = off; off += up((size_t)n_rows * 4);
+  L.off_tcos = off; off += up((size_t)n_rows * 4);
+  L.off_scale = off; off += up((size_t)n_rows * 4);
+  L.off_xs = off; off += up((size_t)n_rows * emb * 2);
+  L.total = off;
+  return L;
+}
+size_t tc_prob_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb) { return prob_layout(n_rows, n_classes, emb).total; }
+
+// w == nullptr: w_hat / inv_norm are already valid (normalised by PartialFC.step), only the logits kernels run.
+// prob_ws != nullptr: MODE_PROB forward (probabilities kept for tc_bwd_prob), else MODE_STATS.
 static int tc_normalize_fwd_enqueue(const float* w, const int64_t* index, const void* x, const int64_t* label, int64_t n_rows, int64_t n_classes,
                                     int emb, float s, float m, int margin_kind, void* w_hat, float* inv_norm, float* part_max, float* part_sum,
-                                    float* target_logit, cudaStream_t st) {
+                                    float* target_logit, char* prob_ws, cudaStream_t st) {
   PFC_REQUIRE(tensor_emb_ok(emb), PFC_E_SHAPE, "tensor path supports emb in {64,128,256,512}, got %d (use PFC_PATH_CHECK)", emb);
   PFC_REQUIRE(n_rows > 0 && n_classes > 0 && n_classes < (1ll << 30) && n_rows < (1ll << 24), PFC_E_SHAPE, "pfc_normalize_fwd_stats: shape out of range");
   auto* wh = reinterpret_cast<__nv_bfloat16*>(w_hat);
   const int bn = g_logits_pair ? 256 : g_fwd_bn;
-  int64_t n_chunks = g_logits_pair ? g_fwd_chunks : 1;                 // the normaliser warps live in the CTA-pair kernel
+  PFC_REQUIRE(!prob_ws || g_logits_pair, PFC_E_ARG, "the stored-probability forward needs the CTA-pair logits kernels");
+  int64_t n_chunks = (g_logits_pair && w) ? g_fwd_chunks : 1;          // the normaliser warps live in the CTA-pair kernel
   if (n_chunks > n_classes / 16384) n_chunks = n_classes / 16384;      // a chunk must keep every SM busy for a while
   if (n_chunks < 1) n_chunks = 1;
   const int64_t chunk = ((n_classes + n_chunks - 1) / n_chunks + 255) / 256 * 256;
   const int grid_full = g_logits_pair ? pair_grid(n_rows, n_classes) : fwd_grid(n_rows, n_classes, bn);
   PFC_CUDA(cudaMemsetAsync(part_sum, 0, sizeof(float) * (size_t)grid_full * 2 * n_rows, st));
   PFC_CUDA(cudaMemsetAsync(target_logit, 0, sizeof(float) * (size_t)n_rows, st));
-  CUtensorMap tx;
+  CUtensorMap tx, tg;
   if (int rc = make_tmap_bf16_2d(&tx, x, n_rows, emb, emb, BM)) return rc;
+  const ProbLayout L = prob_layout(n_rows, n_classes, emb);
+  float* row_bound = nullptr;
+  float* target_cos = nullptr;
+  if (prob_ws) {
+    row_bound = reinterpret_cast<float*>(prob_ws + L.off_bound);
+    target_cos = reinterpret_cast<float*>(prob_ws + L.off_tcos);
+    const uint64_t g_rows = (uint64_t)(L.c_pad / 64) * L.n_rb * BM;                        // blocked scratch viewed as [g_rows, 64]
+    if (int rc = make_tmap_bf16_2d(&tg, prob_ws, g_rows, 64, 64, 32)) return rc;            // epilogue store boxes [32 rows x 64 classes]
+    row_bound_kernel<<<(int)((n_rows + 7) / 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n_rows, emb, s * kLog2e, row_bound);
+    PFC_LAUNCH_CHECK();
+  }
   auto chunk_len = [&](int64_t c0) { return (n_classes - c0 < chunk) ? n_classes - c0 : chunk; };
   // chunk 0 is normalised by the stand-alone kernel; chunk k+1 by the normaliser warps of the logits kernel of chunk k
-  prof_begin(PH_NORMALIZE, st);
-  if (int rc = launch_normalize_rows(index ? w : w, index, chunk_len(0), emb, wh, nullptr, inv_norm, 0, st)) return rc;
-  prof_end(PH_NORMALIZE, st);
+  if (w) {
+    prof_begin(PH_NORMALIZE, st);
+    if (int rc = launch_normalize_rows(w, index, chunk_len(0), emb, wh, nullptr, inv_norm, 0, st)) return rc;
+    prof_end(PH_NORMALIZE, st);
+  }
   int k = 0;
   for (int64_t c0 = 0; c0 < n_classes; c0 += chunk, ++k) {
     const int64_t cc = chunk_len(c0);
     const int64_t n0 = c0 + chunk;                                     // first class of the next chunk
-    const bool has_next = n0 < n_classes;
+    const bool has_next = w && n0 < n_classes;
     CUtensorMap tw;
     if (int rc = make_tmap_bf16_2d(&tw, wh + c0 * emb, cc, emb, emb, g_logits_pair ? 128 : bn)) return rc;
     LogitsParams p{};
     p.label = label; p.n_rows = (int)n_rows; p.n_classes = (int)cc; p.class_base = (int)c0; p.emb = emb;
     p.n_rb = (int)((n_rows + BM - 1) / BM); p.n_ct = (int)((cc + bn - 1) / bn);
     p.s = s; p.m = m; p.margin_kind = margin_kind; p.part_max = part_max; p.part_sum = part_sum; p.target_logit = target_logit; p.accumulate_stats = k > 0; p.prefetch = g_prefetch[0];
+    p.row_bound = row_bound; p.target_cos = target_cos; p.ldg = L.c_pad;
     if (has_next) {
       p.norm_w = index ? w : w + n0 * emb; p.norm_index = index ? index + n0 : nullptr; p.norm_rows = chunk_len(n0);
       p.norm_out = wh + n0 * emb; p.norm_inv = inv_norm + n0;
@@ -1776,6 +2034,7 @@ static int tc_normalize_fwd_enqueue(const float* w, const int64_t* index, const 
     prof_begin(PH_FWD, st);
     int rc;
     if (!g_logits_pair) rc = dispatch_logits<MODE_STATS>(tx, tw, p, bn, grid, st);
+    else if (prob_ws) rc = has_next ? launch_logits2<4, MODE_PROB, true>(tx, tw, tg, p, grid, st) : launch_logits2<4, MODE_PROB>(tx, tw, tg, p, grid, st);
     else if (has_next) rc = launch_logits2<4, MODE_STATS, true>(tx, tw, tw, p, grid, st);
     else rc = launch_logits2<4, MODE_STATS>(tx, tw, tw, p, grid, st);
     if (rc) return rc;
@@ -1787,13 +2046,190 @@ static int tc_normalize_fwd_enqueue(const float* w, const int64_t* index, const 
 int tc_normalize_fwd(const float* w, const int64_t* index, const void* x, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb,
                      float s, float m, int margin_kind, void* w_hat, float* inv_norm, float* part_max, float* part_sum, float* target_logit, cudaStream_t st) {
   auto enqueue = [&](cudaStream_t cs) {
-    return tc_normalize_fwd_enqueue(w, index, x, label, n_rows, n_classes, emb, s, m, margin_kind, w_hat, inv_norm, part_max, part_sum, target_logit, cs);
+    return tc_normalize_fwd_enqueue(w, index, x, label, n_rows, n_classes, emb, s, m, margin_kind, w_hat, inv_norm, part_max, part_sum, target_logit, nullptr, cs);
   };
   if (!graph_eligible(st)) return enqueue(st);
   KeyBuilder kb;
   kb.add(2).add(w).add(index).add(x).add(label).add(n_rows).add(n_classes).add(emb).add(s).add(m).add(margin_kind).add(w_hat).add(inv_norm).add(part_max)
       .add(part_sum).add(target_logit).add(g_fwd_bn).add(g_logits_pair).add(g_fwd_chunks).add(g_norm_blocks_per_sm).add(g_prefetch[0]);
   return run_cached_graph(kb, st, enqueue);
+}
+
+// ---- stored-probability path: forward keeps P, backward = per-row prep + (dx || dw) -------------
+int tc_normalize_fwd_prob(const float* w, const int64_t* index, const void* x, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb,
+                          float s, float m, int margin_kind, void* w_hat, float* inv_norm, float* part_max, float* part_sum, float* target_logit,
+                          void* prob_ws, size_t prob_ws_bytes, cudaStream_t st) {
+  PFC_REQUIRE(prob_ws && prob_ws_bytes >= tc_prob_workspace_bytes(n_rows, n_classes, emb), PFC_E_WORKSPACE,
+              "pfc_normalize_fwd_prob: probability workspace too small (%zu < %zu)", prob_ws_bytes, tc_prob_workspace_bytes(n_rows, n_classes, emb));
+  PFC_REQUIRE((reinterpret_cast<uintptr_t>(prob_ws) & 1023) == 0, PFC_E_ARG, "pfc_normalize_fwd_prob: workspace must be 1024-byte aligned");
+  auto enqueue = [&](cudaStream_t cs) {
+    return tc_normalize_fwd_enqueue(w, index, x, label, n_rows, n_classes, emb, s, m, margin_kind, w_hat, inv_norm, part_max, part_sum, target_logit,
+                                    reinterpret_cast<char*>(prob_ws), cs);
+  };
+  if (!graph_eligible(st)) return enqueue(st);
+  KeyBuilder kb;
+  kb.add(3).add(w).add(index).add(x).add(label).add(n_rows).add(n_classes).add(emb).add(s).add(m).add(margin_kind).add(w_hat).add(inv_norm).add(part_max)
+      .add(part_sum).add(target_logit).add(prob_ws).add(g_fwd_bn).add(g_logits_pair).add(g_fwd_chunks).add(g_norm_blocks_per_sm).add(g_prefetch[0]);
+  return run_cached_graph(kb, st, enqueue);
+}
+
+struct ProbBwdPlan {
+  bool dx_pair, side_by_side;
+  int dx_bn, n_eh, ksplit, dcs, dx_ctas, sm_dw;
+  size_t dxp_bytes;
+};
+static int g_prob_dx_sms = 0;            // 0 = choose from the shape; > 0: SM budget of the dx kernel (tuning knob)
+static float g_prob_dw_rate = 0.42f;     // measured per-SM throughput of the dw kernel relative to the dx kernel
+static int g_sweep_lead = 0;             // classes the faster of dx / dw may run ahead of the other (0 = not paced: measured no gain)
+
+static ProbBwdPlan make_prob_bwd_plan(int64_t n_rows, int64_t n_classes, int emb) {
+  ProbBwdPlan pl{};
+  const int64_t n_rb = (n_rows + BM - 1) / BM;
+  const int sms = sm_count();
+  pl.dx_bn = emb < 256 ? emb : 256;
+  pl.n_eh = emb / pl.dx_bn;
+  pl.dx_pair = g_dx_pair && g_logits_pair && emb >= 256 && n_rb % 4 == 0;
+  pl.dcs = g_dx_cluster;
+  if (pl.dx_bn < 128) pl.dcs = 1;
+  if (pl.dx_bn == 128 && pl.dcs > 2) pl.dcs = 2;
+  const int64_t units = pl.dx_pair ? (n_rb / 4) * pl.n_eh * 2 : ((n_rb + pl.dcs - 1) / pl.dcs) * pl.dcs * pl.n_eh;   // CTAs per k-split
+  const int64_t max_ks = (n_classes + BK - 1) / BK < 64 ? (n_classes + BK - 1) / BK : 64;
+  // dx and dw run side by side on disjoint SMs; pick the k-split whose slower side finishes first
+  int64_t best = 0;
+  float best_t = 0.f;
+  for (int64_t ks = 1; ks <= max_ks && units * ks <= sms - 16; ++ks) {
+    const float t_dx = 1.f / (float)(units * ks), t_dw = 1.f / (g_prob_dw_rate * (float)(sms - units * ks));
+    const float t = g_prob_dx_sms > 0 ? fabsf((float)(units * ks - g_prob_dx_sms)) : (t_dx > t_dw ? t_dx : t_dw);
+    if (best == 0 || t < best_t) { best = ks; best_t = t; }
+  }
+  pl.side_by_side = best > 0;
+  if (!pl.side_by_side) {                 // more dx units than SMs to spare: one kernel after the other, each on the whole GPU
+    best = sms / units;
+    if (best < 1) best = 1;
+    if (best > max_ks) best = max_ks;
+  }
+  pl.ksplit = (int)best;
+  pl.dx_ctas = (int)(units * best);
+  pl.sm_dw = pl.side_by_side ? sms - pl.dx_ctas : sms;
+  pl.dxp_bytes = ((size_t)pl.ksplit * n_rows * emb * 4 + 1023) / 1024 * 1024;
+  return pl;
+}
+
+size_t tc_bwd_prob_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb) {
+  const ProbBwdPlan pl = make_prob_bwd_plan(n_rows, n_classes, emb);
+  return pl.dxp_bytes + 1024;       // split-K slabs + the two sweep counters
+}
+
+static int tc_bwd_prob_enqueue(const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_sum, int64_t n_rows, int64_t n_classes,
+                               int emb, float s, float m, int margin_kind, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
+                               const void* x, char* prob_ws, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  PFC_REQUIRE(tensor_emb_ok(emb), PFC_E_SHAPE, "tensor path supports emb in {64,128,256,512}, got %d (use PFC_PATH_CHECK)", emb);
+  PFC_REQUIRE(n_rows > 0 && n_classes > 0 && n_classes < (1ll << 30) && n_rows < (1ll << 24), PFC_E_SHAPE, "pfc_bwd_prob: shape out of range");
+  const ProbLayout L = prob_layout(n_rows, n_classes, emb);
+  const ProbBwdPlan pl = make_prob_bwd_plan(n_rows, n_classes, emb);
+  PFC_REQUIRE(workspace_bytes >= pl.dxp_bytes + 1024, PFC_E_WORKSPACE, "pfc_bwd_prob: workspace too small (%zu < %zu)", workspace_bytes,
+              pl.dxp_bytes + 1024);
+  int* sweep_ctr = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + pl.dxp_bytes);      // [0] dx, [1] dw
+  PFC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, PFC_E_ARG, "pfc_bwd_prob: workspace must be 1024-byte aligned");
+  float* dx_part = reinterpret_cast<float*>(workspace);
+  auto* scratch = reinterpret_cast<__nv_bfloat16*>(prob_ws);
+  const float* row_bound = reinterpret_cast<const float*>(prob_ws + L.off_bound);
+  const float* target_cos = reinterpret_cast<const float*>(prob_ws + L.off_tcos);
+  float* row_scale = reinterpret_cast<float*>(prob_ws + L.off_scale);
+  auto* xs = reinterpret_cast<__nv_bfloat16*>(prob_ws + L.off_xs);
+  const auto* wh = reinterpret_cast<const __nv_bfloat16*>(w_hat);
+  const int n_rb = L.n_rb;
+  const float g_scale = s * inv_total_batch;
+
+  // (1) per-row prep: scaled x_hat, row scales, target elements of the scratch
+  prof_begin(PH_GRAD, st);
+  prob_prep_kernel<<<(int)((n_rows + 7) / 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), label, row_sum, row_bound, target_cos, n_rows, emb,
+                                                            n_rb, n_classes, s, m, margin_kind, g_scale, xs, row_scale, scratch);
+  PFC_LAUNCH_CHECK();
+  prof_end(PH_GRAD, st);
+
+  // (2) dx || dw over the whole shard
+  const uint64_t g_rows = (uint64_t)(L.c_pad / 64) * n_rb * BM;
+  CUtensorMap tg_k, tw_mn, tg_mn, tx_mn, twh_e, tdw_e;
+  if (int rc = make_tmap_bf16_2d(&tg_k, scratch, g_rows, 64, 64, BM)) return rc;           // dx A: [128 rows x 64 classes] blocks
+  if (int rc = make_tmap_bf16_2d(&tw_mn, wh, n_classes, emb, emb, 64)) return rc;          // dx B: MN-major boxes [64 classes x 64 e]
+  if (int rc = make_tmap_bf16_2d(&tg_mn, scratch, g_rows, 64, 64, 64)) return rc;          // dw A: [64 rows x 64 classes] boxes
+  if (int rc = make_tmap_bf16_2d(&tx_mn, xs, n_rows, emb, emb, 64)) return rc;             // dw B: scaled x_hat, [64 rows x 64 e]
+  if (int rc = make_tmap_bf16_2d(&twh_e, wh, n_classes, emb, emb, 32)) return rc;          // dw epilogue: per-warp [32 classes x 64 e]
+  if (int rc = make_tmap_f32_2d(&tdw_e, dw, n_classes, emb, emb, 32)) return rc;           // dw epilogue: per-warp [32 classes x 32 e] fp32
+  cudaStream_t sX = st, sW = st;
+  EventPool pool;
+  const bool paced = pl.side_by_side && g_sweep_lead > 0;
+  if (paced) PFC_CUDA(cudaMemsetAsync(sweep_ctr, 0, 2 * sizeof(int), st));
+  if (pl.side_by_side) {
+    if (int rc = side_streams(&sX, &sW)) return rc;
+    PFC_EDGE(st, sX);
+    PFC_EDGE(st, sW);
+  }
+  DxParams dp{};
+  if (paced) dp.sweep = SweepSync{sweep_ctr, sweep_ctr + 1, g_sweep_lead};
+  dp.n_rows = (int)n_rows; dp.n_classes = (int)n_classes; dp.emb = emb; dp.n_rb = n_rb; dp.n_eh = pl.n_eh; dp.ksplit = pl.ksplit;
+  dp.dx_part = dx_part; dp.accumulate = 0; dp.prefetch = g_prefetch[1]; dp.strided = pl.side_by_side ? 1 : 0;
+  int rc = 0;
+  static const int exp_mode = getenv("FEDFR_EXP") ? atoi(getenv("FEDFR_EXP")) : 0;      // timing experiments only (wrong results)
+  prof_begin(PH_DX, sX);
+  if (exp_mode == 3) rc = 0;                   // dw alone
+  else if (pl.dx_pair) rc = launch_dx2(tg_k, tw_mn, dp, pl.dx_ctas, sX);
+  else switch (pl.dx_bn) {
+    case 256: rc = launch_dx<256>(tg_k, tw_mn, dp, pl.dx_ctas, pl.dcs, sX); break;
+    case 128: rc = launch_dx<128>(tg_k, tw_mn, dp, pl.dx_ctas, pl.dcs, sX); break;
+    default: rc = launch_dx<64>(tg_k, tw_mn, dp, pl.dx_ctas, pl.dcs, sX); break;
+  }
+  if (rc) return rc;
+  prof_end(PH_DX, sX);
+  DwParams wp{};
+  if (paced) wp.sweep = SweepSync{sweep_ctr + 1, sweep_ctr, g_sweep_lead};
+  wp.n_rows = (int)n_rows; wp.n_classes = (int)n_classes; wp.emb = emb; wp.n_ct = (int)((n_classes + BM - 1) / BM); wp.n_rb = n_rb;
+  wp.inv_norm = inv_norm; wp.accumulate = accumulate_dw; wp.dbg = g_dbg; wp.prefetch = g_prefetch[2];
+  prof_begin(PH_DW, sW);
+  if (exp_mode == 4) rc = 0;                   // dx alone
+  else switch (emb) {
+    case 512: rc = launch_dw<512>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
+    case 256: rc = launch_dw<256>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
+    case 128: rc = launch_dw<128>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
+    default: rc = launch_dw<64>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
+  }
+  if (rc) return rc;
+  prof_end(PH_DW, sW);
+  if (pl.side_by_side) {
+    PFC_EDGE(sX, st);
+    PFC_EDGE(sW, st);
+  }
+  // (3) dx = row scale x sum of the split-K slabs
+  const int64_t n_vec = n_rows * emb / 4;
+  int64_t blocks = (n_vec + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
+  reduce_dx_scaled_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(dx_part), pl.ksplit, n_vec, emb / 4, row_scale,
+                                                       reinterpret_cast<float4*>(dx));
+  PFC_LAUNCH_CHECK();
+  return 0;
+}
+
+int tc_bwd_prob(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_sum, int64_t n_rows, int64_t n_classes,
+                int emb, float s, float m, int margin_kind, float inv_total_batch, float* dx, float* dw, int accumulate_dw, void* prob_ws,
+                size_t prob_ws_bytes, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  PFC_REQUIRE(prob_ws && prob_ws_bytes >= tc_prob_workspace_bytes(n_rows, n_classes, emb), PFC_E_WORKSPACE, "pfc_bwd_prob: probability workspace too small");
+  auto enqueue = [&](cudaStream_t cs) {
+    return tc_bwd_prob_enqueue(w_hat, inv_norm, label, row_sum, n_rows, n_classes, emb, s, m, margin_kind, inv_total_batch, dx, dw, accumulate_dw, x,
+                               reinterpret_cast<char*>(prob_ws), workspace, workspace_bytes, cs);
+  };
+  if (!graph_eligible(st)) return enqueue(st);
+  KeyBuilder kb;
+  kb.add(4).add(x).add(w_hat).add(inv_norm).add(label).add(row_sum).add(dx).add(dw).add(workspace).add(prob_ws).add(n_rows).add(n_classes)
+      .add(workspace_bytes).add(emb).add(accumulate_dw).add(s).add(m).add(margin_kind).add(inv_total_batch).add(g_logits_pair).add(g_dx_cluster)
+      .add(g_dw_cluster).add(g_prob_dx_sms).add(g_prob_dw_rate).add(g_sweep_lead).add(g_prefetch[1]).add(g_prefetch[2]).add(g_dx_pair);
+  return run_cached_graph(kb, st, enqueue);
+}
+
+void tc_set_prob_split(int dx_sms, float dw_rate, int sweep_lead) {
+  g_prob_dx_sms = dx_sms > 0 ? dx_sms : 0;
+  if (dw_rate > 0.05f && dw_rate < 4.f) g_prob_dw_rate = dw_rate;
+  if (sweep_lead >= 0) g_sweep_lead = sweep_lead;
 }
 
 void tc_set_fwd_overlap(int chunks, int norm_blocks_per_sm) {
@@ -1812,7 +2248,6 @@ void tc_set_pipeline(int on, int sm_g, int sm_dx, int sm_dw, int ring) {
 void tc_set_chunk_mb(int mb) { g_chunk_budget_mb = mb > 0 ? mb : 0; }
 void tc_set_fwd_bn(int bn) { g_fwd_bn = (bn == 256) ? 256 : 128; }
 void tc_set_debug(long long* p) { g_dbg = p; }
-void tc_set_radial_mode(int m) { g_radial_mode = m; }
 void tc_set_logits_pair(int on) { g_logits_pair = on ? 1 : 0; }
 void tc_set_clusters(int dx_cs, int dw_cs) {
   if (dx_cs == 1 || dx_cs == 2 || dx_cs == 4) g_dx_cluster = dx_cs;

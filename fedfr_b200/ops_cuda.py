@@ -3,9 +3,16 @@
 Each method takes/returns torch CUDA tensors, passes raw pointers + the current stream to
 ``libfedfr_b200.so`` and raises ``RuntimeError`` on any non-zero return code.
 """
+import os
+
 import torch
 
 from . import _native as N
+
+# backward flavour of the tensor path: "prob" (default) keeps the unnormalised probabilities of the forward GEMM and
+# needs no recomputation GEMM; "recompute" re-derives the logits in the backward (no [Bt, Cs] bf16 workspace, no
+# restriction on s * |x|, see include/fedfr_b200.h).
+BWD_MODE = os.environ.get("FEDFR_BWD_MODE", "prob")
 
 
 def _stream(device):
@@ -24,6 +31,10 @@ class CudaOps:
         with torch.cuda.device(self.device):
             N.check(N.lib.pfc_query_device(self.device.index or 0, None, None, None), "pfc_query_device")
         self._ws = {}
+        self.bwd_mode = BWD_MODE if path == N.PATH_TENSOR else "recompute"
+        if self.bwd_mode not in ("prob", "recompute"):
+            raise ValueError("FEDFR_BWD_MODE must be 'prob' or 'recompute'")
+        self._prob = None       # (workspace, bt, cs, emb) of the last stored-probability forward
 
     # ------------------------------------------------------------------ helpers
     def _persist(self, name, shape, dtype):
@@ -130,11 +141,25 @@ class CudaOps:
         part = self._persist("part", (2, n_part, bt), torch.float32)
         tz = self._persist("target_logit", (bt,), torch.float32)
         st = _stream(self.device)
-        N.check(N.lib.pfc_normalize_fwd_stats(N.ptr(sub_weight), None, N.ptr(x_hat), N.ptr(label), bt, n, emb, float(s), float(m), int(margin_kind), N.ptr(w_hat),
-                                              N.ptr(inv), N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), self.path, st), "pfc_normalize_fwd_stats")
+        self._prob = None
+        if self.bwd_mode == "prob":
+            pws, off, nbytes = self._prob_ws(bt, n, emb)
+            N.check(N.lib.pfc_normalize_fwd_prob(N.ptr(sub_weight), None, N.ptr(x_hat), N.ptr(label), bt, n, emb, float(s), float(m), int(margin_kind),
+                                                 N.ptr(w_hat), N.ptr(inv), N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), pws.data_ptr() + off, nbytes, st),
+                    "pfc_normalize_fwd_prob")
+            self._prob = (pws, off, nbytes, bt, n, emb)
+        else:
+            N.check(N.lib.pfc_normalize_fwd_stats(N.ptr(sub_weight), None, N.ptr(x_hat), N.ptr(label), bt, n, emb, float(s), float(m), int(margin_kind),
+                                                  N.ptr(w_hat), N.ptr(inv), N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), self.path, st),
+                    "pfc_normalize_fwd_stats")
         stats = self._persist("stats", (bt, 3), torch.float32)
         N.check(N.lib.pfc_merge_stats(N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), n_part, bt, N.ptr(stats), st), "pfc_merge_stats")
         return w_hat, inv, stats
+
+    def _prob_ws(self, bt, cs, emb):
+        nbytes = N.lib.pfc_prob_workspace_bytes(bt, cs, emb)
+        ws = self._buf("prob", nbytes + 1024)
+        return ws, (-ws.data_ptr()) % 1024, nbytes
 
     def cast_features(self, total_features):
         if self.path == N.PATH_CHECK:
@@ -152,8 +177,17 @@ class CudaOps:
         part = self._persist("part", (2, n_part, bt), torch.float32)
         tz = self._persist("target_logit", (bt,), torch.float32)
         st = _stream(self.device)
-        N.check(N.lib.pfc_fwd_stats(N.ptr(x_hat), N.ptr(w_hat), N.ptr(label), bt, cs, emb, float(s), float(m), int(margin_kind), N.ptr(part[0]), N.ptr(part[1]),
-                                    N.ptr(tz), self.path, st), "pfc_fwd_stats")
+        self._prob = None
+        if self.bwd_mode == "prob":     # w == NULL: w_hat / inv_norm are already valid
+            pws, off, nbytes = self._prob_ws(bt, cs, emb)
+            inv = self._persist("inv_norm", (cs,), torch.float32)
+            N.check(N.lib.pfc_normalize_fwd_prob(None, None, N.ptr(x_hat), N.ptr(label), bt, cs, emb, float(s), float(m), int(margin_kind), N.ptr(w_hat),
+                                                 N.ptr(inv), N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), pws.data_ptr() + off, nbytes, st),
+                    "pfc_normalize_fwd_prob")
+            self._prob = (pws, off, nbytes, bt, cs, emb)
+        else:
+            N.check(N.lib.pfc_fwd_stats(N.ptr(x_hat), N.ptr(w_hat), N.ptr(label), bt, cs, emb, float(s), float(m), int(margin_kind), N.ptr(part[0]),
+                                        N.ptr(part[1]), N.ptr(tz), self.path, st), "pfc_fwd_stats")
         stats = torch.empty((bt, 3), dtype=torch.float32, device=self.device)
         N.check(N.lib.pfc_merge_stats(N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), n_part, bt, N.ptr(stats), st), "pfc_merge_stats")
         return stats
@@ -174,6 +208,16 @@ class CudaOps:
         bt, emb = x_hat.shape
         cs = w_hat.shape[0]
         dx = self._persist("dx", (bt, emb), torch.float32)
+        if self._prob is not None and self._prob[3:] == (bt, cs, emb):      # the forward kept its probabilities
+            pws, poff, pbytes = self._prob[:3]
+            self._prob = None
+            nbytes = N.lib.pfc_bwd_prob_workspace_bytes(bt, cs, emb)
+            ws = self._buf("bwd_prob", nbytes + 1024)
+            off = (-ws.data_ptr()) % 1024
+            N.check(N.lib.pfc_bwd_prob(N.ptr(x_hat), N.ptr(w_hat), N.ptr(inv_norm), N.ptr(label), N.ptr(row_sum), bt, cs, emb, float(s), float(m),
+                                       int(margin_kind), float(inv_total_batch), N.ptr(dx), N.ptr(dw), 1 if accumulate else 0, pws.data_ptr() + poff,
+                                       pbytes, ws.data_ptr() + off, ws.numel() - off, _stream(self.device)), "pfc_bwd_prob")
+            return dx
         nbytes = N.lib.pfc_bwd_workspace_bytes(bt, cs, emb, self.path)
         ws = self._buf("bwd", nbytes + 1024)
         off = (-ws.data_ptr()) % 1024

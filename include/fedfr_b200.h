@@ -151,6 +151,35 @@ int pfc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64
             float s, float m, int margin_kind, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
             void* workspace, size_t workspace_bytes, int path, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Stored-probability variant (tensor path only; the default of fedfr_b200.PartialFC)
+ *                                                  partial_fc.py:137-168 without the recomputation GEMM
+ * ------------------------------------------------------------------------------------------------
+ * pfc_normalize_fwd_prob = pfc_normalize_fwd_stats, and additionally keeps
+ *     P_ij = exp2(s log2e (x_i . w_hat_j) - a_i)      bf16, blocked [ceil(C/256)*4][ceil(Bt/128)][128][64]
+ * in prob_ws, where a_i = s log2e |x_i| (1 + 2^-7) - 58 is an upper bound of every logit of row i (in log2 units)
+ * minus a fixed headroom, so no row maximum is needed before the GEMM.  The partial statistics it emits are
+ * (a_i ln 2, sum_j P_ij): valid (max, sum-exp) pairs for pfc_merge_stats / pfc_finalize_stats, and equal on every rank.
+ * The target column is stored as zero; pfc_bwd_prob writes it from fp32 statistics.
+ * Domain: rows whose largest logit lies more than ~184 log2 units (127 nats) below s |x_i| underflow to P = 0
+ * (cannot happen for unit-norm features with s <= 64; use pfc_normalize_fwd_stats + pfc_bwd otherwise).
+ *   w == NULL: w_hat / inv_norm are already valid and only the logits kernels run.
+ *   prob_ws: device scratch of pfc_prob_workspace_bytes(...) bytes, 1024-byte aligned, handed unchanged to pfc_bwd_prob. */
+size_t pfc_prob_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb);
+int pfc_normalize_fwd_prob(const float* w, const int64_t* index, const void* x, const int64_t* label,
+                           int64_t n_rows, int64_t n_classes, int emb, float s, float m, int margin_kind, void* w_hat,
+                           float* inv_norm, float* part_max, float* part_sum, float* target_logit,
+                           void* prob_ws, size_t prob_ws_bytes, void* stream);
+
+/* Backward of pfc_normalize_fwd_prob: same outputs as pfc_bwd.  row_sum = the GLOBAL sum_j P_ij of
+ * pfc_finalize_stats.  G_ij = (s / (row_sum_i total_batch)) P_ij is never formed: dx = row-scaled P . w_hat,
+ * dwh = P^T . (row-scaled x); the radial term w_hat_j . dwh_j of the normalize backward is taken from the dw accumulator. */
+size_t pfc_bwd_prob_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb);
+int pfc_bwd_prob(const void* x, const void* w_hat, const float* inv_norm, const int64_t* label, const float* row_sum,
+                 int64_t n_rows, int64_t n_classes, int emb, float s, float m, int margin_kind, float inv_total_batch,
+                 float* dx, float* dw, int accumulate_dw, void* prob_ws, size_t prob_ws_bytes,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* losses.CosFace.forward on materialised logits (dense twin, client.py:430): in place
  * cosine[i, label[i]] -= m for label[i] != -1, then out = cosine * s.      losses.py:23-29 */
 int pfc_cosface_dense(float* cosine, const int64_t* label, int64_t n_rows, int64_t n_classes, float s, float m,
