@@ -444,7 +444,9 @@ def run_ours(args):
     cnt = (CT.c_int * 5)()
     N.lib.pfc_profile_collect(ms, cnt)
     N.lib.pfc_profile_enable(0)
-    names = ["normalize_rows", "logits_stats(fwd)", "logits_grad(bwd)", "dx", "dw"]
+    prob = head._ops.bwd_mode == "prob"
+    names = (["normalize_rows(chunk 0)", "logits_prob(fwd, normalises the next chunk)", "prob_prep", "dx", "dw"] if prob else
+             ["normalize_rows(chunk 0)", "logits_stats(fwd, normalises the next chunk)", "logits_grad(bwd)", "dx", "dw"])
     phase_ms = {n: ms[i] / prof_steps for i, n in enumerate(names)}
     phase_launches = {n: cnt[i] // prof_steps for i, n in enumerate(names)}
 
@@ -458,19 +460,32 @@ def run_ours(args):
     Bt = B * world
     Cs = head.num_sample if sr < 1 else head.num_local
     gemm_flops = 2.0 * Bt * Cs * E                       # one GEMM of the three (6*Bt*Cs*E per step)
-    gemm_phases = ["logits_stats(fwd)", "logits_grad(bwd)", "dx", "dw"]
+    gemm_phases = [names[1], "dx", "dw"] + ([] if prob else [names[2]])
     dom = max(gemm_phases, key=lambda n: phase_ms[n])
     dom_launches = max(phase_launches[dom], 1)
     dom_ms = phase_ms[dom]
     achieved = gemm_flops / (dom_ms * 1e-3) / 1e12
+    # DRAM bytes of the dominant kernel per launch from the committed `ncu --set full` capture (profiles/traffic.json, c3 at N=1 only)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if world == 1 and args.workload == "c3" and os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("prob" if prob else "recompute", {}).get(dom.split("(")[0])
+        except Exception:                                 # noqa: BLE001
+            traffic = None
+    # HBM view of the whole step: bytes this design moves per step, not the minimum any design needs
+    design_bytes = (16.0 * Cs * E + 6.0 * Bt * Cs) if prob else (18.0 * Cs * E + 6.0 * Bt * Cs)
     roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+            "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
             "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside the step loop); burst {peaks['tflops']}",
             "flops_per_launch": gemm_flops / dom_launches, "ms_per_launch": dom_ms / dom_launches, "launches_per_step": dom_launches,
+            "note": "dx and dw run side by side on disjoint SM subsets (their phase times overlap); achieved = the kernel's GEMM FLOPs / its own duration",
             "phase_ms_per_step": phase_ms,
             "step_tflops": 6.0 * Bt * Cs * E / (ms_step * 1e-3) / 1e12 / 1.0,
             "step_frac_of_burst_peak_per_gpu": 6.0 * Bt * Cs * E / (ms_step * 1e-3) / 1e12 / peaks["tflops"],
-            "normalize_gbs": Cs * E * 6.0 / (phase_ms["normalize_rows"] * 1e-3) / 1e9 if phase_ms["normalize_rows"] > 0 else None}
+            "step_hbm": {"design_bytes_per_step": design_bytes, "gbs": design_bytes / (ms_step * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                         "frac": design_bytes / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+            "backward": "stored probabilities (3 GEMMs)" if prob else "recompute (4 GEMMs)"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

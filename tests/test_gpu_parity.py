@@ -364,3 +364,69 @@ def test_fused_step_matches_torch_sgd(pkg, sample_rate, nesterov, dampening, mon
         assert rel(outs[-1][0], outs[-2][0]) < 1e-3
     if sample_rate == 1.0 and not nesterov and dampening == 0.0:
         assert torch.equal(heads[0].weight, heads[1].weight), "same arithmetic as torch's foreach SGD -> same bits"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# stored-probability backward (the default of the tensor path) against the recomputing backward and the oracle
+# ---------------------------------------------------------------------------------------------------------------
+def _run_mode(pkg, mode, cfg, w, x, y):
+    head = _make_head(pkg, cfg, w, False)
+    head._ops.bwd_mode = mode
+    opt = torch.optim.SGD([{"params": head.parameters()}], lr=0.1, momentum=0.9)
+    x_grad, loss = head.forward_backward(y.to(head.device), x.to(head.device), opt)
+    return x_grad.cpu(), float(loss), head.sub_weight.grad.cpu()
+
+
+@pytest.mark.parametrize("B,C,E,s,margin", [(512, 30000, 512, 64.0, "cosface"), (300, 5000, 256, 30.0, "arcface"), (130, 700, 128, 64.0, "cosface"),
+                                             (70, 300, 64, 64.0, "cosface")])
+def test_backward_modes_agree(pkg, B, C, E, s, margin):
+    """'prob' (forward keeps exp2(logit - bound), no recomputation GEMM) and 'recompute' are two routes to the same
+    partial_fc.py:150-168 quantities: each within the bf16 tolerance of the oracle, every embedding size / cluster shape."""
+    from oracle import partial_fc_oracle as O
+    g = torch.Generator().manual_seed(B + C + E)
+    w = torch.randn(C, E, generator=g) * 0.01
+    y = torch.randint(0, C, (B,), generator=g)
+    y[1] = y[0]                                                        # two rows of one class
+    x = torch.nn.functional.normalize(torch.randn(B, E, generator=g) + 2.0 * torch.nn.functional.normalize(w[y]) * (torch.arange(B) % 4 == 0)[:, None])
+    m = 0.4 if margin == "cosface" else 0.5
+    ref = O.forward_backward([x], [y], [w], C, s, m, margin=margin)
+    cfg = dict(batch=B, num_classes=C, emb=E, s=s, m=m, sample_rate=1.0, loss=margin)
+    for mode in ("prob", "recompute"):
+        dx, loss, dw = _run_mode(pkg, mode, cfg, w, x, y)
+        assert abs(loss - float(ref.loss)) <= 1e-2 * float(ref.loss), mode
+        assert rel(dx, ref.x_grad[0]) < 1e-2, mode
+        assert rel(dw, ref.dw[0]) < 1e-2, mode
+
+
+def test_prob_unnormalised_features(pkg):
+    """forward_backward uses the features as passed (partial_fc.py:110): row norms from 0.3 to 1.6 move the per-row
+    bound of the stored-probability forward; s |x| stays inside its documented range (include/fedfr_b200.h)."""
+    from oracle import partial_fc_oracle as O
+    B, C, E, s = 256, 6000, 512, 30.0
+    g = torch.Generator().manual_seed(77)
+    w = torch.randn(C, E, generator=g) * 0.01
+    y = torch.randint(0, C, (B,), generator=g)
+    x = torch.nn.functional.normalize(torch.randn(B, E, generator=g)) * torch.linspace(0.3, 1.6, B)[:, None]
+    x[3] = 0.0                                                         # a zero row: every logit 0, uniform softmax
+    ref = O.forward_backward([x], [y], [w], C, s, 0.4)
+    dx, loss, dw = _run_mode(pkg, "prob", dict(batch=B, num_classes=C, emb=E, s=s, m=0.4, sample_rate=1.0), w, x, y)
+    assert abs(loss - float(ref.loss)) <= 1e-2 * float(ref.loss)
+    assert rel(dx, ref.x_grad[0]) < 1e-2
+    assert rel(dw, ref.dw[0]) < 1e-2
+
+
+@pytest.mark.parametrize("mode", ["prob", "recompute"])
+def test_hard_sample_clamp_tensor_path(pkg, mode):
+    """cos = -1 to the own class with s = 64: the target probability underflows, the loss takes the 1e-30 clamp
+    (partial_fc.py:162) and the target gradient is -s / Bt -- also when the probability was never stored."""
+    from oracle import partial_fc_oracle as O
+    B, C, E = 8, 300, 64
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(C, E, generator=g)
+    x = torch.nn.functional.normalize(torch.randn(B, E, generator=g))
+    y = torch.randint(0, C, (B,), generator=g)
+    x[0] = -torch.nn.functional.normalize(w[y[0]], dim=0)
+    ref = O.forward_backward([x], [y], [w], C, 64.0, 0.4)
+    dx, loss, dw = _run_mode(pkg, mode, dict(batch=B, num_classes=C, emb=E, s=64.0, m=0.4, sample_rate=1.0), w, x, y)
+    assert abs(loss - float(ref.loss)) < 1e-2 * float(ref.loss)
+    assert rel(dx, ref.x_grad[0]) < 1e-2 and rel(dw, ref.dw[0]) < 1e-2

@@ -1,6 +1,6 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, bench lines (c3 + c5), ncu launch list, ncu full captures of the dominant kernels.
-# usage: tools/gpu_round.sh <tag> [skip-tests] [skip-ncu]
+# One GPU-box visit: parity tests, bench lines (c3 + c5 + reference arm), per-rank shape bench, ncu launch list,
+# ncu full captures of the dominant kernels.      usage: tools/gpu_round.sh <tag> [skip-tests] [skip-ncu]
 TAG=${1:-rXX}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
@@ -11,14 +11,16 @@ if [ "$2" != "skip-tests" ]; then
 fi
 timeout 600 python bench.py --steps 20 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
 cat $OUT/bench.json
+FEDFR_BWD_MODE=recompute timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $OUT/bench_recompute.json 2> $OUT/bench_recompute.err; echo "bench recompute rc=$?"
 timeout 300 python bench.py --workload c5 --steps 10 --warmup 3 > $OUT/bench_c5.json 2> $OUT/bench_c5.err; echo "bench c5 rc=$?"
 cat $OUT/bench_c5.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; echo "bench ref rc=$?"
-cat $OUT/bench_reference.json
+timeout 300 python tools/shape_bench.py 1 2 4 8 > $OUT/shape_bench.jsonl 2> $OUT/shape_bench.err
+cat $OUT/shape_bench.jsonl
 if [ "$3" != "skip-ncu" ]; then
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 160 --csv --log-file $OUT/launches.csv \
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 120 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/launches_bench.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'logits2?_kernel|dx2?_kernel|dw_kernel|normalize' -s 12 -c 6 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'logits2?_kernel|dx2?_kernel|dw_kernel|normalize_rows' -s 8 -c 7 \
     -o $OUT/prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/prof_bench.log 2>&1
   timeout 600 ncu --set full --clock-control none -k regex:'fedavg' -s 3 -c 1 \
     -o $OUT/prof_c5 python bench.py --workload c5 --steps 2 --warmup 3 --no-cpu-baseline > $OUT/prof_c5_bench.log 2>&1
