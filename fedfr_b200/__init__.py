@@ -1,8 +1,9 @@
 """fedfr_b200 -- B200-native (sm_100a) PartialFC CosFace head + FedAvg, drop-in for jackie840129/FedFR's
 ``partial_fc.PartialFC`` / ``losses.CosFace`` / ``server.FedPavg`` hot path.  See DESIGN.md."""
 from . import _native  # noqa: F401  (fails loudly when the CUDA extension has not been built)
+from .dense_head import MarginSoftmaxHead, margin_cross_entropy
 from .fedavg import FedAvg_on_FC, FedPavg, FedPavg_sharded
 from .losses import ArcFace, CosFace
 from .partial_fc import PartialFC
 
-__all__ = ["PartialFC", "CosFace", "ArcFace", "FedPavg", "FedAvg_on_FC", "FedPavg_sharded"]
+__all__ = ["PartialFC", "CosFace", "ArcFace", "FedPavg", "FedAvg_on_FC", "FedPavg_sharded", "margin_cross_entropy", "MarginSoftmaxHead"]
