@@ -171,8 +171,11 @@ class PartialFC(Module):
         """partial_fc.py:118-128: gather labels, sample, rewire the optimizer onto ``sub_weight`` and its
         momentum buffer, normalise the sub-shard.  Returns ``(total_label, norm_weight)``.
         (``forward_backward`` defers the normalisation: it is fused with the logits kernel.)"""
-        total_label = torch.zeros(size=[self.batch_size * self.world_size], device=self.device, dtype=torch.long)
-        self._all_gather(total_label, label.to(self.device))
+        if self.world_size == 1:        # nothing to gather: the copy the reference's sample() mutates in place
+            total_label = label.to(self.device, dtype=torch.long, copy=True)
+        else:
+            total_label = torch.zeros(size=[self.batch_size * self.world_size], device=self.device, dtype=torch.long)
+            self._all_gather(total_label, label.to(self.device))
         self.sample(total_label)
         optimizer.state.pop(optimizer.param_groups[-1]['params'][0], None)
         optimizer.param_groups[-1]['params'][0] = self.sub_weight
@@ -197,8 +200,11 @@ class PartialFC(Module):
             self._label_buf = torch.empty_like(total_label)
         self._label_buf.copy_(total_label)          # stable address for the replayed backward graph
         total_label = self._label_buf
-        total_features = torch.zeros(size=[B * W, E], device=self.device)
-        self._all_gather(total_features, features.data.to(torch.float32))
+        if W == 1:                      # nothing to gather (partial_fc.py:132-134 with one rank is a copy): read the features in place
+            total_features = features.data.to(device=self.device, dtype=torch.float32).contiguous()
+        else:
+            total_features = torch.zeros(size=[B * W, E], device=self.device)
+            self._all_gather(total_features, features.data.to(torch.float32))
         x_hat = ops.cast_features(total_features)
 
         # forward: per-shard (max, sum-exp, target logit), then one exchange instead of three all-reduces
