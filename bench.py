@@ -462,6 +462,27 @@ def run_ours(args):
     except Exception as e:           # noqa: BLE001  (extras never fail the bench line)
         extras["error"] = repr(e)
     head._prenorm = None
+    # context: the reference's formulation (client.py:69-74 + losses.py:23-29 + F.cross_entropy, autograd) in stock PyTorch
+    # eager fp32 on this same GPU, single rank only (it materialises the [B, C] logits: ~10 GB of temporaries at c3)
+    if world == 1 and sr >= 1 and not args.no_cpu_baseline:
+        try:
+            F = torch.nn.functional
+            w_ref = head.weight.detach().clone().requires_grad_(True)
+            x_ref = feats.clone().requires_grad_(True)
+
+            def torch_step():
+                w_ref.grad = None
+                x_ref.grad = None
+                cosine = F.linear(x_ref, F.normalize(w_ref))
+                onehot = torch.zeros_like(cosine).scatter_(1, label[:, None], M)
+                F.cross_entropy((cosine - onehot) * S, label).backward()
+
+            opt_time(torch_step, 2)
+            extras["torch_eager_fp32_same_gpu_ms"] = opt_time(torch_step, 3)
+            del w_ref, x_ref
+            torch.cuda.empty_cache()
+        except Exception as e:       # noqa: BLE001
+            extras["torch_eager_error"] = repr(e)
 
     # per-phase device times (events on the launch stream inside the library) for the roofline of the dominant kernel
     import ctypes as CT
