@@ -88,6 +88,7 @@ class PartialFC(Module):
         else:
             self.sub_weight = Parameter(torch.empty((0, 0), device=self.device))
         self._norm = None       # (w_hat, inv_norm) of the current step
+        self._range_checks = 0  # forward_backward calls since the last s * |x| range check (stored-probability path)
         self._prenorm = None    # (w_hat, inv_norm, weight ptr, weight version) left behind by step(prenormalize=True)
         self._label_buf = None
 
@@ -159,6 +160,31 @@ class PartialFC(Module):
         if pre is not None:
             self._prenorm = (pre[0], pre[1], self.weight.data_ptr(), self.weight._version)
 
+    # ------------------------------------------------------------------ range guard of the stored-probability path
+    _RANGE_LIMIT = 80.0         # nats: s * max|x_i| beyond this leaves the exponent window of include/fedfr_b200.h
+    _RANGE_PERIOD = 256         # calls between checks (callers either always or never normalise their embeddings)
+
+    def _check_logit_range(self, features):
+        """The stored-probability forward references every row to the bound s |x_i| (no row maximum is known before
+        the GEMM); with un-normalised embeddings of large norm that bound is hundreds of nats above the real logits and
+        they would underflow.  The first call, and every 256th after it, looks at max |x_i| (one small reduction and one
+        host read) and switches this head to the recomputing backward for good if the bound is out of range -- all
+        ranks together, so that the shards keep one reference point per row."""
+        ops = self._ops
+        if getattr(ops, "bwd_mode", None) != "prob":
+            return
+        self._range_checks += 1
+        if self._range_checks != 1 and self._range_checks % self._RANGE_PERIOD:
+            return
+        worst = features.detach().to(torch.float32).norm(dim=1).max() * self._s
+        if self.world_size > 1:
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        if not float(worst) <= self._RANGE_LIMIT:          # also catches NaN
+            logging.getLogger('FL_face.partial').warning(
+                "PartialFC: s * |x| = %.1f is outside the stored-probability range; using the recomputing backward "
+                "(normalise the embeddings, as partial_fc.py's callers do, to get the faster path)", float(worst))
+            ops.bwd_mode = "recompute"
+
     # ------------------------------------------------------------------ collectives
     def _all_gather(self, out, inp):
         if self.world_size == 1:
@@ -195,6 +221,7 @@ class PartialFC(Module):
                              "partial_fc.py:120-122,132-134)")
         ops = self._ops
         fused = hasattr(ops, "normalize_fwd_stats")
+        self._check_logit_range(features)
         total_label, w_hat = self.prepare(label, optimizer, _defer_normalize=fused)
         if self._label_buf is None or self._label_buf.shape != total_label.shape:
             self._label_buf = torch.empty_like(total_label)
