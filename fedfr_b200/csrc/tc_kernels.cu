@@ -1,13 +1,19 @@
 // Tensor-core path (sm_100a): TMA-fed tcgen05.mma kernels with TMEM accumulators.
 //
-//   logits_kernel<MODE_STATS>  z = s (x.w_hat - m[y]) tile by tile, CosFace margin + online max / sum-exp in the
-//                              epilogue; logits never leave the SM.          (partial_fc.py:137-147, losses.py:23-29)
-//   logits_kernel<MODE_GRAD>   recompute z, G = s (softmax - onehot) / Bt -> bf16 chunk scratch    (partial_fc.py:150-166)
-//   dx_kernel                  dx (+)= G . w_hat      (split over the class axis, fp32 partial slabs)  (autograd of :110)
-//   dw_kernel                  dw = normalize_bwd(G^T . x)                                            (autograd of :110,127)
+//   logits2_kernel<MODE_PROB>   P = exp2(s2 (x.w_hat) - bound) tile by tile -> bf16 scratch, row sums and the target
+//                               logit in the epilogue; optional normaliser warps produce w_hat of the next class chunk.
+//                               The [Bt, Cs] logits never exist.            (partial_fc.py:127,137-147, losses.py:23-45)
+//   logits2_kernel<MODE_STATS>  recompute flavour: online (max, sum-exp) only                    (same lines)
+//   logits2_kernel<MODE_GRAD>   recompute flavour: G = s (softmax - onehot) / Bt -> bf16 chunk scratch   (partial_fc.py:150-166)
+//   logits_kernel<...>          single-CTA variants of STATS / GRAD (tuning knob pfc_set_logits_pair(0))
+//   dx2_kernel / dx_kernel      dx (+)= G . w_hat  (split over the class axis, fp32 partial slabs)        (autograd of :110)
+//   dw_kernel                   dw = normalize_bwd(G^T . x), radial term from its own accumulator        (autograd of :110,127)
+//   prob_prep / row_bound / reduce_dx_scaled: the per-row glue of the stored-probability backward
 //
-// All kernels: 192 threads = 4 epilogue warps (TMEM lanes 0..127) + 1 TMA producer warp + 1 MMA issuer warp,
-// 128-byte-swizzled operand tiles, mbarrier pipelines (smem full/empty, TMEM full/empty).
+// Roles per CTA: epilogue warps (TMEM lane quadrants) + 1 TMA producer warp + 1 MMA issuer warp (+ normaliser warps);
+// 128-byte-swizzled operand tiles, mbarrier pipelines (smem full/empty, TMEM full/empty), CTA pairs (cta_group::2) for
+// the logits and dx kernels, an e-split CTA pair with a DSMEM exchange for dw.  Host side at the bottom: tensor maps,
+// launch plans, CUDA-graph cache (one replay per phase).
 #include "tc_common.cuh"
 #include "rows_device.cuh"
 #include <mutex>
@@ -63,7 +69,7 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 
 namespace tc {
 
-constexpr int kThreads = 192;          // dx / dw kernels: 4 epilogue warps + TMA warp + MMA warp
+constexpr int kThreads = 192;          // dx kernels: 4 epilogue warps + TMA warp + MMA warp
 constexpr int kLogitsEpiWarps = 8;     // logits kernels: two warps per TMEM lane quadrant, each takes half of the tile's columns
 constexpr int kLogitsThreads = (kLogitsEpiWarps + 2) * 32;
 constexpr int BM = 128;
