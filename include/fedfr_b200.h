@@ -116,7 +116,7 @@ int pfc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_
 
 /* prepare + forward in one call: norm_weight = normalize(sub_weight[index]) (partial_fc.py:105,127) fused with
  * pfc_fwd_stats (partial_fc.py:137-147).  The class axis is processed in chunks: the HBM-bound normalisation of
- * chunk k+1 runs on a side stream underneath the tensor-core logits kernel of chunk k (one replayed CUDA graph).
+ * chunk k+1 is done by extra warps INSIDE the tensor-core logits kernel of chunk k (one replayed CUDA graph).
  *   w      fp32 [*, emb] (sub_weight, or the whole shard when index != NULL), index int64 [n_classes] or NULL
  *   w_hat  out: bf16 (PFC_PATH_TENSOR) / fp32 (PFC_PATH_CHECK) [n_classes, emb];  inv_norm out: fp32 [n_classes]
  *   the remaining arguments are those of pfc_fwd_stats; target_logit / part_sum are zero-filled here. */
