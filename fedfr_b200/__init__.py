@@ -5,5 +5,6 @@ from .dense_head import MarginSoftmaxHead, margin_cross_entropy
 from .fedavg import FedAvg_on_FC, FedPavg, FedPavg_sharded
 from .losses import ArcFace, CosFace
 from .partial_fc import PartialFC
+from .spreadout import SpreadOut_Module
 
-__all__ = ["PartialFC", "CosFace", "ArcFace", "FedPavg", "FedAvg_on_FC", "FedPavg_sharded", "margin_cross_entropy", "MarginSoftmaxHead"]
+__all__ = ["PartialFC", "CosFace", "ArcFace", "FedPavg", "FedAvg_on_FC", "FedPavg_sharded", "margin_cross_entropy", "MarginSoftmaxHead", "SpreadOut_Module"]

@@ -21,6 +21,9 @@ int tc_bwd_prob(const void* x, const void* w_hat, const float* inv_norm, const i
                 int emb, float s, float m, int margin_kind, float inv_total_batch, float* dx, float* dw, int accumulate_dw, void* prob_ws,
                 size_t prob_ws_bytes, void* workspace, size_t workspace_bytes, cudaStream_t st);
 void tc_set_prob_split(int dx_sms, float dw_rate, int sweep_lead);
+size_t tc_spreadout_workspace_bytes(int64_t n, int emb);
+int tc_spreadout(const void* w_hat, int64_t n, int emb, float margin, float* part_max, float* part_sum, float* hw_out, void* workspace,
+                 size_t workspace_bytes, cudaStream_t st);
 void tc_set_fwd_overlap(int chunks, int norm_blocks_per_sm);
 int launch_normalize_rows(const float* w, const int64_t* index, int64_t n_rows, int emb, __nv_bfloat16* ob, float* of, float* inv_norm,
                           int blocks_per_sm, cudaStream_t st);
@@ -119,6 +122,20 @@ int pfc_bwd_prob(const void* x, const void* w_hat, const float* inv_norm, const 
 int pfc_set_prob_split(int dx_sms, float dw_rate, int sweep_lead) {
   tc_set_prob_split(dx_sms, dw_rate, sweep_lead);
   return 0;
+}
+
+/* ---- SpreadOut (server.py:48-63) -------------------------------------------------------------------------------- */
+size_t pfc_spreadout_workspace_bytes(int64_t n, int emb) {
+  if (n <= 0 || emb <= 0) return 0;
+  return tc_spreadout_workspace_bytes(n, emb);
+}
+
+int pfc_spreadout(const void* w_hat, int64_t n, int emb, float margin, float* part_max, float* part_sum, float* hw_out, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  PFC_REQUIRE(w_hat && part_max && part_sum && hw_out && workspace, PFC_E_ARG, "pfc_spreadout: null argument");
+  PFC_REQUIRE(n > 0 && emb > 0, PFC_E_ARG, "pfc_spreadout: empty shape");
+  return tc_spreadout(w_hat, n, emb, margin, part_max, part_sum, hw_out, workspace, workspace_bytes, as_stream(stream));
 }
 
 int pfc_set_fwd_overlap(int chunks, int norm_blocks_per_sm) {   /* class chunks of the fused forward, normalise blocks per SM */

@@ -77,7 +77,7 @@ constexpr int BK = 64;
 constexpr int kChunkBytes = BM * BK * 2;      // one [128 x 64] bf16 K-major tile = 16 KB
 constexpr int kBoxBytes = 64 * BK * 2;        // one [64 x 64] bf16 box = 8 KB
 
-enum { MODE_STATS = 0, MODE_GRAD = 1, MODE_PROB = 2 };
+enum { MODE_STATS = 0, MODE_GRAD = 1, MODE_PROB = 2, MODE_HINGE = 3 };
 
 struct LogitsParams {
   const int64_t* label;      // [n_rows] shard-local id or -1
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? norm_warps(MODE) * 32
       const int rp = (int)(t / p.n_ct), ct = (int)(t % p.n_ct);
       if (rp != cur_rp) {
         if (MODE != MODE_GRAD && cur_rp >= 0 && row_ok) {
-          p.part_max[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = (MODE == MODE_PROB ? M2 : run_m) * kLn2;
+          p.part_max[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = MODE == MODE_HINGE ? 0.f : (MODE == MODE_PROB ? M2 : run_m) * kLn2;
           p.part_sum[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = run_l;
         }
         cur_rp = rp;
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? norm_warps(MODE) * 32
         row = rb * BM + quad * 32 + lane;
         row_ok = row < p.n_rows;
         my_label = kNoLabel;
-        if (row_ok) {
+        if (row_ok && MODE != MODE_HINGE) {
           const int64_t y = p.label[row];
           if (y >= 0) my_label = (int)(y - p.class_base);
         }
@@ -587,6 +587,7 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? norm_warps(MODE) * 32
           M2 = row_ok ? p.row_bound[row] : INFINITY;
           if (p.accumulate_stats && row_ok) run_l = p.part_sum[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row];
         }
+        if (MODE == MODE_HINGE && p.accumulate_stats && row_ok) run_l = p.part_sum[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row];
       }
       const int acc = (int)(it & 1);
       mbar_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1));
@@ -609,7 +610,49 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? norm_warps(MODE) * 32
             if (MODE == MODE_PROB) p.target_cos[row] = c_hit;
           }
         }
-        if (MODE == MODE_PROB) {
+        if (MODE == MODE_HINGE) {
+          // SpreadOut (server.py:48-63): H = relu(cos - margin) off the diagonal (x_hat == w_hat: row i, column j are classes),
+          // sum of H^2 per row into this CTA's slot, H -> bf16 scratch for the gradient GEMM  dW_hat = 4 H . w_hat
+          const float2 mv = make_float2(-p.m, -p.m), zero2 = make_float2(0.f, 0.f);
+          float2 g[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float2 d = __fadd2_rn(make_float2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), mv);
+            g[q] = make_float2(fmaxf(d.x, zero2.x), fmaxf(d.y, zero2.y));
+          }
+          const int diag = row - (p.class_base + cb);                  // in [0, 32) iff this row's own column is in the group
+          if ((diag >= 0 && diag < 32) || tile_has_oob || !row_ok) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              if (2 * q == diag || cb + 2 * q >= p.n_classes || !row_ok) g[q].x = 0.f;
+              if (2 * q + 1 == diag || cb + 2 * q + 1 >= p.n_classes || !row_ok) g[q].y = 0.f;
+            }
+          }
+          float2 sum = __fmul2_rn(g[0], g[0]);
+#pragma unroll
+          for (int q = 1; q < 16; ++q) sum = __ffma2_rn(g[q], g[q], sum);
+          run_l += sum.x + sum.y;
+          uint32_t pk[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) pk[q] = pack_bf16x2(g[q].x, g[q].y);
+          const int half = (c >> 5) & 1;
+          if (half == 0) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(gbuf + sw128_off(lane, half * 4 + q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          if (half == 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            const int cbg = p.class_base + cb;
+            if (lane == 0 && cbg < p.ldg && rb < p.n_rb) {
+              tma_store_2d(&tmap_g, gbuf, 0, ((cbg >> 6) * p.n_rb + rb) * BM + quad * 32);
+              tma_store_commit();
+            }
+          }
+        } else if (MODE == MODE_PROB) {
           // P = exp2(s2 cos - bound): summed in fp32 (the softmax denominator, target included), stored as bf16 with the
           // target column zeroed -- the backward writes that one element from fp32 statistics (no p - 1 cancellation).
           const float2 s2v = make_float2(s2, s2), m2v = make_float2(-M2, -M2);
@@ -743,7 +786,7 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? norm_warps(MODE) * 32
       }
     }
     if (MODE != MODE_GRAD && cur_rp >= 0 && row_ok) {
-      p.part_max[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = (MODE == MODE_PROB ? M2 : run_m) * kLn2;
+      p.part_max[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = MODE == MODE_HINGE ? 0.f : (MODE == MODE_PROB ? M2 : run_m) * kLn2;
       p.part_sum[(int64_t)(blockIdx.x * 2 + chalf) * p.n_rows + row] = run_l;
     }
     if (MODE != MODE_STATS && lane == 0) tma_store_wait_all();
@@ -2236,6 +2279,85 @@ void tc_set_prob_split(int dx_sms, float dw_rate, int sweep_lead) {
   g_prob_dx_sms = dx_sms > 0 ? dx_sms : 0;
   if (dw_rate > 0.05f && dw_rate < 4.f) g_prob_dw_rate = dw_rate;
   if (sweep_lead >= 0) g_sweep_lead = sweep_lead;
+}
+
+// ---- SpreadOut (server.py:48-63) on the same kernel pair ---------------------------------------
+// similarity = w_hat . w_hat^T is a logits GEMM with x_hat := w_hat; its epilogue (MODE_HINGE) keeps H = relu(sim - margin)
+// off the diagonal as bf16 and sums H^2; the gradient w.r.t. the normalised rows is 4 H . w_hat (H is symmetric), which is
+// the dx GEMM on that scratch.  The row-wise normalize backward and the loss reduction are O(N E) glue on the host side.
+struct SpreadPlan {
+  int n_rb, dx_bn, n_eh, dcs, ksplit, dx_grid;
+  bool dx_pair;
+  int64_t c_pad;
+  size_t scratch_bytes, dxp_bytes;
+};
+static SpreadPlan make_spread_plan(int64_t n, int emb) {
+  SpreadPlan pl{};
+  pl.n_rb = (int)((n + BM - 1) / BM);
+  pl.c_pad = (n + 255) / 256 * 256;
+  pl.dx_bn = emb < 256 ? emb : 256;
+  pl.n_eh = emb / pl.dx_bn;
+  pl.dx_pair = g_dx_pair && emb >= 256 && pl.n_rb % 4 == 0;
+  pl.dcs = g_dx_cluster;
+  if (pl.dx_bn < 128) pl.dcs = 1;
+  if (pl.dx_bn == 128 && pl.dcs > 2) pl.dcs = 2;
+  const int64_t units = pl.dx_pair ? (int64_t)(pl.n_rb / 4) * pl.n_eh * 2 : (int64_t)((pl.n_rb + pl.dcs - 1) / pl.dcs) * pl.dcs * pl.n_eh;
+  int64_t ks = sm_count() / units;
+  const int64_t n_kb = (n + BK - 1) / BK;
+  if (ks > n_kb) ks = n_kb;
+  if (ks > 64) ks = 64;
+  if (ks < 1) ks = 1;
+  pl.ksplit = (int)ks;
+  pl.dx_grid = (int)(units * ks);
+  pl.scratch_bytes = ((size_t)pl.n_rb * BM * pl.c_pad * 2 + 1023) / 1024 * 1024;
+  pl.dxp_bytes = ((size_t)pl.ksplit * n * emb * 4 + 1023) / 1024 * 1024;
+  return pl;
+}
+size_t tc_spreadout_workspace_bytes(int64_t n, int emb) {
+  const SpreadPlan pl = make_spread_plan(n, emb);
+  return pl.scratch_bytes + pl.dxp_bytes;
+}
+
+int tc_spreadout(const void* w_hat, int64_t n, int emb, float margin, float* part_max, float* part_sum, float* hw_out, void* workspace,
+                 size_t workspace_bytes, cudaStream_t st) {
+  PFC_REQUIRE(tensor_emb_ok(emb), PFC_E_SHAPE, "tensor path supports emb in {64,128,256,512}, got %d", emb);
+  PFC_REQUIRE(n > 0 && n < (1ll << 24), PFC_E_SHAPE, "pfc_spreadout: row count out of range");
+  const SpreadPlan pl = make_spread_plan(n, emb);
+  PFC_REQUIRE(workspace_bytes >= pl.scratch_bytes + pl.dxp_bytes, PFC_E_WORKSPACE, "pfc_spreadout: workspace too small (%zu < %zu)", workspace_bytes,
+              pl.scratch_bytes + pl.dxp_bytes);
+  PFC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, PFC_E_ARG, "pfc_spreadout: workspace must be 1024-byte aligned");
+  char* scratch = reinterpret_cast<char*>(workspace);
+  float* dx_part = reinterpret_cast<float*>(scratch + pl.scratch_bytes);
+  const uint64_t g_rows = (uint64_t)(pl.c_pad / 64) * pl.n_rb * BM;
+  CUtensorMap tx, tw, tg_st, tg_k, tw_mn;
+  if (int rc = make_tmap_bf16_2d(&tx, w_hat, n, emb, emb, BM)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tw, w_hat, n, emb, emb, 128)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tg_st, scratch, g_rows, 64, 64, 32)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tg_k, scratch, g_rows, 64, 64, BM)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tw_mn, w_hat, n, emb, emb, 64)) return rc;
+  const int grid = pair_grid(n, n);
+  PFC_CUDA(cudaMemsetAsync(part_sum, 0, sizeof(float) * (size_t)grid * 2 * n, st));
+  LogitsParams p{};
+  p.n_rows = (int)n; p.n_classes = (int)n; p.class_base = 0; p.emb = emb;
+  p.n_rb = pl.n_rb; p.n_ct = (int)((n + 255) / 256); p.m = margin; p.part_max = part_max; p.part_sum = part_sum; p.ldg = pl.c_pad;
+  if (int rc = launch_logits2<4, MODE_HINGE>(tx, tw, tg_st, p, grid, st)) return rc;
+  DxParams dp{};
+  dp.n_rows = (int)n; dp.n_classes = (int)n; dp.emb = emb; dp.n_rb = pl.n_rb; dp.n_eh = pl.n_eh; dp.ksplit = pl.ksplit;
+  dp.dx_part = dx_part; dp.accumulate = 0; dp.prefetch = 0; dp.strided = 0;
+  int rc = 0;
+  if (pl.dx_pair) rc = launch_dx2(tg_k, tw_mn, dp, pl.dx_grid, st);
+  else switch (pl.dx_bn) {
+    case 256: rc = launch_dx<256>(tg_k, tw_mn, dp, pl.dx_grid, pl.dcs, st); break;
+    case 128: rc = launch_dx<128>(tg_k, tw_mn, dp, pl.dx_grid, pl.dcs, st); break;
+    default: rc = launch_dx<64>(tg_k, tw_mn, dp, pl.dx_grid, pl.dcs, st); break;
+  }
+  if (rc) return rc;
+  const int64_t n_vec = n * emb / 4;
+  int64_t blocks = (n_vec + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
+  reduce_dx_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(dx_part), pl.ksplit, n_vec, reinterpret_cast<float4*>(hw_out));
+  PFC_LAUNCH_CHECK();
+  return 0;
 }
 
 void tc_set_fwd_overlap(int chunks, int norm_blocks_per_sm) {

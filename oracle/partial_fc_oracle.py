@@ -268,3 +268,13 @@ def fedavg_on_fc(pretrain_fc: np.ndarray, models: Sequence[np.ndarray], weights:
         return acc
     return ((np.float32(1 - p) * np.asarray(pretrain_fc, dtype=np.float32)).astype(np.float32)
             + (np.float32(p) * acc).astype(np.float32)).astype(np.float32)
+
+
+def spreadout_loss(fc: torch.Tensor, margin: float, mode: str = "sum") -> torch.Tensor:
+    """server.py:55-62 (SpreadOut_Module.forward) as written, minus the ``.cuda()`` on the mask: normalise, full
+    similarity, off-diagonal entries, relu(sim - margin)^2, sum or mean.  Differentiable (use autograd for the gradient)."""
+    w = torch.nn.functional.normalize(fc)
+    similarity = torch.matmul(w, w.t())
+    off = similarity.masked_select(~torch.eye(len(w), dtype=torch.bool))
+    loss = torch.nn.functional.relu(off - margin) ** 2
+    return loss.sum() if mode == "sum" else loss.mean()

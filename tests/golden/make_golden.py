@@ -219,7 +219,46 @@ def fedavg_golden():
     print("fedavg.npz written")
 
 
+def spreadout_golden():
+    """server.SpreadOut_Module (server.py:48-63) on CPU: its forward puts the diagonal mask on the GPU with .cuda(); that
+    one call is patched to a no-op for this run, everything else is the unmodified reference + autograd."""
+    for name in ("easydict", "mxnet", "prettytable"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["easydict"].EasyDict = type("EasyDict", (dict,), {"__getattr__": dict.get, "__setattr__": dict.__setitem__})
+    for sub in ("ndarray", "recordio", "image"):
+        m = types.ModuleType("mxnet." + sub)
+        sys.modules["mxnet." + sub] = m
+        setattr(sys.modules["mxnet"], sub, m)
+    sys.modules["prettytable"].PrettyTable = object
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import server
+    g = torch.Generator().manual_seed(4242)
+    n, e = 200, 64
+    base = torch.randn(n // 16 + 1, e, generator=g)
+    fc = (base[torch.arange(n) % len(base)] + 0.35 * torch.randn(n, e, generator=g)) * 0.05
+    store = {"fc": fc.numpy()}
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for mode, margin in (("sum", 0.4), ("mean", 0.7)):
+            mod = server.SpreadOut_Module(fc.clone(), margin=margin, mode=mode)
+            loss = mod()
+            loss.backward()
+            store[f"loss_{mode}"] = loss.detach().numpy()
+            store[f"grad_{mode}"] = mod.FC.grad.numpy()
+            store[f"margin_{mode}"] = np.float32(margin)
+    finally:
+        torch.Tensor.cuda = orig
+    np.savez_compressed(os.path.join(OUT, "spreadout.npz"), **store)
+    print("spreadout.npz written", {k: float(store[k]) for k in store if k.startswith("loss")})
+
+
 def main():
+    if "spreadout" in sys.argv[1:]:
+        spreadout_golden()
+        return
     only = [a for a in sys.argv[1:] if not a.startswith("-")]       # optional: regenerate just these cases
     for name, cfg in CASES.items():
         if only and name not in only:
