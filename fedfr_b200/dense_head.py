@@ -47,17 +47,31 @@ class _MarginCrossEntropy(torch.autograd.Function):
             stats = ops.fwd_stats(x_hat, w_hat, label, s, m, kind)
         row_max, row_sum, loss = ops.finalize(stats.unsqueeze(0))
         ctx.ops, ctx.margin = ops, (s, m, kind)
-        # row_max / row_sum live in step scratch of `ops`: keep private copies for a backward that runs later
-        ctx.save_for_backward(x_unit, norm, x_hat, w_hat, inv_norm, label, row_max.clone(), row_sum.clone())
+        ctx.token = getattr(ops, "last_token", None)
+        # row_max / row_sum live in step scratch of `ops`: keep private copies for a backward that runs later.  x_hat, w_hat
+        # and inv_norm are step scratch too; backward() rebuilds them if another forward used `ops` in between.
+        ctx.save_for_backward(x_unit, norm, x_hat, w_hat, inv_norm, label, row_max.clone(), row_sum.clone(), w)
         ctx.w_shape, ctx.w_dtype, ctx.x_dtype = tuple(w.shape), weight.dtype, x.dtype
         return loss.clone()
 
     @staticmethod
     def backward(ctx, grad_out):
-        x_unit, norm, x_hat, w_hat, inv_norm, label, row_max, row_sum = ctx.saved_tensors
+        x_unit, norm, x_hat, w_hat, inv_norm, label, row_max, row_sum, w = ctx.saved_tensors
         s, m, kind = ctx.margin
+        ops = ctx.ops
         dw = torch.empty(ctx.w_shape, dtype=torch.float32, device=x_unit.device)
-        d_unit = ctx.ops.bwd(x_hat, w_hat, inv_norm, label, row_max, row_sum, s, m, 1.0 / x_unit.shape[0], dw, False, kind)
+        if ctx.token is not None and ops.last_token != ctx.token:
+            # another forward (a second head of the same shape, a PartialFC on this device) has reused the step buffers:
+            # rebuild this head's operands; the stored probabilities are gone, so the backward recomputes the logits
+            x_hat = ops.cast_features(x_unit.contiguous())
+            w_hat, inv_norm = ops.normalize(w)
+            ops.last_token += 1                              # ... which in turn invalidates whoever owned the buffers until now
+            d_unit = ops.bwd(x_hat, w_hat, inv_norm, label, row_max, row_sum, s, m, 1.0 / x_unit.shape[0], dw, False, kind, token=-1)
+        elif ctx.token is not None:
+            d_unit = ops.bwd(x_hat, w_hat, inv_norm, label, row_max, row_sum, s, m, 1.0 / x_unit.shape[0], dw, False, kind, token=ctx.token)
+        else:
+            d_unit = ops.bwd(x_hat, w_hat, inv_norm, label, row_max, row_sum, s, m, 1.0 / x_unit.shape[0], dw, False, kind)
+        d_unit = d_unit.clone()                              # dx is step scratch as well
         # backward of F.normalize(x):  dx = (d - x_unit (x_unit . d)) / |x|
         dx = (d_unit - x_unit * (x_unit * d_unit).sum(dim=1, keepdim=True)) / norm
         g = grad_out.to(torch.float32)

@@ -34,7 +34,8 @@ class CudaOps:
         self.bwd_mode = BWD_MODE if path == N.PATH_TENSOR else "recompute"
         if self.bwd_mode not in ("prob", "recompute"):
             raise ValueError("FEDFR_BWD_MODE must be 'prob' or 'recompute'")
-        self._prob = None       # (workspace, bt, cs, emb) of the last stored-probability forward
+        self._prob = None       # (workspace, offset, bytes, bt, cs, emb, token) of the last stored-probability forward
+        self.last_token = 0     # bumped by every forward: step buffers (x_hat, w_hat, inv_norm, P) belong to the newest one
 
     # ------------------------------------------------------------------ helpers
     def _persist(self, name, shape, dtype):
@@ -147,13 +148,14 @@ class CudaOps:
             N.check(N.lib.pfc_normalize_fwd_prob(N.ptr(sub_weight), None, N.ptr(x_hat), N.ptr(label), bt, n, emb, float(s), float(m), int(margin_kind),
                                                  N.ptr(w_hat), N.ptr(inv), N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), pws.data_ptr() + off, nbytes, st),
                     "pfc_normalize_fwd_prob")
-            self._prob = (pws, off, nbytes, bt, n, emb)
+            self._prob = (pws, off, nbytes, bt, n, emb, self.last_token + 1)
         else:
             N.check(N.lib.pfc_normalize_fwd_stats(N.ptr(sub_weight), None, N.ptr(x_hat), N.ptr(label), bt, n, emb, float(s), float(m), int(margin_kind),
                                                   N.ptr(w_hat), N.ptr(inv), N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), self.path, st),
                     "pfc_normalize_fwd_stats")
         stats = self._persist("stats", (bt, 3), torch.float32)
         N.check(N.lib.pfc_merge_stats(N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), n_part, bt, N.ptr(stats), st), "pfc_merge_stats")
+        self.last_token += 1
         return w_hat, inv, stats
 
     def _prob_ws(self, bt, cs, emb):
@@ -184,12 +186,13 @@ class CudaOps:
             N.check(N.lib.pfc_normalize_fwd_prob(None, None, N.ptr(x_hat), N.ptr(label), bt, cs, emb, float(s), float(m), int(margin_kind), N.ptr(w_hat),
                                                  N.ptr(inv), N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), pws.data_ptr() + off, nbytes, st),
                     "pfc_normalize_fwd_prob")
-            self._prob = (pws, off, nbytes, bt, cs, emb)
+            self._prob = (pws, off, nbytes, bt, cs, emb, self.last_token + 1)
         else:
             N.check(N.lib.pfc_fwd_stats(N.ptr(x_hat), N.ptr(w_hat), N.ptr(label), bt, cs, emb, float(s), float(m), int(margin_kind), N.ptr(part[0]),
                                         N.ptr(part[1]), N.ptr(tz), self.path, st), "pfc_fwd_stats")
         stats = torch.empty((bt, 3), dtype=torch.float32, device=self.device)
         N.check(N.lib.pfc_merge_stats(N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), n_part, bt, N.ptr(stats), st), "pfc_merge_stats")
+        self.last_token += 1
         return stats
 
     def finalize(self, gathered_stats):
@@ -202,13 +205,15 @@ class CudaOps:
                 "pfc_finalize_stats")
         return row_max, row_sum, loss
 
-    def bwd(self, x_hat, w_hat, inv_norm, label, row_max, row_sum, s, m, inv_total_batch, dw, accumulate, margin_kind=0):
+    def bwd(self, x_hat, w_hat, inv_norm, label, row_max, row_sum, s, m, inv_total_batch, dw, accumulate, margin_kind=0, token=None):
         """Writes/accumulates ``dw`` [Cs, E]; returns this shard's partial ``dx`` [Bt, E] (library-owned scratch,
-        overwritten by the next step: callers hand out a copy)."""
+        overwritten by the next step: callers hand out a copy).  ``token`` = ``last_token`` right after the forward this
+        backward belongs to (None: the newest forward); the stored probabilities are only used when they are that forward's,
+        otherwise the logits are recomputed from the operands passed in."""
         bt, emb = x_hat.shape
         cs = w_hat.shape[0]
         dx = self._persist("dx", (bt, emb), torch.float32)
-        if self._prob is not None and self._prob[3:] == (bt, cs, emb):      # the forward kept its probabilities
+        if self._prob is not None and self._prob[3:6] == (bt, cs, emb) and (token is None or token == self._prob[6]):   # its forward kept P
             pws, poff, pbytes = self._prob[:3]
             self._prob = None
             nbytes = N.lib.pfc_bwd_prob_workspace_bytes(bt, cs, emb)

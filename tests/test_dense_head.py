@@ -80,3 +80,31 @@ def test_dense_head_vs_torch_autograd(kind, s, m, check_mode, tol):
     # second forward/backward accumulates into .grad like any autograd op
     head(xa, y.to(dev)).backward()
     assert rel(head.fc.grad.cpu(), 2 * fr.grad) < tol
+
+
+@pytest.mark.gpu
+def test_two_heads_interleaved(kind="cosface", s=30.0, m=0.4):
+    """Two heads of the same shape on one device share the library's step buffers: forward A, forward B, then one
+    backward over both must still give each head its own gradients (A's backward rebuilds its operands)."""
+    import __graft_entry__ as g
+    g.build()
+    import fedfr_b200
+    dev = torch.device("cuda:0")
+    xa, fca, ya = _case(256, 6100, 512, 21)
+    xb, fcb, yb = _case(256, 6100, 512, 22)
+    refs = []
+    for x, fc, y in ((xa, fca, ya), (xb, fcb, yb)):
+        xr, fr = x.double().requires_grad_(True), fc.double().requires_grad_(True)
+        reference_loss(xr, fr, y, s, m, kind).backward()
+        refs.append((xr.grad, fr.grad))
+    heads, xs = [], []
+    for x, fc in ((xa, fca), (xb, fcb)):
+        h = fedfr_b200.MarginSoftmaxHead(6100, fedfr_b200.CosFace(s, m), 512).to(dev)
+        h.fc.data.copy_(fc.to(dev))
+        heads.append(h)
+        xs.append(x.to(dev).requires_grad_(True))
+    total = heads[0](xs[0], ya.to(dev)) + heads[1](xs[1], yb.to(dev))
+    total.backward()
+    for h, x, (gx, gw) in zip(heads, xs, refs):
+        assert rel(x.grad.cpu(), gx) < 1e-2
+        assert rel(h.fc.grad.cpu(), gw) < 1e-2
