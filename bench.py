@@ -23,9 +23,27 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION writes it to stdout) off it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# Rank 0 prints ONE JSON line on stdout.  NCCL writes its version banner to file descriptor 1 when a communicator is
+# created, so everything but that line is sent to stderr: fd 1 is pointed at fd 2 for the whole run and the JSON line is
+# written to the saved original stdout.
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 WORKLOADS = {
     # name: (batch per GPU, classes (global), emb, sample_rate)
@@ -142,7 +160,7 @@ def run_reference(args):
             "ms_per_step": ms_full, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: PartialFC CosFace fwd+bwd, B={B}/GPU, {C} classes, E={E}, sample_rate={sr}, s={S}, m={M}"},
             "cpu_baseline": cpu, "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def iresnet50_shapes():
@@ -289,7 +307,7 @@ def run_fedavg(args):
                          "ms_per_launch": kernel_ms, "peak_source": peaks["source"] + " copy bandwidth",
                          "note": "value is the whole FedPavg(state_dicts) call, bound by per-tensor Python work over K x 477 tensors"},
             "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -560,7 +578,7 @@ def run_ours(args):
                     "lagged_readback": {"value": Bt / (ms_e2e_lagged * 1e-3), "ms_per_step": ms_e2e_lagged,
                                         "note": "same copies; step n is read back while step n+1 is already enqueued"}},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extras": extras}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -586,6 +604,7 @@ def main():
     ap.add_argument("--prob-split", default="", help="stored-probability backward: 'dx_sms[,dw_rate[,sweep_lead]]' (SM budget of the dx kernel, dx/dw pacing)")
     ap.add_argument("--chunk-mb", type=int, default=0, help="bf16 G scratch per backward chunk in MiB (0 = library default)")
     args = ap.parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "c5":
