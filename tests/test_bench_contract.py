@@ -1,0 +1,31 @@
+"""bench.py contract pieces that run without a GPU: the reference arm prints exactly one JSON line on stdout (library
+chatter goes to stderr), with the keys the driver reads; ranks other than 0 stay silent."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(env_extra):
+    env = dict(os.environ, **env_extra)
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                          capture_output=True, text=True, env=env, timeout=600)
+
+
+def test_reference_arm_prints_one_json_line():
+    r = _run({"RANK": "0", "WORLD_SIZE": "2"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True and d["n_gpus"] == 2
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "c3" in d["config"]["workload"] and d["gpu_launches"] == 0
+
+
+def test_reference_arm_other_ranks_are_silent():
+    r = _run({"RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
