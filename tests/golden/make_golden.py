@@ -255,9 +255,56 @@ def spreadout_golden():
     print("spreadout.npz written", {k: float(store[k]) for k in store if k.startswith("loss")})
 
 
+def _stub_reference_imports():
+    for name in ("easydict", "mxnet", "prettytable"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["easydict"].EasyDict = type("EasyDict", (dict,), {"__getattr__": dict.get, "__setattr__": dict.__setitem__})
+    for sub in ("ndarray", "recordio", "image"):
+        m = types.ModuleType("mxnet." + sub)
+        sys.modules["mxnet." + sub] = m
+        setattr(sys.modules["mxnet"], sub, m)
+    sys.modules["prettytable"].PrettyTable = object
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+
+
+def dense_golden():
+    """The dense head FedFR's live client trains (client.py:63-74 FC_module, losses.py:17-29 CosFace(s=30, m=0.4) as built
+    at client.py:133, F.cross_entropy + loss.backward() as at client.py:430-435), run with the unmodified reference classes
+    on CPU."""
+    _stub_reference_imports()
+    import client
+    import losses
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(777)
+    B, C, E = 48, 211, 64
+    x = torch.randn(B, E, generator=g) * 3.0
+    fc = torch.randn(C, E, generator=g) * 0.01
+    y = torch.randint(0, C, (B,), generator=g)
+    x[::3] += 4.0 * fc[y[::3]] / fc[y[::3]].norm(dim=1, keepdim=True)
+    store = {"x": x.numpy(), "fc": fc.numpy(), "y": y.numpy()}
+    for name, margin in (("cosface", losses.CosFace(s=30, m=0.4)), ("arcface", losses.ArcFace(s=64.0, m=0.5))):
+        head = client.FC_module(E, C, "/tmp")
+        head.fc.data.copy_(fc)
+        xr = x.clone().requires_grad_(True)
+        logits = head(xr)
+        logits = margin(logits, y)
+        loss = F.cross_entropy(logits, y)
+        loss.backward()
+        store[f"loss_{name}"] = loss.detach().numpy()
+        store[f"dx_{name}"] = xr.grad.numpy()
+        store[f"dfc_{name}"] = head.fc.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "dense_head.npz"), **store)
+    print("dense_head.npz written", {k: float(store[k]) for k in store if k.startswith("loss")})
+
+
 def main():
     if "spreadout" in sys.argv[1:]:
         spreadout_golden()
+        return
+    if "dense" in sys.argv[1:]:
+        dense_golden()
         return
     only = [a for a in sys.argv[1:] if not a.startswith("-")]       # optional: regenerate just these cases
     for name, cfg in CASES.items():

@@ -55,6 +55,26 @@ def test_dense_head_host_logic_cpu(kind, s, m):
     assert rel(xa.grad, xr.grad) < 1e-4 and rel(fa.grad, fr.grad) < 1e-4
 
 
+@pytest.mark.parametrize("kind,s,m", [("cosface", 30.0, 0.4), ("arcface", 64.0, 0.5)])
+def test_dense_head_vs_reference_golden_cpu(kind, s, m):
+    """tests/golden/dense_head.npz: loss / x.grad / fc.grad of the UNMODIFIED reference classes (client.FC_module +
+    losses.CosFace / ArcFace + F.cross_entropy + backward, tests/golden/make_golden.py dense).  The adapter's host logic
+    (normalize forward / backward glue around the kernel provider) must reproduce them with the oracle-backed provider."""
+    import numpy as np
+    import fedfr_b200
+    from oracle_ops import OracleOps
+    gold = np.load(os.path.join(HERE, "golden", "dense_head.npz"))
+    x = torch.from_numpy(gold["x"]).clone().requires_grad_(True)
+    fc = torch.from_numpy(gold["fc"]).clone().requires_grad_(True)
+    y = torch.from_numpy(gold["y"])
+    margin = fedfr_b200.CosFace(s, m) if kind == "cosface" else fedfr_b200.ArcFace(s, m)
+    loss = fedfr_b200.margin_cross_entropy(x, fc, y, margin, _ops=OracleOps())
+    loss.backward()
+    assert abs(loss.item() - float(gold[f"loss_{kind}"])) <= 1e-4 * float(gold[f"loss_{kind}"])
+    assert rel(x.grad, torch.from_numpy(gold[f"dx_{kind}"])) < 1e-4
+    assert rel(fc.grad, torch.from_numpy(gold[f"dfc_{kind}"])) < 1e-4
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("check_mode,tol", [(True, 1e-4), (False, 1e-2)])
 @pytest.mark.parametrize("kind,s,m", [("cosface", 30.0, 0.4), ("arcface", 64.0, 0.5)])
