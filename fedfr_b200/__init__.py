@@ -5,6 +5,8 @@ from .dense_head import MarginSoftmaxHead, margin_cross_entropy
 from .fedavg import FedAvg_on_FC, FedPavg, FedPavg_sharded
 from .losses import ArcFace, CosFace
 from .partial_fc import PartialFC
+from .roc import calc_ROC, roc_histogram, tpr_at_fpr
 from .spreadout import SpreadOut_Module
 
-__all__ = ["PartialFC", "CosFace", "ArcFace", "FedPavg", "FedAvg_on_FC", "FedPavg_sharded", "margin_cross_entropy", "MarginSoftmaxHead", "SpreadOut_Module"]
+__all__ = ["PartialFC", "CosFace", "ArcFace", "FedPavg", "FedAvg_on_FC", "FedPavg_sharded", "margin_cross_entropy", "MarginSoftmaxHead", "SpreadOut_Module",
+           "calc_ROC", "roc_histogram", "tpr_at_fpr"]

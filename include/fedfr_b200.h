@@ -226,6 +226,22 @@ int fedavg_weighted_sum(const void* const* seg_src_host, void* const* seg_out_ho
 int fedavg_blend(const float* old_fc, const float* aggr, float one_minus_p, float p, int64_t n, float* out,
                  void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Pairwise-cosine ROC histogram                                 roc_cuda.py:14-28 (launch :40-51)
+ * ------------------------------------------------------------------------------------------------
+ * Replaces the numba kernel `calc_ROC(feature, label, subfeature, sublabel, out)`: for every pair (i, j) with
+ * i < n_sub, j < n and sub_offset + i < j,
+ *     tmp = sum_k fl32(subfeature[i,k] * feature[j,k])   (fp32 products, fp64 sum, k ascending -- the reference's arithmetic)
+ *     hist[2 * int((tmp + 1) * 1000) + (sublabel[i] != label[j])] += 1
+ * feature fp32 [n, emb], label int32 [n], subfeature fp32 [n_sub, emb], sublabel int32 [n_sub]; hist int64 [2001 * 2]
+ * is ADDED to (the reference's `out`, float64 there and cast to int64 by its caller, roc_cuda.py:52).  The reference
+ * always compares local indices (sub_offset = 0: roc_cuda.py:44-48 slices feature[start:] and its first rows); a
+ * non-zero sub_offset lets one call, or one rank, take rows [sub_offset, sub_offset + n_sub) of `feature` as the sub
+ * block, so the reference's whole batch loop (roc_cuda.py:30-53, :136-139) is ONE launch with n_sub = target_size.
+ * Bins are clamped to [0, 2000] (the reference would write out of bounds for |cosine| > 1 by more than rounding). */
+int pfc_roc_histogram(const float* feature, const int32_t* label, int64_t n, const float* subfeature,
+                      const int32_t* sublabel, int64_t n_sub, int64_t sub_offset, int emb, int64_t* hist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
