@@ -104,11 +104,13 @@ class PartialFC(Module):
         model_path = os.path.join(self.prefix, 'FC_rank_%d.pth' % (self.local_rank))
         self.weight.data = torch.load(model_path).to(self.device)
         self.sub_weight = Parameter(self.weight)
+        self._norm = self._prenorm = None       # normalised copies of the previous shard are stale
         print('Load weight from %s' % (model_path))
 
     def update_from_tensor(self, tensor):
         self.weight.data = tensor.to(self.device)
         self.sub_weight = Parameter(self.weight)
+        self._norm = self._prenorm = None
 
     # ------------------------------------------------------------------ sampling (partial_fc.py:89-106)
     @torch.no_grad()
