@@ -1,6 +1,7 @@
 """fedfr_b200 -- B200-native (sm_100a) PartialFC CosFace head + FedAvg, drop-in for jackie840129/FedFR's
 ``partial_fc.PartialFC`` / ``losses.CosFace`` / ``server.FedPavg`` hot path.  See DESIGN.md."""
 from . import _native  # noqa: F401  (fails loudly when the CUDA extension has not been built)
+from .bce_head import BCE_module
 from .dense_head import MarginSoftmaxHead, margin_cross_entropy
 from .fedavg import FedAvg_on_FC, FedPavg, FedPavg_sharded
 from .losses import ArcFace, CosFace
@@ -9,4 +10,4 @@ from .roc import calc_ROC, roc_histogram, tpr_at_fpr
 from .spreadout import SpreadOut_Module
 
 __all__ = ["PartialFC", "CosFace", "ArcFace", "FedPavg", "FedAvg_on_FC", "FedPavg_sharded", "margin_cross_entropy", "MarginSoftmaxHead", "SpreadOut_Module",
-           "calc_ROC", "roc_histogram", "tpr_at_fpr"]
+           "BCE_module", "calc_ROC", "roc_histogram", "tpr_at_fpr"]

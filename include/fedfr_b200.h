@@ -227,6 +227,25 @@ int fedavg_blend(const float* old_fc, const float* aggr, float one_minus_p, floa
                  void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Cosine head of the personalised branch                        client.py:25-60 (BCE_module.forward :45-58)
+ * ------------------------------------------------------------------------------------------------
+ * feat fp32 [n_rows, emb] (output of the module's converter, NOT normalised), weight fp32 [n_classes, emb], bias fp32
+ * [n_classes] or NULL, label int64 [n_rows] (labels >= n_classes and -1 have no positive column, client.py:49-52).
+ *   cosine = normalize(feat) . normalize(weight)^T                                  client.py:47
+ *   logits = r * (g(cosine) -/+ m) + bias,  g(x) = 2 ((x+1)/2)^t - 1,  "-" on gt     client.py:40,53-57
+ *   gt     uint8 [n_rows, n_classes]  (the bool matrix the module returns)           client.py:48-52
+ * cosine [n_rows, n_classes], inv_norm_feat [n_rows], inv_norm_w [n_classes] are kept for the backward.  One launch. */
+int pfc_bce_head_fwd(const float* feat, const float* weight, const float* bias, const int64_t* label, int64_t n_rows,
+                     int64_t n_classes, int emb, float m, float r, float t, float* logits, unsigned char* gt,
+                     float* cosine, float* inv_norm_feat, float* inv_norm_w, void* stream);
+/* autograd of the above from dlogits fp32 [n_rows, n_classes]: dfeat [n_rows, emb] (NULL = not needed),
+ * dweight [n_classes, emb], dbias [n_classes] (NULL when there is no bias).  Overwrites its outputs.  One launch;
+ * emb <= 1024. */
+int pfc_bce_head_bwd(const float* feat, const float* weight, const float* cosine, const float* inv_norm_feat,
+                     const float* inv_norm_w, const float* dlogits, int64_t n_rows, int64_t n_classes, int emb, float r,
+                     float t, float* dfeat, float* dweight, float* dbias, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Pairwise-cosine ROC histogram                                 roc_cuda.py:14-28 (launch :40-51)
  * ------------------------------------------------------------------------------------------------
  * Replaces the numba kernel `calc_ROC(feature, label, subfeature, sublabel, out)`: for every pair (i, j) with

@@ -299,7 +299,43 @@ def dense_golden():
     print("dense_head.npz written", {k: float(store[k]) for k in store if k.startswith("loss")})
 
 
+def bce_golden():
+    """The cosine head of the personalised branch as FedFR's client builds and trains it (client.py:135-136: BCE_module(512,
+    n_class, converter_layer) with m=0.4, r=30, t=3 and losses.BCE_loss(); client.py:386-394: loss = ... + 10 * bce_loss),
+    run with the unmodified reference classes on CPU.  Labels include public-data ids >= n_class (client.py:49-50)."""
+    _stub_reference_imports()
+    import client
+    import losses
+    g = torch.Generator().manual_seed(4242)
+    B, C, E = 40, 37, 64
+    x = torch.randn(B, E, generator=g) * 2.0
+    y = torch.randint(0, C + 12, (B,), generator=g)                 # ~1/4 of the rows carry a public id (no positive column)
+    store = {"x": x.numpy(), "y": y.numpy()}
+    torch.manual_seed(11)
+    mod = client.BCE_module(E, C, 1)
+    with torch.no_grad():                                           # move off the identity / zero initialisation
+        mod.converter[0].weight.add_(0.05 * torch.randn(E, E, generator=g))
+        mod.converter[0].bias.add_(0.1 * torch.randn(E, generator=g))
+        mod.bias.add_(0.2 * torch.randn(C, generator=g))
+        own = y < C
+        mod.weight[y[own]] += 0.02 * x[own]                         # some rows agree with their class
+    store.update({"sd/" + k: v.detach().numpy().copy() for k, v in mod.state_dict().items()})
+    xr = x.clone().requires_grad_(True)
+    logits, gts = mod(xr, y)
+    store["logits"], store["gt"] = logits.detach().numpy().copy(), gts.numpy().copy()
+    loss = 10 * losses.BCE_loss()(logits, gts)                      # edits `logits` in place (losses.py:10-11)
+    loss.backward()
+    store["loss"] = loss.detach().numpy()
+    store["dx"] = xr.grad.numpy()
+    store.update({"grad/" + k: p.grad.numpy() for k, p in mod.named_parameters()})
+    np.savez_compressed(os.path.join(OUT, "bce_head.npz"), **store)
+    print("bce_head.npz written: loss", float(loss), "positives", int(gts.sum()), "of", B)
+
+
 def main():
+    if "bce" in sys.argv[1:]:
+        bce_golden()
+        return
     if "spreadout" in sys.argv[1:]:
         spreadout_golden()
         return
