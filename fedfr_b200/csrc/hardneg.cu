@@ -1,0 +1,103 @@
+// Hard-negative mining by similarity threshold (client.py:208-215 feature-based, client.py:232-235 FC-based):
+//     similarity = A . B^T ;  unique(torch.where(similarity > threshold)[1])        A [n_a, emb], B [n_b, emb], fp32
+// i.e. the set of columns j for which SOME row i has <a_i, b_j> > threshold.  The reference materialises the
+// [n_a, n_b] matrix on the CPU (n_b = 420 k public images) and scans it in 100 slices to bound RAM; here the matrix
+// never exists: a CTA computes a 64 x 64 tile of dot products from 32-wide k slices staged in shared memory, reduces
+// "any row above threshold" per column in the epilogue and sets hit[j].  Row tiles vary fastest across the persistent
+// CTAs, so the column tile of B (the big operand) is read from HBM once and shared through L2.
+// Arithmetic: fp32 FMA chains in k order -- the comparison is a hard threshold on a cosine, which a bf16 tensor-core
+// product (error ~4e-3) would move for every pair inside that band; the fp32 result differs from a BLAS sgemm's only by
+// summation order (|delta| ~ 1e-7).  A tensor-core filter with an fp32 recheck of the band is the next step.
+#include "common.cuh"
+
+namespace pfc {
+
+constexpr int kHnTile = 64;
+constexpr int kHnK = 32;
+constexpr int kHnThreads = 256;
+
+__global__ void __launch_bounds__(kHnThreads, 2)
+similar_columns_kernel(const float* __restrict__ a, int64_t n_a, const float* __restrict__ b, int64_t n_b, int emb,
+                       float threshold, unsigned char* __restrict__ hit) {
+  __shared__ float As[kHnTile][kHnK + 1];
+  __shared__ float Bs[kHnTile][kHnK + 1];
+  __shared__ int col_hit[kHnTile];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t n_ti = (n_a + kHnTile - 1) / kHnTile;
+  const int64_t n_tj = (n_b + kHnTile - 1) / kHnTile;
+  const int64_t total = n_ti * n_tj;
+  for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const int64_t i0 = (t % n_ti) * kHnTile;
+    const int64_t j0 = (t / n_ti) * kHnTile;
+    __syncthreads();                                   // the previous tile's col_hit has been read
+    if (tid < kHnTile) col_hit[tid] = 0;
+    float acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+    for (int k0 = 0; k0 < emb; k0 += kHnK) {
+      __syncthreads();                                 // the previous slice has been consumed
+      {
+        const int kk = tid & 31;
+        const bool k_ok = (k0 + kk) < emb;
+#pragma unroll
+        for (int r = 0; r < kHnTile / 8; ++r) {
+          const int row = (tid >> 5) + 8 * r;
+          const int64_t gi = i0 + row, gj = j0 + row;
+          As[row][kk] = (k_ok && gi < n_a) ? a[gi * emb + k0 + kk] : 0.f;
+          Bs[row][kk] = (k_ok && gj < n_b) ? b[gj * emb + k0 + kk] : 0.f;
+        }
+      }
+      __syncthreads();
+      const int kc = (emb - k0 < kHnK) ? emb - k0 : kHnK;
+#pragma unroll 4
+      for (int kk = 0; kk < kc; ++kk) {
+        float av[4], bv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) av[u] = As[ty + 16 * u][kk];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) bv[v] = Bs[tx + 16 * v][kk];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      bool any = false;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) any = any || ((i0 + ty + 16 * u) < n_a && acc[u][v] > threshold);
+      if (any) col_hit[tx + 16 * v] = 1;               // benign race: every writer stores 1
+    }
+    __syncthreads();
+    if (tid < kHnTile && col_hit[tid] && j0 + tid < n_b) hit[j0 + tid] = 1;
+  }
+}
+
+}  // namespace pfc
+
+using namespace pfc;
+
+extern "C" {
+
+int pfc_similar_columns(const float* a, int64_t n_a, const float* b, int64_t n_b, int emb, float threshold,
+                        unsigned char* hit, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  PFC_REQUIRE(n_a >= 0 && n_b >= 0 && emb >= 1, PFC_E_ARG, "pfc_similar_columns: bad size");
+  if (n_b == 0) return 0;
+  PFC_REQUIRE(hit, PFC_E_ARG, "pfc_similar_columns: null pointer");
+  PFC_CUDA(cudaMemsetAsync(hit, 0, (size_t)n_b, as_stream(stream)));
+  if (n_a == 0) return 0;
+  PFC_REQUIRE(a && b, PFC_E_ARG, "pfc_similar_columns: null pointer");
+  const int64_t total = ((n_a + kHnTile - 1) / kHnTile) * ((n_b + kHnTile - 1) / kHnTile);
+  int64_t grid = (int64_t)sm_count() * 2;
+  if (grid > total) grid = total;
+  similar_columns_kernel<<<(int)grid, kHnThreads, 0, as_stream(stream)>>>(a, n_a, b, n_b, emb, threshold, hit);
+  PFC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -246,6 +246,15 @@ int pfc_bce_head_bwd(const float* feat, const float* weight, const float* cosine
                      float t, float* dfeat, float* dweight, float* dbias, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Hard-negative mining by similarity threshold              client.py:208-215 and client.py:232-235
+ * ------------------------------------------------------------------------------------------------
+ * hit[j] = 1 when some row i has <a_i, b_j> > threshold, else 0  (a fp32 [n_a, emb], b fp32 [n_b, emb], hit uint8 [n_b],
+ * fully overwritten).  nonzero(hit) is the reference's `unique(torch.where(a @ b.T > threshold)[1])`; the [n_a, n_b]
+ * similarity matrix is never materialised.  fp32 FMA chains in k order (see csrc/hardneg.cu for why not bf16). */
+int pfc_similar_columns(const float* a, int64_t n_a, const float* b, int64_t n_b, int emb, float threshold,
+                        unsigned char* hit, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Pairwise-cosine ROC histogram                                 roc_cuda.py:14-28 (launch :40-51)
  * ------------------------------------------------------------------------------------------------
  * Replaces the numba kernel `calc_ROC(feature, label, subfeature, sublabel, out)`: for every pair (i, j) with

@@ -332,7 +332,44 @@ def bce_golden():
     print("bce_head.npz written: loss", float(loss), "positives", int(gts.sum()), "of", B)
 
 
+def hardneg_golden():
+    """FC-based hard-negative mining: the unmodified ``Client.choose_hard_negative`` (client.py:227-266) called on CPU with
+    stub loader / logger objects (it only reads ``dataset.imgidx`` of a deep copy and logs).  ``HN_ID`` is what it selects;
+    ``imgidx`` the 1-based image list it derives (client.py:249-255).  The feature-based variant
+    (``choose_hard_negative_2``, client.py:191-224) needs a CUDA backbone; its array part (client.py:208-215) is evaluated
+    here by the same torch expressions on synthetic features."""
+    _stub_reference_imports()
+    import client
+    from functools import reduce
+    g = torch.Generator().manual_seed(9090)
+    E, n_self, n_pub = 64, 23, 500
+    pretrain_fc = torch.randn(n_pub, E, generator=g)
+    self_fc = torch.randn(n_self, E, generator=g)
+    self_fc[:9] = pretrain_fc[torch.randint(0, n_pub, (9,), generator=g)] + 0.9 * torch.randn(9, E, generator=g)   # some close pairs
+    pretrain_label = torch.randint(0, n_pub, (3000,), generator=g)
+    loader = types.SimpleNamespace(dataset=types.SimpleNamespace(imgidx=None))
+    me = types.SimpleNamespace(logger=types.SimpleNamespace(info=lambda *a, **k: None))
+    _, subset = client.Client.choose_hard_negative(me, pretrain_fc, loader, pretrain_label, self_fc, threshold=0.2)
+    store = {"self_fc": self_fc.numpy(), "pretrain_fc": pretrain_fc.numpy(), "pretrain_label": pretrain_label.numpy(),
+             "threshold": np.float64(0.2), "HN_ID": np.asarray(me.HN_ID, dtype=np.int64), "imgidx": np.asarray(subset.dataset.imgidx)}
+    # feature-based array part, client.py:208-215
+    local_feats = torch.nn.functional.normalize(torch.randn(130, E, generator=g))
+    pretrained_feats = torch.nn.functional.normalize(torch.randn(900, E, generator=g) + 0.5 * local_feats[torch.randint(0, 130, (900,), generator=g)])
+    similarity = torch.matmul(local_feats, pretrained_feats.t())
+    times = 100
+    batch = len(similarity) // times + 1
+    unique_idx = [torch.where(similarity[i * batch:(i + 1) * batch] > 0.35)[1].numpy() for i in range(times)]
+    unique_idx = sorted(reduce(np.union1d, unique_idx))
+    store.update({"local_feats": local_feats.numpy(), "pretrained_feats": pretrained_feats.numpy(), "threshold2": np.float64(0.35),
+                  "unique_idx": np.asarray(unique_idx, dtype=np.int64)})
+    np.savez_compressed(os.path.join(OUT, "hardneg.npz"), **store)
+    print("hardneg.npz written:", len(me.HN_ID), "of", n_pub, "ids;", len(unique_idx), "of 900 images")
+
+
 def main():
+    if "hardneg" in sys.argv[1:]:
+        hardneg_golden()
+        return
     if "bce" in sys.argv[1:]:
         bce_golden()
         return

@@ -26,6 +26,11 @@ extern "C" void emu_roc(const float* feature, const int32_t* label, int64_t n, c
   });
 }
 ''',
+    "hardneg": r'''
+extern "C" void emu_similar(const float* a, int64_t n_a, const float* b, int64_t n_b, int emb, float thr, unsigned char* hit, int grid) {
+  emu_launch((unsigned)grid, pfc::kHnThreads, [=]() { pfc::similar_columns_kernel(a, n_a, b, n_b, emb, thr, hit); });
+}
+''',
     "bce_head": r'''
 extern "C" void emu_bce_fwd(const float* feat, const float* weight, const float* bias, const int64_t* label, int64_t n_rows,
                             int64_t n_classes, int emb, float m, float r, float t, float* logits, unsigned char* gt,
@@ -122,3 +127,19 @@ def test_bce_head_kernels_under_emulation(libs, B, Cn, E, t, grid):
     libs["bce_head"].emu_bce_bwd(_p(feat), _p(weight), _p(cosine), _p(inv_nf), _p(inv_nw), _p(dlogits), C.c_int64(B),
                                  C.c_int64(Cn), E, C.c_float(30.0), C.c_float(t), None, _p(dweight2), None)
     assert np.array_equal(dweight2, dweight)
+
+
+@pytest.mark.parametrize("na,nb,emb,thr,grid", [(70, 130, 40, 0.1, 3), (5, 64, 33, 0.0, 1), (130, 65, 7, 0.3, 4), (64, 64, 64, -2.0, 2)])
+def test_similar_columns_kernel_under_emulation(libs, na, nb, emb, thr, grid):
+    from oracle import hardneg_oracle as O
+    rng = np.random.default_rng(na * 7 + nb)
+    a = rng.standard_normal((na, emb)).astype(np.float32)
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b = (rng.standard_normal((nb, emb)) + 0.8 * a[rng.integers(0, na, nb)]).astype(np.float32)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    hit = np.zeros(nb, dtype=np.uint8)
+    libs["hardneg"].emu_similar(_p(a), C.c_int64(na), _p(b), C.c_int64(nb), emb, C.c_float(thr), _p(hit), grid)
+    certain, amb = O.similar_columns(a, b, thr)
+    got = set(np.nonzero(hit)[0].tolist())
+    assert set(certain.tolist()) <= got <= set(certain.tolist()) | set(amb.tolist())
+    assert 0 < len(got) <= nb
