@@ -58,6 +58,37 @@ static inline float __shfl_xor_sync(unsigned, float v, int o) {
   return r;
 }
 
+template <class T> static inline T emu_shfl_exchange(T v, int src_lane_xor, int src_lane_abs) {
+  static_assert(sizeof(T) <= 8, "shuffle of <= 64-bit values");
+  static unsigned long long slots[64][32];
+  const int t = (int)g_fibers[g_cur].tid.x, w = t / 32, l = t % 32;
+  const int lanes = ((w + 1) * 32 <= (int)g_blockDim.x) ? 32 : (int)g_blockDim.x - w * 32;
+  unsigned long long raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  slots[w][l] = raw;
+  emu_warp_barrier(w, lanes);
+  const int src = src_lane_abs >= 0 ? src_lane_abs : (l ^ src_lane_xor);
+  raw = slots[w][src < lanes ? src : l];
+  emu_warp_barrier(w, lanes);
+  T r;
+  memcpy(&r, &raw, sizeof(T));
+  return r;
+}
+static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int o) { return emu_shfl_exchange(v, o, -1); }
+static inline int __shfl_xor_sync(unsigned, int v, int o) { return emu_shfl_exchange(v, o, -1); }
+static inline double __shfl_xor_sync(unsigned, double v, int o) { return emu_shfl_exchange(v, o, -1); }
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl_exchange(v, 0, src); }
+static inline unsigned __ballot_sync(unsigned, bool pred) {
+  unsigned m = 0;
+  for (int b = 0; b < 32; ++b) m |= (emu_shfl_exchange<unsigned>(pred ? 1u : 0u, 0, b) & 1u) << b;   // lanes beyond the block read themselves
+  const int t = (int)g_fibers[g_cur].tid.x, w = t / 32;
+  const int lanes = ((w + 1) * 32 <= (int)g_blockDim.x) ? 32 : (int)g_blockDim.x - w * 32;
+  return lanes == 32 ? m : (m & ((1u << lanes) - 1u));
+}
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline void __threadfence() {}
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+
 static void emu_trampoline() { g_body(); g_fibers[g_cur].done = true; }
 
 template <class F> static void emu_launch(unsigned grid, unsigned block, F body) {
@@ -100,7 +131,43 @@ static inline double __dmul_rn(double a, double b) { volatile double r = a * b; 
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p += v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 
+static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
+static inline float atomicAdd(float* p, float v) { float o = *p; *p += v; return o; }
+
+static inline int64_t min(int64_t a, int64_t b) { return a < b ? a : b; }
+static inline int64_t max(int64_t a, int64_t b) { return a > b ? a : b; }
+
+// vector types and streaming accessors
+struct float4 { float x, y, z, w; };
+struct uint2 { unsigned x, y; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+
+// host runtime: "device" memory is host memory, streams are ignored
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return 0; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
+template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = (T*)malloc(n); return *p ? 0 : 2; }
+static inline cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+
+#include "../../include/fedfr_b200.h"
+
 namespace pfc {
+static char g_emu_err[512];
+static inline void set_error(const char* fmt, ...) { (void)fmt; snprintf(g_emu_err, sizeof(g_emu_err), "%s", fmt); }
+static long long g_launch_count = 0;
+static inline int require_sm100() { return 0; }
+static inline cudaStream_t as_stream(void* s) { return s; }
+static inline float4 ld_stream_f4(const float4* p) { return *p; }
+static inline void st_stream_f4(float4* p, const float4& v) { *p = v; }
+#define PFC_REQUIRE(cond, code, ...) do { if (!(cond)) { ::pfc::set_error(__VA_ARGS__); return (code); } } while (0)
+#define PFC_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return (int)e__; } while (0)
+#define PFC_LAUNCH_CHECK() do { ::pfc::g_launch_count++; } while (0)
 static inline int sm_count() { return 2; }
 static inline float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

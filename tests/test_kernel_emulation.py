@@ -50,6 +50,75 @@ extern "C" void emu_bce_bwd(const float* feat, const float* weight, const float*
 }
 
 
+def _match_close(src, i, open_ch, close_ch):
+    depth = 0
+    for j in range(i, len(src)):
+        if src[j] == open_ch:
+            depth += 1
+        elif src[j] == close_ch:
+            depth -= 1
+            if depth == 0:
+                return j
+    raise ValueError("unbalanced")
+
+
+def _split_top(text):
+    parts, depth, cur = [], 0, ""
+    for ch in text:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    return parts + [cur]
+
+
+def _transform_launches(src):
+    """``kernel<T><<<grid, block, smem, stream>>>(args);`` -> ``emu_launch(grid, block, [=]() { kernel<T>(args); });``"""
+    import re
+    out, pos = "", 0
+    while True:
+        i = src.find("<<<", pos)
+        if i < 0:
+            return out + src[pos:]
+        j = i                                           # walk back over the kernel name (+ template arguments)
+        if src[j - 1] == ">":
+            depth = 0
+            while True:
+                j -= 1
+                depth += (src[j] == ">") - (src[j] == "<")
+                if depth == 0:
+                    break
+        m = re.search(r"[\w:]+$", src[:j])
+        name = src[m.start():i]
+        k = src.index(">>>", i)
+        cfg = _split_top(src[i + 3:k])
+        a0 = src.index("(", k)
+        a1 = _match_close(src, a0, "(", ")")
+        out += src[pos:m.start()] + "emu_launch((unsigned)(%s), (unsigned)(%s), [=]() { %s%s; })" % (
+            cfg[0].strip(), cfg[1].strip(), name, src[a0:a1 + 1])
+        pos = a1 + 1
+
+
+def _build_abi(name, tmp):
+    """Whole translation unit (kernels AND the extern "C" entry points) on the emulator: launches become emu_launch,
+    the CUDA runtime calls act on host memory."""
+    src = open(os.path.join(ROOT, "fedfr_b200", "csrc", name + ".cu")).read()
+    body = _transform_launches(src.replace('#include "common.cuh"', '#include "cuda_emu.h"'))
+    assert "<<<" not in body and "cuda_emu.h" in body
+    cpp = os.path.join(tmp, name + "_abi_emu.cpp")
+    with open(cpp, "w") as f:
+        f.write(body)
+    so = os.path.join(tmp, name + "_abi_emu.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                           "-I", os.path.join(HERE, "emu"), cpp, "-o", so])
+    return C.CDLL(so)
+
+
 def _build(name, tmp):
     src = open(os.path.join(ROOT, "fedfr_b200", "csrc", name + ".cu")).read()
     end = src.index("}  // namespace pfc") + len("}  // namespace pfc")
@@ -73,7 +142,9 @@ def libs(tmp_path_factory):
     import __graft_entry__ as g
     g.build()                                          # the C oracle
     tmp = str(tmp_path_factory.mktemp("emu"))
-    return {n: _build(n, tmp) for n in HARNESS}
+    out = {n: _build(n, tmp) for n in HARNESS}
+    out.update({n + "_abi": _build_abi(n, tmp) for n in ("sample", "fedavg")})
+    return out
 
 
 @pytest.mark.parametrize("n,emb,t,off,grid", [(150, 40, 100, 0, 3), (131, 33, 131, 0, 2), (70, 7, 20, 35, 1), (64, 32, 64, 0, 5)])
@@ -143,3 +214,102 @@ def test_similar_columns_kernel_under_emulation(libs, na, nb, emb, thr, grid):
     got = set(np.nonzero(hit)[0].tolist())
     assert set(certain.tolist()) <= got <= set(certain.tolist()) | set(amb.tolist())
     assert 0 < len(got) <= nb
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Whole C-ABI entry points under emulation (kernels + their host orchestration), against the REFERENCE goldens
+
+def _sample_abi(lib, labels_global, perm, class_start, num_local, num_sample):
+    """pfc_remap_labels + pfc_sample_index exactly as fedfr_b200.ops_cuda calls them; returns (index, remapped labels)."""
+    lib.pfc_sample_workspace_bytes.restype = C.c_size_t
+    n = labels_global.shape[0]
+    local = np.empty(n, dtype=np.int64)
+    assert lib.pfc_remap_labels(_p(labels_global), C.c_int64(n), C.c_int64(class_start), C.c_int64(num_local), _p(local), None) == 0
+    perm = perm.astype(np.float32).copy()
+    index = np.full(num_local, -7, dtype=np.int64)
+    n_index = np.zeros(1, dtype=np.int64)
+    ws_bytes = lib.pfc_sample_workspace_bytes(C.c_int64(num_local))
+    ws = np.zeros(ws_bytes + 256, dtype=np.uint8)
+    ws_ptr = (ws.ctypes.data + 255) // 256 * 256
+    rc = lib.pfc_sample_index(_p(local), C.c_int64(n), _p(perm), C.c_int64(num_local), C.c_int64(num_sample), _p(index),
+                              _p(n_index), C.c_void_p(ws_ptr), C.c_size_t(ws_bytes), None)
+    assert rc == 0
+    return index[:int(n_index[0])], local
+
+
+@pytest.mark.parametrize("name", ["w1_sr01", "w1_sr_pos_overflow", "w2_sr03", "w2_arc_sr03"])
+def test_sampling_abi_under_emulation_matches_reference(libs, name):
+    """The sampled index the unmodified reference produced (partial_fc.py:89-106) must come out of the index kernel chain
+    bit for bit, given the reference's own torch.rand draw."""
+    sys.path.insert(0, HERE)
+    from golden_util import Case
+    from oracle import partial_fc_oracle as O
+    case = Case(name)
+    cfg = case.cfg
+    W, C_all = cfg["world_size"], cfg["num_classes"]
+    total = torch.cat(case.labels).numpy().astype(np.int64)
+    for r in range(W):
+        num_local = C_all // W + int(r < C_all % W)
+        class_start = C_all // W * r + min(r, C_all % W)
+        num_sample = int(cfg["sample_rate"] * num_local)
+        for step in range(cfg["steps"]):
+            if not case.has(r, step, "perm"):
+                continue
+            index, local = _sample_abi(libs["sample_abi"], total, case.get(r, step, "perm"), class_start, num_local, num_sample)
+            assert np.array_equal(index, case.get(r, step, "index")), (name, r, step)
+            want_local = O.relabel_to_sample(O.remap_labels(total, class_start, num_local), case.get(r, step, "index"))
+            assert np.array_equal(local, want_local)
+
+
+@pytest.mark.parametrize("num_local,n_label,num_sample,seed", [(5000, 64, 500, 0), (2049, 300, 100, 1), (300, 10, 0, 2), (257, 4, 257, 3)])
+def test_sampling_abi_under_emulation_matches_oracle(libs, num_local, n_label, num_sample, seed):
+    from oracle import partial_fc_oracle as O
+    rng = np.random.default_rng(seed)
+    perm = rng.random(num_local, dtype=np.float32)
+    perm[rng.integers(0, num_local, 6)] = perm[0]                       # ties, also at the threshold for some k
+    labels = rng.integers(-50, num_local + 50, n_label).astype(np.int64)
+    index, local = _sample_abi(libs["sample_abi"], labels, perm, 0, num_local, num_sample)
+    local0 = O.remap_labels(labels, 0, num_local)
+    want = O.sample_index(local0, perm, num_sample)
+    assert np.array_equal(index, want)
+    assert np.array_equal(local, O.relabel_to_sample(local0, want))
+
+
+def test_fedavg_abi_under_emulation_matches_reference(libs):
+    """fedavg_weighted_sum (pointer table, fp32 + int64 segments, ragged tails) and fedavg_blend against the outputs of the
+    unmodified server.FedPavg / FedAvg_on_FC (tests/golden/fedavg.npz) -- bit for bit."""
+    from oracle import partial_fc_oracle as O
+    lib = libs["fedavg_abi"]
+    lib.fedavg_table_bytes.restype = C.c_size_t
+    z = np.load(os.path.join(HERE, "golden", "fedavg.npz"))
+    K = int(z["K"])
+    keys = [k[4:] for k in z.files if k.startswith("in0/")]
+    wn = np.array([np.float32(w) for w in O.fedavg_weights([float(w) for w in z["weights"]])], dtype=np.float32)
+    srcs = [[np.ascontiguousarray(z[f"in{i}/{k}"]) for i in range(K)] for k in keys]
+    outs = [np.full(max(g[0].size, 1), np.nan, dtype=np.float32) for g in srcs]
+    n_seg = len(keys)
+    seg_src = np.array([a.ctypes.data for g in srcs for a in g], dtype=np.uint64)
+    seg_out = np.array([o.ctypes.data for o in outs], dtype=np.uint64)
+    seg_len = np.array([g[0].size for g in srcs], dtype=np.int64)
+    seg_dtype = np.array([1 if g[0].dtype == np.int64 else 0 for g in srcs], dtype=np.int32)
+    assert all(g[0].dtype in (np.float32, np.int64) for g in srcs) and seg_dtype.sum() >= 1
+    tb = lib.fedavg_table_bytes(n_seg, K)
+    table = np.zeros(tb + 256, dtype=np.uint8)
+    rc = lib.fedavg_weighted_sum(_p(seg_src), _p(seg_out), _p(seg_len), _p(seg_dtype), n_seg, _p(wn), K,
+                                 C.c_void_p((table.ctypes.data + 255) // 256 * 256), C.c_size_t(tb), None)
+    assert rc == 0
+    for k, o, g in zip(keys, outs, srcs):
+        want = np.asarray(z["out/" + k], dtype=np.float32).reshape(-1)
+        assert np.array_equal(o[:want.size], want), k
+
+    fcs = [np.ascontiguousarray(z[f"fc_in{i}"]) for i in range(K)]
+    aggr = np.empty_like(fcs[0])
+    seg_src = np.array([a.ctypes.data for a in fcs], dtype=np.uint64)
+    seg_out = np.array([aggr.ctypes.data], dtype=np.uint64)
+    rc = lib.fedavg_weighted_sum(_p(seg_src), _p(seg_out), _p(np.array([aggr.size], dtype=np.int64)), _p(np.zeros(1, np.int32)), 1,
+                                 _p(wn), K, C.c_void_p((table.ctypes.data + 255) // 256 * 256), C.c_size_t(tb), None)
+    assert rc == 0 and np.array_equal(aggr, z["fc_out_p1"])
+    out = np.empty_like(aggr)
+    old = np.ascontiguousarray(z["fc_old"])
+    assert lib.fedavg_blend(_p(old), _p(aggr), C.c_float(np.float32(1 - 0.7)), C.c_float(np.float32(0.7)), C.c_int64(aggr.size), _p(out), None) == 0
+    assert np.array_equal(out, z["fc_out_p07"])
