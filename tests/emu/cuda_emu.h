@@ -126,6 +126,7 @@ template <class F> static void emu_launch(unsigned grid, unsigned block, F body)
 // arithmetic with CUDA's names (compile with -ffp-contract=off so * and + stay separate roundings)
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p += v; return o; }
@@ -136,6 +137,9 @@ static inline float atomicAdd(float* p, float v) { float o = *p; *p += v; return
 
 static inline int64_t min(int64_t a, int64_t b) { return a < b ? a : b; }
 static inline int64_t max(int64_t a, int64_t b) { return a > b ? a : b; }
+
+struct __nv_bfloat16 { uint16_t bits; };
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 
 // vector types and streaming accessors
 struct float4 { float x, y, z, w; };
@@ -162,6 +166,10 @@ static char g_emu_err[512];
 static inline void set_error(const char* fmt, ...) { (void)fmt; snprintf(g_emu_err, sizeof(g_emu_err), "%s", fmt); }
 static long long g_launch_count = 0;
 static inline int require_sm100() { return 0; }
+enum { PH_NORMALIZE = 0, PH_FWD = 1, PH_GRAD = 2, PH_DX = 3, PH_DW = 4, PH_COUNT = 5 };
+static inline void prof_begin(int, cudaStream_t) {}
+static inline void prof_end(int, cudaStream_t) {}
+static inline bool prof_enabled() { return false; }
 static inline cudaStream_t as_stream(void* s) { return s; }
 static inline float4 ld_stream_f4(const float4* p) { return *p; }
 static inline void st_stream_f4(float4* p, const float4& v) { *p = v; }
@@ -169,6 +177,19 @@ static inline void st_stream_f4(float4* p, const float4& v) { *p = v; }
 #define PFC_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return (int)e__; } while (0)
 #define PFC_LAUNCH_CHECK() do { ::pfc::g_launch_count++; } while (0)
 static inline int sm_count() { return 2; }
+static inline float warp_max(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+static inline unsigned emu_bf16_rn(float f) {            // round to nearest even, like __floats2bfloat162_rn
+  unsigned u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fffu;
+  return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+}
+static inline uint32_t pack_bf16x2(float lo, float hi) { return emu_bf16_rn(lo) | (emu_bf16_rn(hi) << 16); }
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
 static inline float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;

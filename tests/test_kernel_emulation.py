@@ -108,14 +108,19 @@ def _build_abi(name, tmp):
     """Whole translation unit (kernels AND the extern "C" entry points) on the emulator: launches become emu_launch,
     the CUDA runtime calls act on host memory."""
     src = open(os.path.join(ROOT, "fedfr_b200", "csrc", name + ".cu")).read()
-    body = _transform_launches(src.replace('#include "common.cuh"', '#include "cuda_emu.h"'))
+    for inc in ("rows_device.cuh",):                                  # in-tree device headers are inlined
+        if '#include "%s"' % inc in src:
+            src = src.replace('#include "%s"' % inc, open(os.path.join(ROOT, "fedfr_b200", "csrc", inc)).read())
+    src = src.replace("#pragma once", "")
+    body = _transform_launches(src.replace('#include "common.cuh"', '#include "cuda_emu.h"', 1).replace('#include "common.cuh"', ""))
     assert "<<<" not in body and "cuda_emu.h" in body
     cpp = os.path.join(tmp, name + "_abi_emu.cpp")
     with open(cpp, "w") as f:
         f.write(body)
     so = os.path.join(tmp, name + "_abi_emu.so")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
-                           "-I", os.path.join(HERE, "emu"), cpp, "-o", so])
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                        "-I", os.path.join(HERE, "emu"), cpp, "-o", so], capture_output=True, text=True)
+    assert r.returncode == 0, "\n".join(l for l in r.stderr.splitlines() if "error" in l)[:1500]
     return C.CDLL(so)
 
 
@@ -143,7 +148,7 @@ def libs(tmp_path_factory):
     g.build()                                          # the C oracle
     tmp = str(tmp_path_factory.mktemp("emu"))
     out = {n: _build(n, tmp) for n in HARNESS}
-    out.update({n + "_abi": _build_abi(n, tmp) for n in ("sample", "fedavg")})
+    out.update({n + "_abi": _build_abi(n, tmp) for n in ("sample", "fedavg", "rows", "stats")})
     return out
 
 
@@ -313,3 +318,133 @@ def test_fedavg_abi_under_emulation_matches_reference(libs):
     old = np.ascontiguousarray(z["fc_old"])
     assert lib.fedavg_blend(_p(old), _p(aggr), C.c_float(np.float32(1 - 0.7)), C.c_float(np.float32(0.7)), C.c_int64(aggr.size), _p(out), None) == 0
     assert np.array_equal(out, z["fc_out_p07"])
+
+
+def _bf16_bits(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).view(torch.int16).numpy()
+
+
+@pytest.mark.parametrize("n_src,emb,gather", [(37, 512, False), (50, 128, True), (9, 64, True), (5, 1024, False)])
+def test_row_kernels_abi_under_emulation(libs, n_src, emb, gather):
+    """normalize (+gather) / cast / gather / scatter (partial_fc.py:105-106,113-116,127) through their C-ABI entries."""
+    import torch.nn.functional as F
+    lib = libs["rows_abi"]
+    rng = np.random.default_rng(n_src + emb)
+    w = (rng.standard_normal((n_src, emb)) * 0.01).astype(np.float32)
+    w[1] = 0.0                                                            # the eps clamp of F.normalize
+    mom = (rng.standard_normal((n_src, emb)) * 0.001).astype(np.float32)
+    index = np.sort(rng.choice(n_src, size=n_src // 2, replace=False)).astype(np.int64) if gather else None
+    rows = w[index] if gather else w
+    n = rows.shape[0]
+    w_bf16 = np.zeros((n, emb), dtype=np.int16)
+    w_f32 = np.zeros((n, emb), dtype=np.float32)
+    inv = np.zeros(n, dtype=np.float32)
+    assert lib.pfc_normalize_rows(_p(w), _p(index), C.c_int64(n), emb, _p(w_bf16), _p(w_f32), _p(inv), None) == 0
+    want = F.normalize(torch.from_numpy(rows)).numpy()
+    np.testing.assert_allclose(w_f32, want, rtol=4e-7, atol=0)           # a division by the norm; the norm's summation
+                                                                         # order differs from CPU torch's by <= 1 ulp
+    np.testing.assert_allclose(inv, 1.0 / np.maximum(np.linalg.norm(rows.astype(np.float64), axis=1), 1e-12), rtol=2e-6)
+    assert np.array_equal(w_bf16, _bf16_bits(w_f32))                     # the bf16 copy is the rounding of the fp32 one
+    bf_only = np.zeros((n, emb), dtype=np.int16)                          # product mode: bf16 only (reciprocal multiply)
+    assert lib.pfc_normalize_rows(_p(w), _p(index), C.c_int64(n), emb, _p(bf_only), None, _p(inv), None) == 0
+    assert np.abs(bf_only.astype(np.int32) - _bf16_bits(want).astype(np.int32)).max() <= 1
+
+    cast = np.zeros((n_src, emb), dtype=np.int16)
+    assert lib.pfc_cast_rows_bf16(_p(w), C.c_int64(n_src), emb, _p(cast), None) == 0
+    assert np.array_equal(cast, _bf16_bits(w))
+
+    if gather:
+        sub_w, sub_m = np.zeros((n, emb), np.float32), np.zeros((n, emb), np.float32)
+        assert lib.pfc_gather_rows2(_p(w), _p(mom), _p(index), C.c_int64(n), emb, _p(sub_w), _p(sub_m), None) == 0
+        assert np.array_equal(sub_w, w[index]) and np.array_equal(sub_m, mom[index])
+        w2, m2 = w.copy(), mom.copy()
+        new_w, new_m = sub_w + 1.0, sub_m - 1.0
+        assert lib.pfc_scatter_rows2(_p(w2), _p(m2), _p(index), C.c_int64(n), emb, _p(new_w), _p(new_m), None) == 0
+        ew, em = w.copy(), mom.copy()
+        ew[index], em[index] = new_w, new_m
+        assert np.array_equal(w2, ew) and np.array_equal(m2, em)
+
+
+@pytest.mark.parametrize("sampled,nesterov,dampening,wd", [(False, 0, 0.0, 5e-4), (True, 0, 0.0, 5e-4), (False, 1, 0.0, 0.0), (True, 0, 0.1, 1e-3)])
+def test_sgd_step_abi_under_emulation_matches_torch(libs, sampled, nesterov, dampening, wd):
+    """pfc_sgd_step == torch.optim.SGD.step() (+ update() when sampled) on the same numbers, two consecutive steps."""
+    lib = libs["rows_abi"]
+    g = torch.Generator().manual_seed(11 + nesterov)
+    n_all, emb = 40, 128
+    weight = torch.randn(n_all, emb, generator=g) * 0.01
+    mom = torch.randn(n_all, emb, generator=g) * 0.001
+    index = torch.sort(torch.randperm(n_all, generator=g)[:17])[0] if sampled else None
+    w_np, m_np = weight.numpy().copy(), mom.numpy().copy()
+    for step in range(2):
+        n = 17 if sampled else n_all
+        grad = torch.randn(n, emb, generator=g) * 0.1
+        sub = torch.nn.Parameter((weight[index] if sampled else weight).clone())
+        sub.grad = grad.clone()
+        opt = torch.optim.SGD([sub], lr=0.1, momentum=0.9, dampening=dampening, weight_decay=wd, nesterov=bool(nesterov))
+        opt.state[sub]["momentum_buffer"] = (mom[index] if sampled else mom).clone()      # partial_fc.py:126
+        opt.step()
+        if sampled:                                                                        # partial_fc.py:113-116
+            mom[index] = opt.state[sub]["momentum_buffer"]
+            weight[index] = sub.data
+        else:
+            weight, mom = sub.data.clone(), opt.state[sub]["momentum_buffer"].clone()
+        w_hat = np.zeros((n_all, emb), np.int16)
+        inv = np.zeros(n_all, np.float32)
+        rc = lib.pfc_sgd_step(_p(w_np), _p(m_np), _p(grad.numpy()), _p(index.numpy()) if sampled else None, C.c_int64(n), emb,
+                              C.c_float(0.1), C.c_float(0.9), C.c_float(dampening), C.c_float(wd), nesterov,
+                              None if sampled else _p(w_hat), None if sampled else _p(inv), None)
+        assert rc == 0
+        np.testing.assert_allclose(w_np, weight.numpy(), rtol=0, atol=2e-9)
+        np.testing.assert_allclose(m_np, mom.numpy(), rtol=0, atol=2e-8)
+        if not sampled:                                                   # the operands of the next forward
+            want = torch.nn.functional.normalize(torch.from_numpy(w_np)).numpy()
+            assert np.abs(w_hat.astype(np.int32) - _bf16_bits(want).astype(np.int32)).max() <= 1
+            np.testing.assert_allclose(inv, 1.0 / np.linalg.norm(w_np.astype(np.float64), axis=1), rtol=2e-6)
+
+
+def test_cosface_dense_abi_under_emulation(libs):
+    """losses.CosFace.forward on materialised logits (losses.py:23-29): in-place margin, then a scaled copy."""
+    lib = libs["rows_abi"]
+    g = torch.Generator().manual_seed(3)
+    cosine = torch.rand(19, 41, generator=g) * 2 - 1
+    label = torch.randint(0, 41, (19,), generator=g)
+    label[::4] = -1
+    want_c = cosine.clone()
+    rows = torch.where(label != -1)[0]
+    want_c[rows, label[rows]] -= 0.4
+    c_np, out = cosine.numpy().copy(), np.zeros((19, 41), np.float32)
+    assert lib.pfc_cosface_dense(_p(c_np), _p(label.numpy()), C.c_int64(19), C.c_int64(41), C.c_float(64.0), C.c_float(0.4), _p(out), None) == 0
+    assert np.array_equal(c_np, want_c.numpy()) and np.array_equal(out, (want_c * 64.0).numpy())
+
+
+@pytest.mark.parametrize("world,n_rows,n_part", [(1, 33, 5), (3, 70, 2), (2, 1100, 1)])
+def test_stats_abi_under_emulation(libs, world, n_rows, n_part):
+    """pfc_merge_stats + pfc_finalize_stats == the reference's max / sum-exp / target all-reduces and loss
+    (partial_fc.py:140-162), from per-tile partials."""
+    lib = libs["stats_abi"]
+    rng = np.random.default_rng(world * 100 + n_rows)
+    C_per = 24
+    z = (rng.standard_normal((world, n_part, n_rows, C_per)) * 20).astype(np.float32)      # logits per rank / partial slot
+    owner = rng.integers(0, world, n_rows)
+    tcol = rng.integers(0, n_part * C_per, n_rows)
+    gathered = np.zeros((world, n_rows, 3), np.float32)
+    for r in range(world):
+        pm = z[r].max(axis=2)                                                               # [n_part, n_rows]
+        ps = np.exp(z[r] - pm[:, :, None]).sum(axis=2).astype(np.float32)
+        tl = np.zeros(n_rows, np.float32)
+        mine = owner == r
+        flat = z[r].transpose(1, 0, 2).reshape(n_rows, -1)
+        tl[mine] = flat[mine, tcol[mine]]
+        stats = np.zeros((n_rows, 3), np.float32)
+        assert lib.pfc_merge_stats(_p(np.ascontiguousarray(pm)), _p(np.ascontiguousarray(ps)), _p(tl), n_part, C.c_int64(n_rows), _p(stats), None) == 0
+        gathered[r] = stats
+    row_max, row_sum, loss = np.zeros(n_rows, np.float32), np.zeros(n_rows, np.float32), np.zeros(1, np.float32)
+    assert lib.pfc_finalize_stats(_p(gathered), world, C.c_int64(n_rows), _p(row_max), _p(row_sum), _p(loss), None) == 0
+    full = z.transpose(2, 0, 1, 3).reshape(n_rows, -1).astype(np.float64)
+    M = full.max(axis=1)
+    S = np.exp(full - M[:, None]).sum(axis=1)
+    tz = np.array([z[owner[i]].transpose(1, 0, 2).reshape(n_rows, -1)[i, tcol[i]] for i in range(n_rows)], dtype=np.float64)
+    want_loss = -np.mean(np.log(np.maximum(np.exp(tz - M) / S, 1e-30)))
+    np.testing.assert_allclose(row_max, M, rtol=1e-6)
+    np.testing.assert_allclose(row_sum, S, rtol=1e-5)
+    assert abs(float(loss[0]) - want_loss) < 1e-5 * abs(want_loss)
