@@ -12,7 +12,12 @@
 #include <functional>
 #include <vector>
 
-struct EmuDim3 { unsigned x = 1, y = 1, z = 1; };
+struct EmuDim3 {
+  unsigned x = 1, y = 1, z = 1;
+  EmuDim3() {}
+  EmuDim3(unsigned x_, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+typedef EmuDim3 dim3;
 struct EmuFiber { ucontext_t ctx; std::vector<char> stack; bool done = false; EmuDim3 tid; };
 
 static EmuDim3 g_blockIdx, g_blockDim, g_gridDim;
@@ -91,11 +96,12 @@ static inline void __syncwarp(unsigned = 0xffffffffu) {}
 
 static void emu_trampoline() { g_body(); g_fibers[g_cur].done = true; }
 
-template <class F> static void emu_launch(unsigned grid, unsigned block, F body) {
-  g_gridDim.x = grid; g_blockDim.x = block;
+template <class F> static void emu_launch(EmuDim3 grid, unsigned block, F body) {
+  g_gridDim = grid; g_blockDim.x = block;
   g_body = body;
-  for (unsigned b = 0; b < grid; ++b) {
-    g_blockIdx.x = b;
+  for (unsigned b = 0; b < grid.x * grid.y; ++b) {
+    g_blockIdx.x = b % grid.x;
+    g_blockIdx.y = b / grid.x;
     g_bar_count = 0;
     memset(g_w_count, 0, sizeof(g_w_count));
     g_fibers.assign(block, EmuFiber());
@@ -188,6 +194,16 @@ static inline unsigned emu_bf16_rn(float f) {            // round to nearest eve
   return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
 }
 static inline uint32_t pack_bf16x2(float lo, float hi) { return emu_bf16_rn(lo) | (emu_bf16_rn(hi) << 16); }
+static inline float margin_cos(float c, float m, int kind) {          // same definitions as csrc/common.cuh
+  if (kind == PFC_MARGIN_COSFACE) return c - m;
+  c = fminf(fmaxf(c, -1.f), 1.f);
+  return cosf(acosf(c) + m);
+}
+static inline float margin_slope(float c, float m, int kind) {
+  if (kind == PFC_MARGIN_COSFACE) return 1.f;
+  c = fminf(fmaxf(c, -1.f), 1.f);
+  return sinf(acosf(c) + m) * rsqrtf(fmaxf(1.f - c * c, 1e-12f));
+}
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 static inline float warp_sum(float v) {

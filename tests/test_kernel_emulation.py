@@ -50,6 +50,22 @@ extern "C" void emu_bce_bwd(const float* feat, const float* weight, const float*
 }
 
 
+# simt_check.cu's host functions are C++ (api.cu dispatches to them): export them for ctypes
+CHECK_EXPORTS = r'''
+extern "C" int emu_check_num_partials(int64_t n_rows, int64_t n_classes) { return pfc::simt_fwd_num_partials(n_rows, n_classes); }
+extern "C" int emu_check_fwd_stats(const float* x, const float* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb,
+                                   float s, float m, int kind, float* part_max, float* part_sum, float* target_logit) {
+  return pfc::simt_fwd_stats(x, w_hat, label, n_rows, n_classes, emb, s, m, kind, part_max, part_sum, target_logit, nullptr);
+}
+extern "C" size_t emu_check_bwd_ws(int64_t n_rows, int64_t n_classes, int emb) { return pfc::simt_bwd_workspace_bytes(n_rows, n_classes, emb); }
+extern "C" int emu_check_bwd(const float* x, const float* w_hat, const float* inv_norm, const int64_t* label, const float* row_max,
+                             const float* row_sum, int64_t n_rows, int64_t n_classes, int emb, float s, float m, int kind, float inv_b,
+                             float* dx, float* dw, int accumulate, void* ws, size_t ws_bytes) {
+  return pfc::simt_bwd(x, w_hat, inv_norm, label, row_max, row_sum, n_rows, n_classes, emb, s, m, kind, inv_b, dx, dw, accumulate, ws, ws_bytes, nullptr);
+}
+'''
+
+
 def _match_close(src, i, open_ch, close_ch):
     depth = 0
     for j in range(i, len(src)):
@@ -99,15 +115,15 @@ def _transform_launches(src):
         cfg = _split_top(src[i + 3:k])
         a0 = src.index("(", k)
         a1 = _match_close(src, a0, "(", ")")
-        out += src[pos:m.start()] + "emu_launch((unsigned)(%s), (unsigned)(%s), [=]() { %s%s; })" % (
+        out += src[pos:m.start()] + "emu_launch(EmuDim3(%s), (unsigned)(%s), [=]() { %s%s; })" % (
             cfg[0].strip(), cfg[1].strip(), name, src[a0:a1 + 1])
         pos = a1 + 1
 
 
-def _build_abi(name, tmp):
+def _build_abi(name, tmp, extra=""):
     """Whole translation unit (kernels AND the extern "C" entry points) on the emulator: launches become emu_launch,
     the CUDA runtime calls act on host memory."""
-    src = open(os.path.join(ROOT, "fedfr_b200", "csrc", name + ".cu")).read()
+    src = open(os.path.join(ROOT, "fedfr_b200", "csrc", name + ".cu")).read() + extra
     for inc in ("rows_device.cuh",):                                  # in-tree device headers are inlined
         if '#include "%s"' % inc in src:
             src = src.replace('#include "%s"' % inc, open(os.path.join(ROOT, "fedfr_b200", "csrc", inc)).read())
@@ -149,6 +165,7 @@ def libs(tmp_path_factory):
     tmp = str(tmp_path_factory.mktemp("emu"))
     out = {n: _build(n, tmp) for n in HARNESS}
     out.update({n + "_abi": _build_abi(n, tmp) for n in ("sample", "fedavg", "rows", "stats")})
+    out["check_abi"] = _build_abi("simt_check", tmp, CHECK_EXPORTS)
     return out
 
 
@@ -448,3 +465,56 @@ def test_stats_abi_under_emulation(libs, world, n_rows, n_part):
     np.testing.assert_allclose(row_max, M, rtol=1e-6)
     np.testing.assert_allclose(row_sum, S, rtol=1e-5)
     assert abs(float(loss[0]) - want_loss) < 1e-5 * abs(want_loss)
+
+
+@pytest.mark.parametrize("name", ["w1_sr1_small", "w1_sr1_s30", "w1_arc_small", "w2_sr1_ragged"])
+def test_check_mode_path_under_emulation_matches_reference(libs, name):
+    """The fp32 check-mode kernels (PFC_PATH_CHECK: simt_check.cu + rows.cu + stats.cu), chained exactly as
+    fedfr_b200.PartialFC.forward_backward chains them, against loss / x_grad / dw of the unmodified reference
+    (partial_fc.py:130-176) -- tolerance 1e-4 relative, the north-star check-mode bar."""
+    sys.path.insert(0, HERE)
+    from golden_util import Case
+    case = Case(name)
+    cfg = case.cfg
+    W, B, E = cfg["world_size"], cfg["batch"], cfg["emb"]
+    kind = 1 if cfg.get("loss", "cosface") == "arcface" else 0
+    s_, m_ = float(cfg["s"]), float(cfg["m"])
+    rows_lib, stats_lib, chk, smp = libs["rows_abi"], libs["stats_abi"], libs["check_abi"], libs["sample_abi"]
+    chk.emu_check_bwd_ws.restype = C.c_size_t
+    x = np.ascontiguousarray(torch.cat(case.features).numpy())                       # the all-gathered batch
+    total_label = torch.cat(case.labels).numpy().astype(np.int64)
+    Bt = B * W
+    per_rank, gathered = [], np.zeros((W, Bt, 3), np.float32)
+    for r in range(W):
+        w = np.ascontiguousarray(case.weights[r].numpy())
+        Cl = w.shape[0]
+        class_start = cfg["num_classes"] // W * r + min(r, cfg["num_classes"] % W)
+        local = np.empty(Bt, np.int64)
+        assert smp.pfc_remap_labels(_p(total_label), C.c_int64(Bt), C.c_int64(class_start), C.c_int64(Cl), _p(local), None) == 0
+        w_hat, inv = np.zeros((Cl, E), np.float32), np.zeros(Cl, np.float32)
+        assert rows_lib.pfc_normalize_rows(_p(w), None, C.c_int64(Cl), E, None, _p(w_hat), _p(inv), None) == 0
+        n_part = chk.emu_check_num_partials(C.c_int64(Bt), C.c_int64(Cl))
+        pm, ps, tl = np.zeros((n_part, Bt), np.float32), np.zeros((n_part, Bt), np.float32), np.zeros(Bt, np.float32)
+        assert chk.emu_check_fwd_stats(_p(x), _p(w_hat), _p(local), C.c_int64(Bt), C.c_int64(Cl), E, C.c_float(s_), C.c_float(m_), kind,
+                                       _p(pm), _p(ps), _p(tl)) == 0
+        stats = np.zeros((Bt, 3), np.float32)
+        assert stats_lib.pfc_merge_stats(_p(pm), _p(ps), _p(tl), n_part, C.c_int64(Bt), _p(stats), None) == 0
+        gathered[r] = stats                                                          # the one all-gather of the W > 1 path
+        per_rank.append((w_hat, inv, local, Cl))
+    row_max, row_sum, loss = np.zeros(Bt, np.float32), np.zeros(Bt, np.float32), np.zeros(1, np.float32)
+    assert stats_lib.pfc_finalize_stats(_p(gathered), W, C.c_int64(Bt), _p(row_max), _p(row_sum), _p(loss), None) == 0
+    dx_sum = np.zeros((Bt, E), np.float64)
+    for r, (w_hat, inv, local, Cl) in enumerate(per_rank):
+        ws_bytes = chk.emu_check_bwd_ws(C.c_int64(Bt), C.c_int64(Cl), E)
+        ws = np.zeros(ws_bytes // 4 + 64, np.float32)
+        dx, dw = np.zeros((Bt, E), np.float32), np.zeros((Cl, E), np.float32)
+        assert chk.emu_check_bwd(_p(x), _p(w_hat), _p(inv), _p(local), _p(row_max), _p(row_sum), C.c_int64(Bt), C.c_int64(Cl), E,
+                                 C.c_float(s_), C.c_float(m_), kind, C.c_float(1.0 / Bt), _p(dx), _p(dw), 0, _p(ws), C.c_size_t(ws_bytes)) == 0
+        dx_sum += dx
+        want_dw = case.get(r, 0, "dw")
+        assert np.linalg.norm(dw - want_dw) < 1e-4 * np.linalg.norm(want_dw), (name, r)
+    for r in range(W):                                                               # reduce-scatter + x W (partial_fc.py:171-174)
+        assert abs(float(loss[0]) - float(case.get(r, 0, "loss"))) < 1e-4 * abs(float(case.get(r, 0, "loss")))
+        got = dx_sum[r * B:(r + 1) * B] * W
+        want = case.get(r, 0, "x_grad")
+        assert np.linalg.norm(got - want) < 1e-4 * np.linalg.norm(want), (name, r)
