@@ -518,3 +518,49 @@ def test_check_mode_path_under_emulation_matches_reference(libs, name):
         got = dx_sum[r * B:(r + 1) * B] * W
         want = case.get(r, 0, "x_grad")
         assert np.linalg.norm(got - want) < 1e-4 * np.linalg.norm(want), (name, r)
+
+
+def test_new_entry_points_with_the_product_ctypes_signatures(libs, tmp_path):
+    """pfc_bce_head_fwd/bwd, pfc_similar_columns and pfc_roc_histogram called on the emulated build with the argtypes of
+    fedfr_b200/_native.py and arguments marshalled the way the Python wrappers marshal them (data_ptr ints, Python
+    ints/floats, None for NULL): catches a signature drift between include/fedfr_b200.h, the .cu files and _native.py."""
+    from fedfr_b200 import _native as N
+    from oracle import bce_head_oracle as OB, hardneg_oracle as OH, roc_oracle as OR
+    built = {"pfc_bce_head_fwd": _build_abi("bce_head", str(tmp_path)), "pfc_similar_columns": _build_abi("hardneg", str(tmp_path)),
+             "pfc_roc_histogram": _build_abi("roc", str(tmp_path))}
+    built["pfc_bce_head_bwd"] = built["pfc_bce_head_fwd"]
+    fn = {}
+    for name, lib in built.items():
+        f = getattr(lib, name)
+        f.restype, f.argtypes = N.SIGNATURES[name]
+        fn[name] = f
+    g = torch.Generator().manual_seed(5)
+    B, Cn, E = 6, 4, 48
+    feat, weight, bias = torch.randn(B, E, generator=g), torch.randn(Cn, E, generator=g) * 0.01, torch.randn(Cn, generator=g)
+    y = torch.tensor([0, 3, 9, 1, 2, 2])
+    logits, gt, cosine = torch.empty(B, Cn), torch.empty(B, Cn, dtype=torch.uint8), torch.empty(B, Cn)
+    inv_nf, inv_nw = torch.empty(B), torch.empty(Cn)
+    assert fn["pfc_bce_head_fwd"](N.ptr(feat), N.ptr(weight), N.ptr(bias), N.ptr(y), B, Cn, E, 0.4, 30.0, 3.0, N.ptr(logits), N.ptr(gt),
+                                  N.ptr(cosine), N.ptr(inv_nf), N.ptr(inv_nw), None) == 0
+    lo, gto, cso, nf, nw = OB.forward(feat.double(), weight.double(), bias.double(), y, 0.4, 30.0, 3)
+    assert torch.equal(gt.bool(), gto) and torch.allclose(logits.double(), lo, rtol=1e-5, atol=1e-5)
+    dlogits = torch.randn(B, Cn, generator=g)
+    dfeat, dweight, dbias = torch.empty(B, E), torch.empty(Cn, E), torch.empty(Cn)
+    assert fn["pfc_bce_head_bwd"](N.ptr(feat), N.ptr(weight), N.ptr(cosine), N.ptr(inv_nf), N.ptr(inv_nw), N.ptr(dlogits), B, Cn, E, 30.0, 3.0,
+                                  N.ptr(dfeat), N.ptr(dweight), N.ptr(dbias), None) == 0
+    dfo, dwo, dbo = OB.backward(feat.double(), weight.double(), cso, nf, nw, dlogits.double(), 30.0, 3)
+    assert torch.allclose(dfeat.double(), dfo, rtol=1e-4, atol=1e-7) and torch.allclose(dweight.double(), dwo, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(dbias.double(), dbo, rtol=1e-5, atol=1e-6)
+
+    a = torch.nn.functional.normalize(torch.randn(10, E, generator=g))
+    b = torch.nn.functional.normalize(torch.randn(70, E, generator=g))
+    hit = torch.full((70,), 7, dtype=torch.uint8)
+    assert fn["pfc_similar_columns"](N.ptr(a), a.shape[0], N.ptr(b), b.shape[0], E, 0.2, N.ptr(hit), None) == 0
+    certain, amb = OH.similar_columns(a.numpy(), b.numpy(), 0.2)
+    got = set(torch.nonzero(hit, as_tuple=True)[0].tolist())
+    assert set(certain.tolist()) <= got <= set(certain.tolist()) | set(amb.tolist()) and int(hit.max()) <= 1
+
+    lab = torch.randint(0, 3, (70,), generator=g).int()
+    out = torch.zeros(4002, dtype=torch.int64)
+    assert fn["pfc_roc_histogram"](N.ptr(b), N.ptr(lab), 70, N.ptr(b[20:50]), N.ptr(lab[20:50]), 30, 20, E, N.ptr(out), None) == 0
+    assert np.array_equal(out.numpy(), OR.roc_histogram(b.numpy(), lab.numpy(), b[20:50].numpy(), lab[20:50].numpy(), 20))
