@@ -26,6 +26,14 @@ extern "C" void emu_roc(const float* feature, const int32_t* label, int64_t n, c
   });
 }
 ''',
+    "roc2": r'''
+extern "C" void emu_roc2(const float* feature, const int32_t* label, int64_t n, const float* sub, const int32_t* sublabel,
+                         int64_t n_sub, int64_t sub_offset, int emb, float coef, unsigned long long* hist, int grid) {
+  emu_launch((unsigned)grid, pfc::kRocThreads, [=]() {
+    pfc::roc_hist2_kernel(feature, label, n, sub, sublabel, n_sub, sub_offset, emb, coef, hist);
+  });
+}
+''',
     "hardneg": r'''
 extern "C" void emu_similar(const float* a, int64_t n_a, const float* b, int64_t n_b, int emb, float thr, unsigned char* hit, int grid) {
   emu_launch((unsigned)grid, pfc::kHnThreads, [=]() { pfc::similar_columns_kernel(a, n_a, b, n_b, emb, thr, hit); });
@@ -141,7 +149,7 @@ def _build_abi(name, tmp, extra=""):
 
 
 def _build(name, tmp):
-    src = open(os.path.join(ROOT, "fedfr_b200", "csrc", name + ".cu")).read()
+    src = open(os.path.join(ROOT, "fedfr_b200", "csrc", {"roc2": "roc"}.get(name, name) + ".cu")).read()
     end = src.index("}  // namespace pfc") + len("}  // namespace pfc")
     body = src[:end].replace('#include "common.cuh"', '#include "cuda_emu.h"')
     assert "cuda_emu.h" in body
@@ -564,3 +572,35 @@ def test_new_entry_points_with_the_product_ctypes_signatures(libs, tmp_path):
     out = torch.zeros(4002, dtype=torch.int64)
     assert fn["pfc_roc_histogram"](N.ptr(b), N.ptr(lab), 70, N.ptr(b[20:50]), N.ptr(lab[20:50]), 30, 20, E, N.ptr(out), None) == 0
     assert np.array_equal(out.numpy(), OR.roc_histogram(b.numpy(), lab.numpy(), b[20:50].numpy(), lab[20:50].numpy(), 20))
+
+
+@pytest.mark.parametrize("kind,n,emb,t,off,grid", [("random", 150, 40, 100, 0, 3), ("random", 70, 512, 40, 0, 2), ("edges", 96, 64, 96, 0, 2),
+                                                  ("edges", 70, 33, 30, 20, 1), ("scaled", 80, 100, 80, 0, 4)])
+def test_two_tier_roc_kernel_is_integer_identical(libs, kind, n, emb, t, off, grid):
+    """roc_hist2_kernel (fp32 FMA filter + exact chain near bin edges) must reproduce the exact kernel's histogram for every
+    input -- including rows whose cosine sits EXACTLY on a bin edge (one-hot, duplicate, opposite, zero rows)."""
+    from oracle import roc_oracle as R
+    rng = np.random.default_rng(n + emb)
+    f = rng.standard_normal((n, emb)).astype(np.float32)
+    f /= np.linalg.norm(f, axis=1, keepdims=True)
+    if kind == "edges":
+        for r in range(0, n, 3):                       # one-hot rows: dots are exactly 0 or 1 -> x = 1000 / 2000 on the edge
+            f[r] = 0
+            f[r, (r // 3) % emb] = 1.0
+        f[1] = f[4]
+        f[7] = -f[4]
+        f[10] = 0.0
+        f[13] = 0.5 * f[16]                            # cosine-like value 0.5 * |f16|^2 ~ 0.5 -> x ~ 1500 (edge or a hair off it)
+    if kind == "scaled":
+        f *= rng.uniform(0.2, 1.0, (n, 1)).astype(np.float32)
+    l = rng.integers(0, 5, n).astype(np.int32)
+    sub, subl = np.ascontiguousarray(f[off:off + t]), np.ascontiguousarray(l[off:off + t])
+    want = R.roc_histogram(f, l, sub, subl, off)
+    coef = np.float32((32 + (emb + 31) // 32 + 2) * 2.0 ** -24)
+    hist = np.zeros(4002, dtype=np.uint64)
+    libs["roc2"].emu_roc2(_p(f), _p(l), C.c_int64(n), _p(sub), _p(subl), C.c_int64(sub.shape[0]), C.c_int64(off), emb, C.c_float(coef),
+                          _p(hist), grid)
+    assert np.array_equal(hist.astype(np.int64), want)
+    exact = np.zeros(4002, dtype=np.uint64)
+    libs["roc"].emu_roc(_p(f), _p(l), C.c_int64(n), _p(sub), _p(subl), C.c_int64(sub.shape[0]), C.c_int64(off), emb, _p(exact), grid)
+    assert np.array_equal(hist, exact)

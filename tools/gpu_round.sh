@@ -18,6 +18,7 @@ timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_r
 timeout 300 python tools/shape_bench.py 1 2 4 8 > $OUT/shape_bench.jsonl 2> $OUT/shape_bench.err
 cat $OUT/shape_bench.jsonl
 timeout 120 python tools/roc_bench.py > $OUT/roc_bench.jsonl 2> $OUT/roc_bench.err
+timeout 120 python tools/roc_bench.py --mode 1 >> $OUT/roc_bench.jsonl 2>> $OUT/roc_bench.err
 cat $OUT/roc_bench.jsonl
 if [ "$3" != "skip-ncu" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 120 --csv --log-file $OUT/launches.csv \
