@@ -77,10 +77,12 @@ def test_gpu_matches_oracle(pkg, na, nb, emb, thr):
     from oracle import hardneg_oracle as O
     g = torch.Generator().manual_seed(na + nb)
     a = torch.nn.functional.normalize(torch.randn(na, emb, generator=g))
-    b = torch.nn.functional.normalize(torch.randn(nb, emb, generator=g) + (0.6 * a[torch.randint(0, max(na, 1), (nb,), generator=g)] if na else 0))
+    b = torch.nn.functional.normalize(torch.randn(nb, emb, generator=g) + (0.21 * emb ** 0.5 * a[torch.randint(0, max(na, 1), (nb,), generator=g)] if na else 0))
     got = pkg.similar_columns(a.to("cuda:0"), b.to("cuda:0"), thr)
     c, amb = O.similar_columns(a.numpy(), b.numpy(), thr)
     assert _agrees(got, c, amb)
+    if (na, nb) == (300, 5000):
+        assert 0.2 * nb < len(got) < 0.8 * nb                 # a real mix of hits and misses
     if thr == -1.5 and na:
         assert len(got) == nb
     if thr == 2.0 or na == 0:
