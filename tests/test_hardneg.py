@@ -63,11 +63,11 @@ def test_gpu_matches_reference_golden(pkg, golden):
     from oracle import hardneg_oracle as O
     dev = "cuda:0"
     ids = pkg.hard_negative_ids(torch.from_numpy(golden["self_fc"]).to(dev), torch.from_numpy(golden["pretrain_fc"]).to(dev), 0.2)
-    c, a = O.similar_columns(O.normalize(golden["self_fc"]), O.normalize(golden["pretrain_fc"]), 0.2)
+    c, a = O.similar_columns(O.normalize(golden["self_fc"]), O.normalize(golden["pretrain_fc"]), 0.2, band=1e-5)
     assert _agrees(ids, c, a) and len(set(ids.tolist()) ^ set(golden["HN_ID"].tolist())) <= len(a)
     idx = pkg.similar_columns(torch.from_numpy(golden["local_feats"]).to(dev), torch.from_numpy(golden["pretrained_feats"]).to(dev),
                               float(golden["threshold2"]))
-    c, a = O.similar_columns(golden["local_feats"], golden["pretrained_feats"], float(golden["threshold2"]))
+    c, a = O.similar_columns(golden["local_feats"], golden["pretrained_feats"], float(golden["threshold2"]), band=1e-5)
     assert _agrees(idx, c, a) and np.all(np.diff(idx) > 0)
 
 
@@ -79,8 +79,8 @@ def test_gpu_matches_oracle(pkg, na, nb, emb, thr):
     a = torch.nn.functional.normalize(torch.randn(na, emb, generator=g))
     b = torch.nn.functional.normalize(torch.randn(nb, emb, generator=g) + (0.21 * emb ** 0.5 * a[torch.randint(0, max(na, 1), (nb,), generator=g)] if na else 0))
     got = pkg.similar_columns(a.to("cuda:0"), b.to("cuda:0"), thr)
-    c, amb = O.similar_columns(a.numpy(), b.numpy(), thr)
-    assert _agrees(got, c, amb)
+    c, amb = O.similar_columns(a.numpy(), b.numpy(), thr, band=1e-5)      # 512-step fp32 FMA chain: gamma_512 * sum|ab| < 1e-5 here
+    assert _agrees(got, c, amb) and len(amb) <= 5
     if (na, nb) == (300, 5000):
         assert 0.2 * nb < len(got) < 0.8 * nb                 # a real mix of hits and misses
     if thr == -1.5 and na:
