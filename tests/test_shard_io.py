@@ -161,5 +161,6 @@ def test_gpu_checkpoint_roundtrip_and_loaders(pkg, tmp_path, sr):
         c.update_from_tensor(new_w)
         x, y, x_grad, loss = _train_one_step(c, seed=3)
         ref = O.forward_backward([x.cpu()], [y.cpu()], [new_w], 300, 64.0, 0.4)
-        assert abs(float(loss) - float(ref.loss)) < 1e-2 * abs(float(ref.loss))
-        assert float((x_grad.cpu() - ref.x_grad[0]).norm() / ref.x_grad[0].norm()) < 1e-2
+        # which shard was used, not kernel numerics (those are test_gpu_parity's job): a stale shard is off by O(1)
+        assert abs(float(loss) - float(ref.loss)) < 5e-2 * abs(float(ref.loss))
+        assert float((x_grad.cpu() - ref.x_grad[0]).norm() / ref.x_grad[0].norm()) < 5e-2
