@@ -17,6 +17,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 
+# EMU_ASAN=1 (set by test_emulated_kernels_under_address_sanitizer for its child process) instruments the emulated builds
+SAN_FLAGS = ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"] if os.environ.get("EMU_ASAN") == "1" else []
+
 HARNESS = {
     "roc": r'''
 extern "C" void emu_roc(const float* feature, const int32_t* label, int64_t n, const float* sub, const int32_t* sublabel,
@@ -142,8 +145,8 @@ def _build_abi(name, tmp, extra=""):
     with open(cpp, "w") as f:
         f.write(body)
     so = os.path.join(tmp, name + "_abi_emu.so")
-    r = subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
-                        "-I", os.path.join(HERE, "emu"), cpp, "-o", so], capture_output=True, text=True)
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas"] + SAN_FLAGS +
+                       ["-I", os.path.join(HERE, "emu"), cpp, "-o", so], capture_output=True, text=True)
     assert r.returncode == 0, "\n".join(l for l in r.stderr.splitlines() if "error" in l)[:1500]
     return C.CDLL(so)
 
@@ -157,8 +160,8 @@ def _build(name, tmp):
     with open(cpp, "w") as f:
         f.write(body + "\n" + HARNESS[name])
     so = os.path.join(tmp, name + "_emu.so")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
-                           "-I", os.path.join(HERE, "emu"), cpp, "-o", so])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas"] + SAN_FLAGS +
+                          ["-I", os.path.join(HERE, "emu"), cpp, "-o", so])
     return C.CDLL(so)
 
 
@@ -604,3 +607,19 @@ def test_two_tier_roc_kernel_is_integer_identical(libs, kind, n, emb, t, off, gr
     exact = np.zeros(4002, dtype=np.uint64)
     libs["roc"].emu_roc(_p(f), _p(l), C.c_int64(n), _p(sub), _p(subl), C.c_int64(sub.shape[0]), C.c_int64(off), emb, _p(exact), grid)
     assert np.array_equal(hist, exact)
+
+
+@pytest.mark.skipif(os.environ.get("EMU_ASAN") == "1", reason="this IS the sanitizer child")
+def test_emulated_kernels_under_address_sanitizer():
+    """memcheck on the CPU: every test of this file again in a child process whose emulated builds are compiled with
+    -fsanitize=address (shared-memory arrays are instrumented globals, "device" buffers are malloc'd numpy arrays with red
+    zones), so an out-of-bounds load or store in any emulated kernel aborts the child."""
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    env = dict(os.environ, LD_PRELOAD=asan, EMU_ASAN="1", ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, cwd=ROOT, timeout=1500)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0 and "AddressSanitizer" not in r.stdout + r.stderr.replace(
+        "ASan doesn't fully support makecontext/swapcontext", ""), tail
