@@ -99,7 +99,11 @@ static void emu_trampoline() { g_body(); g_fibers[g_cur].done = true; }
 template <class F> static void emu_launch(EmuDim3 grid, unsigned block, F body) {
   g_gridDim = grid; g_blockDim.x = block;
   g_body = body;
-  for (unsigned b = 0; b < grid.x * grid.y; ++b) {
+  // EMU_SCHEDULE=reverse runs the threads of a block (and the blocks of a grid) in descending order: a missing barrier
+  // that ascending order happens to mask (writer has the lower index) is exposed by the other extreme
+  static const bool reverse = getenv("EMU_SCHEDULE") && strcmp(getenv("EMU_SCHEDULE"), "reverse") == 0;
+  for (unsigned bq = 0; bq < grid.x * grid.y; ++bq) {
+    const unsigned b = reverse ? grid.x * grid.y - 1 - bq : bq;
     g_blockIdx.x = b % grid.x;
     g_blockIdx.y = b / grid.x;
     g_bar_count = 0;
@@ -117,7 +121,8 @@ template <class F> static void emu_launch(EmuDim3 grid, unsigned block, F body) 
     }
     for (long rounds = 0;; ++rounds) {
       bool any = false;
-      for (unsigned t = 0; t < block; ++t) {
+      for (unsigned q = 0; q < block; ++q) {
+        const unsigned t = reverse ? block - 1 - q : q;   // each fiber runs to its next rendezvous; the order decides who gets there first
         if (g_fibers[t].done) continue;
         any = true;
         g_cur = (int)t;

@@ -613,11 +613,13 @@ def test_two_tier_roc_kernel_is_integer_identical(libs, kind, n, emb, t, off, gr
 def test_emulated_kernels_under_address_sanitizer():
     """memcheck on the CPU: every test of this file again in a child process whose emulated builds are compiled with
     -fsanitize=address (shared-memory arrays are instrumented globals, "device" buffers are malloc'd numpy arrays with red
-    zones), so an out-of-bounds load or store in any emulated kernel aborts the child."""
+    zones), so an out-of-bounds load or store in any emulated kernel aborts the child.  The child also runs threads and
+    blocks in DESCENDING order (EMU_SCHEDULE=reverse): results that depend on a missing barrier differ between the two orders."""
     asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
     if not os.path.isabs(asan) or not os.path.exists(asan):
         pytest.skip("libasan not available")
-    env = dict(os.environ, LD_PRELOAD=asan, EMU_ASAN="1", ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
+    env = dict(os.environ, LD_PRELOAD=asan, EMU_ASAN="1", EMU_SCHEDULE="reverse",      # and the opposite thread/block order
+               ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, cwd=ROOT, timeout=1500)
     tail = (r.stdout + r.stderr)[-3000:]
