@@ -5,7 +5,8 @@
 // never exists: a CTA computes a 64 x 64 tile of dot products from 32-wide k slices staged in shared memory, reduces
 // "any row above threshold" per column in the epilogue and sets hit[j].  Row tiles vary fastest across the persistent
 // CTAs, so the column tile of B (the big operand) is read from HBM once and shared through L2.
-// Arithmetic: fp32 FMA chains in k order -- the comparison is a hard threshold on a cosine, which a bf16 tensor-core
+// Arithmetic: fp32 FMA chains over 32-wide k slices, slices added in fp32 (error <= (32 + emb/32) * 2^-24 * |a||b|, i.e.
+// 3e-6 for unit rows at emb = 512) -- the comparison is a hard threshold on a cosine, which a bf16 tensor-core
 // product (error ~4e-3) would move for every pair inside that band; the fp32 result differs from a BLAS sgemm's only by
 // summation order (|delta| ~ 1e-7).  A tensor-core filter with an fp32 recheck of the band is the next step.
 #include "common.cuh"
@@ -52,6 +53,11 @@ similar_columns_kernel(const float* __restrict__ a, int64_t n_a, const float* __
       }
       __syncthreads();
       const int kc = (emb - k0 < kHnK) ? emb - k0 : kHnK;
+      float part[4][4];                                // blocked summation: 32-step chains, then one add per slice
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) part[u][v] = 0.f;
 #pragma unroll 4
       for (int kk = 0; kk < kc; ++kk) {
         float av[4], bv[4];
@@ -62,8 +68,12 @@ similar_columns_kernel(const float* __restrict__ a, int64_t n_a, const float* __
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-          for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
+          for (int v = 0; v < 4; ++v) part[u][v] = fmaf(av[u], bv[v], part[u][v]);
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] += part[u][v];
     }
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
