@@ -110,3 +110,35 @@ def test_two_gpu_sharded_fedavg():
     ret = mgr.dict()
     mp.spawn(_fedavg_worker, args=(2, 29761, ret), nprocs=2, join=True)
     assert max(ret.values()) < 5e-6, dict(ret)
+
+
+def _roc_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from fedfr_b200.roc import roc_histogram
+        z = np.load(os.path.join(HERE, "golden", "roc.npz"))
+        out = {}
+        for c in "abc":          # each rank takes a row range of the sub block (by pair count), one int64 all-reduce
+            out[c] = roc_histogram(z[c + "/feature"], z[c + "/label"], target_size=int(z[c + "/target_size"]),
+                                   device=torch.device("cuda", rank))
+        ret[rank] = out
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_roc_histogram():
+    """roc_cuda.py's multi-GPU fan-out (one worker process per GPU, roc_cuda.py:89-108): both ranks return the reference total."""
+    import __graft_entry__ as g
+    g.build()
+    ret = mp.Manager().dict()
+    mp.spawn(_roc_worker, args=(2, 29766, ret), nprocs=2, join=True)
+    z = np.load(os.path.join(HERE, "golden", "roc.npz"))
+    for r in (0, 1):
+        for c in "abc":
+            assert np.array_equal(ret[r][c].reshape(-1), z[c + "/hist"]), (r, c)
