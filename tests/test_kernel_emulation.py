@@ -625,3 +625,44 @@ def test_emulated_kernels_under_address_sanitizer():
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0 and "AddressSanitizer" not in r.stdout + r.stderr.replace(
         "ASan doesn't fully support makecontext/swapcontext", ""), tail
+
+
+def test_c_abi_error_codes_under_emulation(libs, tmp_path):
+    """The argument checks of the C ABI (include/fedfr_b200.h: 0 ok, PFC_E_ARG -1, PFC_E_SHAPE -2, PFC_E_WORKSPACE -4) return
+    before any launch -- exercised here on the emulated builds, where require_sm100() passes without a GPU."""
+    E_ARG, E_SHAPE, E_WS = -1, -2, -4
+    smp, rows = libs["sample_abi"], libs["rows_abi"]
+    smp.pfc_sample_workspace_bytes.restype = C.c_size_t
+    lab, perm, idx = np.zeros(4, np.int64), np.zeros(16, np.float32), np.zeros(16, np.int64)
+    ws = np.zeros(smp.pfc_sample_workspace_bytes(C.c_int64(16)) + 256, np.uint8)
+    wsp, wsb = C.c_void_p((ws.ctypes.data + 255) // 256 * 256), C.c_size_t(ws.size - 256)
+
+    def sample(label=lab, n_label=4, p=perm, num_local=16, num_sample=4, index=idx, w=wsp, wb=wsb):
+        return smp.pfc_sample_index(_p(label), C.c_int64(n_label), _p(p), C.c_int64(num_local), C.c_int64(num_sample), _p(index), None, w, wb, None)
+    assert sample() == 0
+    assert sample(label=None) == E_ARG and sample(num_local=0) == E_ARG and sample(num_sample=-1) == E_ARG
+    assert sample(num_sample=17) == E_SHAPE                       # more samples than local classes
+    assert sample(wb=C.c_size_t(8)) == E_WS
+    assert smp.pfc_remap_labels(None, C.c_int64(4), C.c_int64(0), C.c_int64(4), _p(lab), None) == E_ARG
+    assert smp.pfc_remap_labels(_p(lab), C.c_int64(0), C.c_int64(0), C.c_int64(4), _p(lab), None) == 0       # empty batch
+
+    x = np.zeros((2, 6), np.float32)
+    out = np.zeros((2, 6), np.int16)
+    assert rows.pfc_cast_rows_bf16(_p(x), C.c_int64(2), 6, _p(out), None) == E_ARG                            # emb % 4 != 0
+    assert rows.pfc_cast_rows_bf16(_p(x), C.c_int64(0), 8, _p(out), None) == 0
+
+    bce = _build_abi("bce_head", str(tmp_path))
+    f = np.zeros((2, 8), np.float32)
+    assert bce.pfc_bce_head_bwd(_p(f), _p(f), _p(f), _p(f), _p(f), _p(f), C.c_int64(2), C.c_int64(2), 2048, C.c_float(30), C.c_float(3),
+                                _p(f), _p(f), None, None) == E_SHAPE                                          # emb > 1024
+    assert bce.pfc_bce_head_fwd(None, _p(f), None, _p(lab), C.c_int64(2), C.c_int64(2), 8, C.c_float(.4), C.c_float(30), C.c_float(3),
+                                _p(f), _p(f), _p(f), _p(f), _p(f), None) == E_ARG
+    roc = _build_abi("roc", str(tmp_path))
+    l32 = np.zeros(2, np.int32)
+    assert roc.pfc_roc_histogram(_p(f), _p(l32), C.c_int64(2), _p(f), _p(l32), C.c_int64(2), C.c_int64(0), 8, None, None) == E_ARG
+    assert roc.pfc_roc_histogram(_p(f), _p(l32), C.c_int64(2), _p(f), _p(l32), C.c_int64(2), C.c_int64(-1), 8, _p(np.zeros(4002, np.int64)), None) == E_ARG
+    assert roc.pfc_set_roc_mode(2) == E_ARG and roc.pfc_set_roc_mode(0) == 0
+    hn = _build_abi("hardneg", str(tmp_path))
+    hit = np.zeros(2, np.uint8)
+    assert hn.pfc_similar_columns(_p(f), C.c_int64(2), _p(f), C.c_int64(2), 0, C.c_float(.2), _p(hit), None) == E_ARG
+    assert hn.pfc_similar_columns(_p(f), C.c_int64(2), _p(f), C.c_int64(2), 8, C.c_float(.2), None, None) == E_ARG
