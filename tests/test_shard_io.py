@@ -164,3 +164,28 @@ def test_gpu_checkpoint_roundtrip_and_loaders(pkg, tmp_path, sr):
         # which shard was used, not kernel numerics (those are test_gpu_parity's job): a stale shard is off by O(1)
         assert abs(float(loss) - float(ref.loss)) < 5e-2 * abs(float(ref.loss))
         assert float((x_grad.cpu() - ref.x_grad[0]).norm() / ref.x_grad[0].norm()) < 5e-2
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "utils", "utils_callbacks.py")), reason="reference checkout not present")
+def test_reference_checkpoint_callback_drives_this_class(pkg, tmp_path):
+    """utils/utils_callbacks.py:115-124 (CallBackModelCheckpoint, the reference's only consumer of PartialFC.save_params) run
+    unmodified with this package's PartialFC in place of the reference's."""
+    import types
+    for name in ("easydict", "mxnet", "prettytable"):                  # import-time dependencies of the reference, absent here
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["easydict"].EasyDict = getattr(sys.modules["easydict"], "EasyDict", dict)
+    for sub in ("ndarray", "recordio", "image"):
+        m = sys.modules.setdefault("mxnet." + sub, types.ModuleType("mxnet." + sub))
+        setattr(sys.modules["mxnet"], sub, m)
+    sys.modules["prettytable"].PrettyTable = getattr(sys.modules["prettytable"], "PrettyTable", object)
+    sys.path.insert(0, REF)
+    from utils.utils_callbacks import CallBackModelCheckpoint
+    head = _head(pkg, tmp_path)
+    _train_one_step(head)
+    backbone = types.SimpleNamespace(module=torch.nn.Linear(4, 4))
+    cb = CallBackModelCheckpoint(rank=0, output=str(tmp_path))
+    cb(0, backbone, head)
+    assert os.listdir(tmp_path) == []                                   # global_step == 0: nothing is written (:121,123)
+    cb(7, backbone, head)
+    assert sorted(os.listdir(tmp_path)) == ["backbone.pth", "rank:0_softmax_weight.pt", "rank:0_softmax_weight_mom.pt"]
+    assert torch.equal(torch.load(head.weight_name), head.weight) and torch.equal(torch.load(head.weight_mom_name), head.weight_mom)
