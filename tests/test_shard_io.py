@@ -5,7 +5,6 @@ with the unmodified reference class in both directions."""
 import os
 import sys
 
-import numpy as np
 import pytest
 import torch
 

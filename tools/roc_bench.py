@@ -4,7 +4,6 @@ N features, E = 512) and at a full triangle; prints one JSON line per shape.  Un
 import json
 import sys
 
-import numpy as np
 import torch
 
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
