@@ -666,3 +666,26 @@ def test_c_abi_error_codes_under_emulation(libs, tmp_path):
     hit = np.zeros(2, np.uint8)
     assert hn.pfc_similar_columns(_p(f), C.c_int64(2), _p(f), C.c_int64(2), 0, C.c_float(.2), _p(hit), None) == E_ARG
     assert hn.pfc_similar_columns(_p(f), C.c_int64(2), _p(f), C.c_int64(2), 8, C.c_float(.2), None, None) == E_ARG
+
+
+def test_sampling_abi_under_emulation_property(libs):
+    """Random shard sizes, label batches (incl. none owned, all owned, duplicates) and perm draws quantised to force ties
+    at the k-th value: the index kernel chain equals the oracle's topk + sort + searchsorted every time."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import partial_fc_oracle as O
+
+    @settings(max_examples=30, deadline=None, derandomize=True)
+    @given(st.integers(1, 2600), st.integers(0, 150), st.floats(0.0, 1.0), st.integers(0, 2 ** 31 - 1), st.sampled_from([0, 4, 64, 4096]))
+    def run(num_local, n_label, rate, seed, quant):
+        rng = np.random.default_rng(seed)
+        perm = rng.random(num_local, dtype=np.float32)
+        if quant:
+            perm = (np.floor(perm * quant) / quant).astype(np.float32)      # heavy ties
+        labels = rng.integers(-20, num_local + 20, n_label).astype(np.int64)
+        num_sample = int(rate * num_local)
+        index, local = _sample_abi(libs["sample_abi"], labels, perm, 0, num_local, num_sample)
+        local0 = O.remap_labels(labels, 0, num_local)
+        want = O.sample_index(local0, perm, num_sample)
+        assert np.array_equal(index, want)
+        assert np.array_equal(local, O.relabel_to_sample(local0, want))
+    run()
