@@ -689,3 +689,46 @@ def test_sampling_abi_under_emulation_property(libs):
         assert np.array_equal(index, want)
         assert np.array_equal(local, O.relabel_to_sample(local0, want))
     run()
+
+
+def test_fedavg_abi_under_emulation_property(libs):
+    """Random client counts, segment counts and lengths around the vector / block boundaries (0, 1, 3, 4, 5, 1023, 1024,
+    1025 ...), fp32 and int64 segments: fedavg_weighted_sum equals the sequential fp32 multiply-then-add of server.py:30-33
+    bit for bit."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import partial_fc_oracle as O
+    lib = libs["fedavg_abi"]
+    lib.fedavg_table_bytes.restype = C.c_size_t
+    lens = st.sampled_from([0, 1, 3, 4, 5, 7, 8, 255, 1023, 1024, 1025, 2048, 3001])
+
+    @settings(max_examples=25, deadline=None, derandomize=True)
+    @given(st.integers(1, 9), st.lists(st.tuples(lens, st.booleans()), min_size=1, max_size=5), st.integers(0, 2 ** 31 - 1))
+    def run(K, segs, seed):
+        rng = np.random.default_rng(seed)
+        weights = [float(w) for w in rng.integers(1, 10000, K)]
+        wn = np.array([np.float32(w) for w in O.fedavg_weights(weights)], dtype=np.float32)
+        models = []
+        for i in range(K):
+            sd = {}
+            for s, (n, is_int) in enumerate(segs):
+                sd[f"t{s}"] = rng.integers(0, 100000, n).astype(np.int64) if is_int else rng.standard_normal(n).astype(np.float32)
+            models.append(sd)
+        keys = list(models[0].keys())
+        srcs = [[np.ascontiguousarray(m[k]) for m in models] for k in keys]
+        outs = [np.full(max(g[0].size, 4), np.nan, dtype=np.float32) for g in srcs]
+        assert all(a.ctypes.data % 16 == 0 or a.size < 4 for g in srcs for a in g)
+        seg_src = np.array([a.ctypes.data for g in srcs for a in g], dtype=np.uint64)
+        seg_out = np.array([o.ctypes.data for o in outs], dtype=np.uint64)
+        seg_len = np.array([g[0].size for g in srcs], dtype=np.int64)
+        seg_dtype = np.array([1 if g[0].dtype == np.int64 else 0 for g in srcs], dtype=np.int32)
+        tb = lib.fedavg_table_bytes(len(keys), K)
+        table = np.zeros(tb + 256, dtype=np.uint8)
+        rc = lib.fedavg_weighted_sum(_p(seg_src), _p(seg_out), _p(seg_len), _p(seg_dtype), len(keys), _p(wn), K,
+                                     C.c_void_p((table.ctypes.data + 255) // 256 * 256), C.c_size_t(tb), None)
+        assert rc == 0
+        want = O.fedpavg(models, weights)
+        for k, o in zip(keys, outs):
+            w = np.asarray(want[k], dtype=np.float32).reshape(-1)
+            assert np.array_equal(o[:w.size], w), (k, w.size)
+            assert np.all(np.isnan(o[w.size:]))                          # nothing written past the segment
+    run()
