@@ -118,9 +118,36 @@ roc_hist_kernel(const float* __restrict__ feature, const int32_t* __restrict__ l
 //   |A - T| <= (32 + n_slices + 2) * 2^-24 * |a_i| |b_j|          (gamma_n bound of the two summation levels + the product
 //                                                                   roundings of T; Cauchy-Schwarz for sum |a_k b_k|)
 // so with x = (A + 1) * 1000 in fp64 and e = 1000 * bound (inflated for the fp32 norms, plus an absolute slack), the bin is
-// int(x) whenever x is farther than e from an integer; otherwise the thread recomputes T from global memory.  The result
+// int(x) whenever x is farther than e from an integer; otherwise the pair is queued in shared memory and the CTA later
+// recomputes T for 256 queued pairs at a time (every lane busy, no divergence inside the tile epilogue).  The result
 // is integer-identical to roc_hist_kernel for every input (tests/test_kernel_emulation.py drives both with rows that
 // land exactly on bin edges).
+constexpr int kRocQueue = 1024;
+
+__device__ __forceinline__ double roc_exact_x(const float* __restrict__ a, const float* __restrict__ b, int emb) {
+  double tmp = 0.0;
+  for (int k = 0; k < emb; ++k) tmp = __dadd_rn(tmp, (double)__fmul_rn(a[k], b[k]));
+  return __dmul_rn(__dadd_rn(tmp, 1.0), 1000.0);
+}
+
+// Exact chain for every queued pair, one pair per thread.  Called by the whole CTA (barriers inside); q_n may exceed the
+// capacity when the queue overflowed -- those pairs were handled by their owners.
+__device__ __forceinline__ void roc_drain(const unsigned int* q_i, const unsigned int* q_j, unsigned int* q_n,
+                                          const float* __restrict__ sub, const int32_t* __restrict__ sublabel,
+                                          const float* __restrict__ feature, const int32_t* __restrict__ label, int emb,
+                                          unsigned int* h) {
+  const unsigned int n_q = *q_n < (unsigned)kRocQueue ? *q_n : (unsigned)kRocQueue;
+  for (unsigned int e = threadIdx.x; e < n_q; e += kRocThreads) {
+    const int64_t i = q_i[e], j = q_j[e];
+    int bin = (int)roc_exact_x(sub + i * emb, feature + j * emb, emb);
+    bin = bin < 0 ? 0 : (bin > kRocBins - 1 ? kRocBins - 1 : bin);
+    atomicAdd(&h[2 * bin + (sublabel[i] != label[j] ? 1 : 0)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *q_n = 0u;
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kRocThreads, 2)
 roc_hist2_kernel(const float* __restrict__ feature, const int32_t* __restrict__ label, int64_t n,
                  const float* __restrict__ sub, const int32_t* __restrict__ sublabel, int64_t n_sub, int64_t sub_offset,
@@ -129,9 +156,12 @@ roc_hist2_kernel(const float* __restrict__ feature, const int32_t* __restrict__ 
   __shared__ float Bs[kRocTile][kRocK + 1];
   __shared__ float nA[kRocTile], nB[kRocTile];
   __shared__ unsigned int h[2 * kRocBins];
+  __shared__ unsigned int q_i[kRocQueue], q_j[kRocQueue];   // pairs that need the exact chain, gathered over several tiles
+  __shared__ unsigned int q_n;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int lane = tid & 31, wrow = tid >> 5;
+  if (tid == 0) q_n = 0u;
   for (int b = tid; b < 2 * kRocBins; b += kRocThreads) h[b] = 0u;
   __syncthreads();
 
@@ -218,22 +248,28 @@ roc_hist2_kernel(const float* __restrict__ feature, const int32_t* __restrict__ 
         const double e = 1000.0 * (double)coef * (double)nA[ty + 16 * u] * (double)nB[tx + 16 * v] + 1e-6;
         const double fl = floor(x);
         if (!(x - fl > e && fl + 1.0 - x > e && x > e)) {              // could be on a bin edge (or below zero, or NaN): exact chain
-          const float* a = sub + i * emb;
-          const float* b = feature + j * emb;
-          double tmp = 0.0;
-          for (int k = 0; k < emb; ++k) tmp = __dadd_rn(tmp, (double)__fmul_rn(a[k], b[k]));
-          x = __dmul_rn(__dadd_rn(tmp, 1.0), 1000.0);
+          const unsigned int slot = atomicAdd(&q_n, 1u);
+          if (slot < (unsigned)kRocQueue) {                             // later, 256 pairs at a time with every lane busy
+            q_i[slot] = (unsigned int)i;
+            q_j[slot] = (unsigned int)j;
+            continue;
+          }
+          x = roc_exact_x(sub + i * emb, feature + j * emb, emb);       // queue full (adversarial input): do it here
         }
         int bin = (int)x;
         bin = bin < 0 ? 0 : (bin > kRocBins - 1 ? kRocBins - 1 : bin);
         atomicAdd(&h[2 * bin + (li != label[j] ? 1 : 0)], 1u);
       }
     }
+    __syncthreads();
+    if (q_n >= (unsigned)(kRocQueue - kRocQueue / 4)) roc_drain(q_i, q_j, &q_n, sub, sublabel, feature, label, emb, h);   // uniform
     if (++tiles_done == kRocFlushTiles) {
       roc_flush(h, hist);
       tiles_done = 0;
     }
   }
+  __syncthreads();
+  roc_drain(q_i, q_j, &q_n, sub, sublabel, feature, label, emb, h);
   roc_flush(h, hist);
 }
 
@@ -258,7 +294,7 @@ int pfc_roc_histogram(const float* feature, const int32_t* label, int64_t n, con
   if (n == 0 || n_sub == 0) return 0;
   PFC_REQUIRE(feature && label && subfeature && sublabel, PFC_E_ARG, "pfc_roc_histogram: null pointer");
   const int64_t total = ((n_sub + kRocTile - 1) / kRocTile) * ((n + kRocTile - 1) / kRocTile);
-  if (g_roc_mode == 1) {
+  if (g_roc_mode == 1 && n < (1ll << 32) && n_sub < (1ll << 32)) {        // the pair queue stores 32-bit row ids
     const float coef = (float)(kRocK + (emb + kRocK - 1) / kRocK + 2) * 5.9604645e-8f;      // (32 + n_slices + 2) * 2^-24
     roc_hist2_kernel<<<roc_grid(total), kRocThreads, 0, as_stream(stream)>>>(
         feature, label, n, subfeature, sublabel, n_sub, sub_offset, emb, coef, reinterpret_cast<unsigned long long*>(hist));

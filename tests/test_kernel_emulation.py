@@ -578,7 +578,8 @@ def test_new_entry_points_with_the_product_ctypes_signatures(libs, tmp_path):
 
 
 @pytest.mark.parametrize("kind,n,emb,t,off,grid", [("random", 150, 40, 100, 0, 3), ("random", 70, 512, 40, 0, 2), ("edges", 96, 64, 96, 0, 2),
-                                                  ("edges", 70, 33, 30, 20, 1), ("scaled", 80, 100, 80, 0, 4)])
+                                                  ("edges", 70, 33, 30, 20, 1), ("scaled", 80, 100, 80, 0, 4),
+                                                  ("alledges", 128, 16, 128, 0, 1), ("halfedges", 200, 24, 150, 0, 2)])
 def test_two_tier_roc_kernel_is_integer_identical(libs, kind, n, emb, t, off, grid):
     """roc_hist2_kernel (fp32 FMA filter + exact chain near bin edges) must reproduce the exact kernel's histogram for every
     input -- including rows whose cosine sits EXACTLY on a bin edge (one-hot, duplicate, opposite, zero rows)."""
@@ -596,6 +597,10 @@ def test_two_tier_roc_kernel_is_integer_identical(libs, kind, n, emb, t, off, gr
         f[13] = 0.5 * f[16]                            # cosine-like value 0.5 * |f16|^2 ~ 0.5 -> x ~ 1500 (edge or a hair off it)
     if kind == "scaled":
         f *= rng.uniform(0.2, 1.0, (n, 1)).astype(np.float32)
+    if kind in ("alledges", "halfedges"):              # every (or every other) pair on a bin edge: the exact-chain queue of a CTA
+        for r in range(0, n, 1 if kind == "alledges" else 2):          # overflows / is drained several times across tiles
+            f[r] = 0
+            f[r, r % emb] = 1.0
     l = rng.integers(0, 5, n).astype(np.int32)
     sub, subl = np.ascontiguousarray(f[off:off + t]), np.ascontiguousarray(l[off:off + t])
     want = R.roc_histogram(f, l, sub, subl, off)
