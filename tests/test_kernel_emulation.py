@@ -626,7 +626,8 @@ def test_emulated_kernels_under_address_sanitizer():
     env = dict(os.environ, LD_PRELOAD=asan, EMU_ASAN="1", EMU_SCHEDULE="reverse",      # and the opposite thread/block order
                ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-p", "no:cacheprovider",
-                        "-k", "not property"],                           # the hypothesis sweeps re-use kernels covered by the fixed cases
+                        "-k", "not property and not sgd_step and not stats_abi and not check_mode"],     # time budget: the sweeps and
+                       # the slowest B200-validated kernels stay in the plain pass only
                        env=env, capture_output=True, text=True, cwd=ROOT, timeout=1500)
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0 and "AddressSanitizer" not in r.stdout + r.stderr.replace(
