@@ -1123,6 +1123,7 @@ struct DwParams {
   int accumulate;
   int prefetch;                   // 1: TMA L2 prefetch of the next tile's G / w_hat boxes
   long long* dbg;                 // optional cycle counters of CTA 0 (developer instrumentation), else nullptr
+  int exp;                        // timing experiments only (FEDFR_DW_EXP, wrong results): 1 no pass 1, 2 no exchange, 4 no pass 2 / stores, 8 no w_hat loads
 };
 
 __device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
@@ -1284,7 +1285,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
     };
     constexpr int kSub = NG == 1 ? 4 : 0;                 // 32-column warps read the upper / lower half of their 64-e box
     const int sub0 = NG == 1 ? ((e_warp >> 5) & 1) * kSub : 0;
-    if (lane == 0 && more(0)) issue_w(0);
+    const int ex = p.exp;
+    if (lane == 0 && more(0) && !(ex & 8)) issue_w(0);
     for (int it = 0; more(it); ++it) {
       const int ct = tile_of(it);
       const int acc = it & 1;
@@ -1296,7 +1298,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
       mbar_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1));
       t_wfull += clock64() - c0;
       c0 = clock64();
-      mbar_wait(wbar, (uint32_t)(it & 1));
+      if (!(ex & 8)) mbar_wait(wbar, (uint32_t)(it & 1));
       t_ww += clock64() - c0;
       c0 = clock64();
       tc_fence_after();
@@ -1316,6 +1318,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
                                 make_float2(__uint_as_float(v[q * 8 + 2 * k]), __uint_as_float(v[q * 8 + 2 * k + 1])), dot2);
           }
         };
+        if (!(ex & 1)) {
         tmem_ld_x32(t_base, va);
 #pragma unroll
         for (int g = 0; g < NG; g += 2) {
@@ -1328,11 +1331,12 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
             dot_group(vb, g + 1);
           }
         }
+        }
       }
       t_p1 += clock64() - c0;
       // ---- exchange: every contributor (column half x cluster rank) publishes its partial to each CTA that needs it
-      float t;
-      {
+      float t = 0.f;
+      if (!(ex & 2)) {
         const int buf = it & 1;
         float* slot = tpart + (buf * 4 + contrib) * 128 + quad * 32 + lane;
         *slot = dot2.x + dot2.y;
@@ -1385,11 +1389,13 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
             tma_store_commit();
           }
         };
+        if (!(ex & 4)) {
 #pragma unroll
         for (int g = 0; g < NG; ++g) {                    // (one group in flight: the 16 w_hat registers leave no room for two)
           tmem_ld_x32(t_base + g * 32, va);
           tmem_ld_wait();
           out_group(va, g);
+        }
         }
       }
       t_p2 += clock64() - c0;
@@ -1398,7 +1404,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
       if (lane == 0) {
         mbar_arrive(&tmem_empty[acc]);
         if (NG > 1) tma_store_wait_read<0>();             // the staging boxes are this warp's w_hat boxes: all reads done before the reload
-        if (more(it + 1)) issue_w(it + 1);
+        if (more(it + 1) && !(ex & 8)) issue_w(it + 1);
       }
       __syncwarp();
       t_ep += clock64() - c0;
@@ -2235,6 +2241,8 @@ static int tc_bwd_prob_enqueue(const void* w_hat, const float* inv_norm, const i
   if (paced) wp.sweep = SweepSync{sweep_ctr + 1, sweep_ctr, g_sweep_lead};
   wp.n_rows = (int)n_rows; wp.n_classes = (int)n_classes; wp.emb = emb; wp.n_ct = (int)((n_classes + BM - 1) / BM); wp.n_rb = n_rb;
   wp.inv_norm = inv_norm; wp.accumulate = accumulate_dw; wp.dbg = g_dbg; wp.prefetch = g_prefetch[2];
+  static const int dw_exp = getenv("FEDFR_DW_EXP") ? atoi(getenv("FEDFR_DW_EXP")) : 0;
+  wp.exp = dw_exp;
   prof_begin(PH_DW, sW);
   if (exp_mode == 4) rc = 0;                   // dx alone
   else switch (emb) {

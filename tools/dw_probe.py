@@ -33,6 +33,7 @@ torch.cuda.synchronize()
 N.lib.pfc_set_debug_buffer(None)
 d = dbg.tolist()
 n_ct = (Cc + 127) // 128
-items = int(os.environ.get("PROBE_ITEMS", "0")) or (n_ct + 49) // 50
+ncl = int(os.environ.get("PROBE_CLUSTERS", "52"))
+items = int(os.environ.get("PROBE_ITEMS", "0")) or (n_ct + ncl - 1) // ncl
 print(f"per item (~{items} items, cycles): total {d[2]/items:.0f} | MMA warp: wait tmem_empty {d[0]/items:.0f} wait stage {d[1]/items:.0f} | "
       f"epilogue warp0: wait tmem_full {d[3]/items:.0f} wait w_hat {d[4]/items:.0f} work {d[5]/items:.0f} (cumulative: pass1 {d[6]/items:.0f} exchange {d[7]/items:.0f} pass2 {d[8]/items:.0f})")
