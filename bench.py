@@ -139,8 +139,24 @@ def oracle_step_time(B, C_sample, E, steps, warmup, threads):
     return sum(times) / len(times)
 
 
+def reference_cpu_steps(B, C, E, sr, steps, warmup, threads):
+    """Per-step seconds of the reference's CPU path for one (B, C, sr) configuration at world size 1: the UNMODIFIED
+    ``partial_fc.PartialFC.forward_backward`` (baseline/_ref, copied by build() from /root/reference) when it is present,
+    else the oracle port.  Returns (times, kind)."""
+    from oracle import reference_runner as R
+    if R.available():
+        times, _ = R.time_steps("cpu", B, C, E, sr, S, M, steps, warmup, threads=threads)
+        return times, "reference"
+    Cs = int(C * sr) if sr < 1 else C
+    t = oracle_step_time(B, Cs, E, steps, warmup, threads)
+    return [t] * steps, "port"
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU path for the same metric/config (rank 0 only)."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores, same metric and
+    config (rank 0 only; the other ranks exit without work).  N = 1: the full configuration, every one of the --steps
+    timed.  N > 1: one rank's batch (B rows) of the B*N-row job against all classes -- the CPU cost is linear in rows, so
+    whole-job samples/s is the same number; the sample is stated in the line."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -149,16 +165,20 @@ def run_reference(args):
         raise SystemExit("--impl reference times the PartialFC path (c2/c3/c4); the FedAvg CPU baseline is the cpu_baseline of --workload c5")
     B, C, E, sr = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
-    C_sample = 131072                # bounded sample: ~1.5 s of host work per step
-    t = oracle_step_time(B, C_sample, E, args.steps, args.warmup, threads)
-    scale = (C * (sr if sr < 1 else 1.0)) / C_sample
-    ms_full = t * scale * 1e3
-    val = B * args.gpus / (ms_full / 1e3) if args.gpus == 1 else B / (ms_full / 1e3)
-    cpu = {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-           "sample": f"oracle port of PartialFC.forward_backward, B={B}, {C_sample} of {C} classes per step, time scaled x{scale:.2f} (cost is linear in classes)"}
+    times, kind = reference_cpu_steps(B, C, E, sr, args.steps, args.warmup, threads)
+    t = sum(times) / len(times)
+    ms = t * 1e3
+    val = B / t
+    what = "unmodified partial_fc.PartialFC.forward_backward + losses.CosFace (baseline/_ref) on CPU, gloo world size 1" if kind == "reference" \
+        else "oracle port of PartialFC.forward_backward (the reference files are not on this box)"
+    sample = f"{what}; B={B}, all {C} classes, sample_rate={sr}, every step at full size"
+    if args.gpus > 1:
+        sample += f"; one rank's {B} rows of the {B * args.gpus}-row global batch per step (cost is linear in rows: same samples/s)"
+    cpu = {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample}
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_full, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: PartialFC CosFace fwd+bwd, B={B}/GPU, {C} classes, E={E}, sample_rate={sr}, s={S}, m={M}"},
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: class-sharded PartialFC CosFace fwd+bwd, B={B}/GPU, {C} classes over {args.gpus} GPU(s), E={E}, "
+                                   f"sample_rate={sr}, s={S}, m={M}"},
             "cpu_baseline": cpu, "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
 
@@ -199,8 +219,9 @@ def iresnet50_shapes():
 
 def run_fedavg(args):
     """--workload c5: server.py FedPavg over 40 client state_dicts (iresnet50 + transformation layer), BASELINE configs[4].
-    value = algorithmic GB/s ((K+1) * N * 4 bytes per call) with the dicts resident in HBM; clients are sharded over the
-    ranks (K/W each) and the partial sums meet in one all-reduce."""
+    value = algorithmic GB/s ((K+1) * N * 4 bytes per call) of the public ``FedPavg`` call with the clients resident in HBM as
+    ``FlatStateDict``s (one flat buffer per client, ``fedfr_b200.flatten_state_dict``); the plain dict-of-477-tensors call is
+    timed beside it.  Clients are sharded over the ranks (K/W each) and the partial sums meet in one all-reduce."""
     import torch
     import torch.distributed as dist
     import __graft_entry__ as G
@@ -219,36 +240,47 @@ def run_fedavg(args):
     mine = list(range(rank, K, world))
     torch.manual_seed(100)
     base = {n: (torch.randn(sh, device=dev) if f else torch.zeros(sh, dtype=torch.int64, device=dev)) for n, sh, f in shapes}
-    models = [{n: (v + 0.01 * torch.randn_like(v)) if v.dtype == torch.float32 else v + i for n, v in base.items()} for i in mine]
+    gens = {i: torch.Generator(device=dev).manual_seed(1000 + i) for i in mine}          # client i is the same tensor on any rank layout
+    models = [{n: (v + 0.01 * torch.randn(v.shape, device=dev, generator=gens[i])) if v.dtype == torch.float32 else v + i for n, v in base.items()}
+              for i in mine]
+    flats = [fedfr_b200.flatten_state_dict(m) for m in models]
     weights = [6000 + 37 * i for i in mine]
     n_elem = sum(v.numel() for v in base.values())
     alg_bytes = (K + 1) * n_elem * 4.0
 
-    def step():
+    def call(clients):
         if world == 1:
-            return fedfr_b200.FedPavg(models, weights)
-        return fedfr_b200.FedPavg_sharded(models, weights)
+            return fedfr_b200.FedPavg(clients, weights)
+        return fedfr_b200.FedPavg_sharded(clients, weights)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
     for _ in range(max(args.warmup, 3)):
-        step()
+        call(flats)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     from fedfr_b200 import _native as N
     l0 = N.lib.pfc_launch_count()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / args.steps
+    ms = timed(lambda: call(flats), args.steps)
     launches = N.lib.pfc_launch_count() - l0
     # the C-ABI call alone (table upload + the one kernel), re-launched from the tables the last call staged
     from fedfr_b200 import fedavg as FA
@@ -261,56 +293,120 @@ def run_fedavg(args):
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / args.steps
     clocks = sampler.stop() if sampler else None
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t)
-    # end to end: the dicts start in pinned HOST memory (where FedFR keeps them, client.py:469), result read back
-    e2e_ms = None
+    for _ in range(2):
+        call(models)
+    ms_dict = timed(lambda: call(models), max(args.steps // 2, 2))
+
+    # parity (driver-visible: exit 3 on failure): W = 1 bit-exact against the reference's own loop order in torch fp32 on the
+    # device (mul, then add, client order; 0 + first term) and flat == dict path; W > 1 against an fp64 sum, 1e-6, same bits on all ranks
+    out = call(flats)
+    out_d = call(models)
+    names = [n for n, _, _ in shapes]
+    probe = [max(names, key=lambda n: base[n].numel()), "conv1.weight", "bn1.num_batches_tracked", "converter.weight", "features.running_var"]
+    tot_w = float(sum(6000 + 37 * i for i in range(K)))
+    parity = {"keys_checked": probe, "world": world}
+    ok = all(out[n].dtype == torch.float32 for n in names)
     if world == 1:
-        host_models = [{n: v.cpu().pin_memory() for n, v in m.items()} for m in models[:8]]      # bounded: 8 of the 40 clients
-        fedfr_b200.FedPavg(host_models, weights[:8])
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        o = fedfr_b200.FedPavg(host_models, weights[:8])
-        _ = {n: v.cpu() for n, v in o.items()}
-        e2e_ms = (time.perf_counter() - t0) * 1e3
+        wn = [w / tot_w for w in weights]
+        exact = True
+        for n in probe:
+            ref = 0
+            for wi, m in zip(wn, models):
+                ref = ref + wi * m[n]                         # python_float * tensor, then add: server.py:31-32
+            exact = exact and bool(torch.equal(out[n], ref)) and bool(torch.equal(out_d[n], ref))
+        parity["bit_exact_vs_reference_order"] = exact
+        ok = ok and exact
+    else:
+        worst = 0.0
+        same = True
+        for n in probe:
+            part = torch.zeros_like(base[n], dtype=torch.float64)
+            for i, m in zip(mine, models):
+                part += ((6000 + 37 * i) / tot_w) * m[n].double()
+            dist.all_reduce(part)
+            worst = max(worst, float((out[n].double() - part).norm() / part.norm().clamp_min(1e-30)))
+            g = [torch.empty_like(out[n]) for _ in range(world)]
+            dist.all_gather(g, out[n].contiguous())
+            same = same and all(bool(torch.equal(g[0], t)) for t in g)
+        parity["max_rel_err_vs_fp64"] = worst
+        parity["identical_on_all_ranks"] = same
+        ok = ok and worst < 1e-6 and same
+    if world > 1:
+        flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item() > 0)
+    parity["ok_all_ranks"] = ok
+    del out, out_d
+
+    # end to end: every client starts as a FlatStateDict in pinned HOST memory (where FedFR keeps the uploads, client.py:469),
+    # one H2D copy per client buffer, result read back to the host; all K/W clients of this rank, K in total
+    host_flats = [fedfr_b200.flatten_state_dict(m, device="cpu", pin_memory=True) for m in models]
+    torch.cuda.synchronize()
+
+    def e2e_call():
+        o = call(host_flats)
+        return o.flat_f32.cpu() if hasattr(o, "flat_f32") else {n: v.cpu() for n, v in o.items()}
+
+    e2e_call()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e2e_call()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t)
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
+        if not ok:
+            sys.exit(3)
         return
     peaks = load_peaks()
     gbs = alg_bytes / (ms * 1e-3) / 1e9
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import partial_fc_oracle as O
+        from oracle import reference_runner as R
         torch.set_num_threads(os.cpu_count() or 1)
-        cm = [{n: v.cpu().numpy() for n, v in m.items()} for m in models[:8]]
+        n_cpu = 8
+        cm = [{n: v.cpu() for n, v in m.items()} for m in models[:n_cpu]]
+        try:
+            ref_fedpavg, _ = R.load_server_functions()
+            kind, what = "reference", "unmodified server.FedPavg (baseline/_ref/server.py:25-34) on CPU tensors"
+        except FileNotFoundError:
+            from oracle import partial_fc_oracle as O
+            ref_fedpavg, kind, what = (lambda ms_, ws_: O.fedpavg([{n: v.numpy() for n, v in m.items()} for m in ms_], ws_)), "port", "oracle port of server.FedPavg"
         t0 = time.perf_counter()
-        O.fedpavg(cm, weights[:8])
+        ref_fedpavg(cm, weights[:n_cpu])
         t = time.perf_counter() - t0
-        cpu = {"value": 9 * n_elem * 4.0 / t / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
-               "sample": "oracle port of server.FedPavg (numpy, sequential fp32 mul+add), 8 of the 40 clients"}
+        cpu = {"value": (n_cpu + 1) * n_elem * 4.0 / t / 1e9, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": kind,
+               "sample": f"{what}, {n_cpu} of the {K} clients (incl. its deepcopy of client 0)"}
     line = {"metric": "FedPavg weighted average, algorithmic GB/s ((K+1)*N*4 bytes)", "value": gbs, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"c5: FedPavg of {K} client state_dicts (iresnet50 475 tensors + transformation layer, {n_elem} elements each), "
-                                   f"clients sharded over {world} GPU(s)", "l2": "inputs larger than L2 (7 GB of client tensors)"},
-            "e2e": None if e2e_ms is None else {"value": 9 * n_elem * 4.0 / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_ms,
-                                                "h2d_bytes_per_step": 8 * n_elem * 4, "d2h_bytes_per_step": n_elem * 4,
-                                                "sample": "8 of the 40 clients from pinned host memory, result copied back"},
+            "config": {"workload": f"c5: FedPavg of {K} client state_dicts (iresnet50 475 tensors + transformation layer, {n_elem} elements each) held as "
+                                   f"FlatStateDicts, clients sharded over {world} GPU(s)" + (", one all-reduce of the flat partial sum" if world > 1 else ""),
+                       "l2": "inputs larger than L2 (7 GB of client tensors)"},
+            "e2e": {"value": alg_bytes / e2e_s / 1e9, "unit": "GB/s", "ms_per_step": e2e_s * 1e3,
+                    "h2d_bytes_per_step": len(mine) * n_elem * 4, "d2h_bytes_per_step": n_elem * 4,
+                    "sample": f"all {K} clients from pinned host memory ({len(mine)} per rank, one H2D copy per client buffer), result copied back"},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "fedavg_kernel (fedavg_weighted_sum call: table upload + one launch)",
                          "achieved": (len(mine) + 1) * n_elem * 4.0 / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": (len(mine) + 1) * n_elem * 4.0 / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
-                         "ms_per_launch": kernel_ms, "peak_source": peaks["source"] + " copy bandwidth",
-                         "note": "value is the whole FedPavg(state_dicts) call, bound by per-tensor Python work over K x 477 tensors"},
-            "cpu_baseline": cpu}
+                         "ms_per_launch": kernel_ms, "peak_source": peaks["source"] + " copy bandwidth"},
+            "cpu_baseline": cpu, "parity": parity,
+            "extras": {"dict_of_tensors_call_ms": ms_dict, "dict_of_tensors_call_gbs": alg_bytes / (ms_dict * 1e-3) / 1e9,
+                       "note": "same call on plain state_dicts (K x 477 tensors): bound by per-tensor Python work"}}
     emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not ok:
+        sys.exit(3)
 
 
 def run_ours(args):
@@ -442,6 +538,20 @@ def run_ours(args):
         step_e2e_lagged()
     ms_e2e_lagged = timed(step_e2e_lagged, args.steps) / args.steps
 
+    # parity of this very configuration, on every rank (driver-visible: a failure makes the run exit 3): one more step,
+    # checked against a chunked device-side restatement of partial_fc.py:127-174 (fedfr_b200/selfcheck.py) -- the
+    # reference's fp32 arithmetic at 1e-2, the bf16-operand emulation row by row (max 6e-3, rms 1e-3), identical loss bits on all ranks
+    parity = None
+    if not args.no_parity:
+        from fedfr_b200 import selfcheck
+        head.sub_weight.grad = None
+        xg_c, loss_c = head.forward_backward(label, feats, opt)
+        parity = selfcheck.check_head_step(head, label, feats, xg_c, loss_c, **({} if head._ops.bwd_mode == "prob" else {"tol_rows": 2e-2, "tol_rows_rms": 1e-2}))
+        del xg_c, loss_c
+        torch.cuda.empty_cache()
+        if not parity["ok_all_ranks"]:
+            sys.stderr.write(f"[bench] PARITY FAILURE on rank {rank}: {json.dumps(parity)}\n")
+
     # the step either side of the path (reported separately): optimizer.step() + update(), torch vs fused
     def opt_time(fn, n=5):
         torch.cuda.synchronize()
@@ -505,6 +615,19 @@ def run_ours(args):
         except Exception as e:       # noqa: BLE001
             extras["torch_eager_error"] = repr(e)
 
+    # the UNMODIFIED reference class on this same B200 in fp32 (real constructor, nccl group of one rank): context row
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import reference_runner as R
+            if R.available():
+                torch.cuda.empty_cache()
+                tr, _ = R.time_steps(f"cuda:{local_rank}", B, C, E, sr, S, M, 3, 2)
+                extras["reference_on_b200_ms"] = 1e3 * sum(tr) / len(tr)
+                extras["reference_on_b200_note"] = "unmodified partial_fc.PartialFC.forward_backward (baseline/_ref), fp32, same GPU, wall clock around synchronised steps"
+                torch.cuda.empty_cache()
+        except Exception as e:       # noqa: BLE001
+            extras["reference_on_b200_error"] = repr(e)
+
     # per-phase device times (events on the launch stream inside the library) for the roofline of the dominant kernel
     import ctypes as CT
     N.lib.pfc_profile_enable(1)
@@ -526,6 +649,8 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
+        if parity is not None and not parity["ok_all_ranks"]:
+            sys.exit(3)
         return
 
     peaks = load_peaks()
@@ -562,11 +687,11 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        C_sample = min(262144, Cs)                       # bounded sample: ~10 s of host work (cost is linear in classes)
-        t = oracle_step_time(B, C_sample, E, 4, 1, threads)
-        scale = Cs / C_sample
-        cpu = {"value": B / (t * scale), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"oracle port, B={B}, {C_sample} of {Cs} classes, 4 steps after 1 warm-up, time scaled x{scale:.2f}"}
+        times, kind = reference_cpu_steps(B, C, E, sr, 2, 1, threads)        # bounded sample: two full-size steps after one warm-up
+        t = sum(times) / len(times)
+        cpu = {"value": B / t, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
+               "sample": ("unmodified partial_fc.PartialFC.forward_backward (baseline/_ref) on CPU" if kind == "reference" else "oracle port") +
+                         f", B={B}, all {C} classes, sample_rate={sr}, 2 full-size steps after 1 warm-up"}
 
     line = {"metric": METRIC, "value": Bt / (ms_step * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -577,11 +702,13 @@ def run_ours(args):
                     "ms_per_step": ms_e2e, "readback": "synchronous: the host waits for x_grad and the loss of every step before starting the next",
                     "lagged_readback": {"value": Bt / (ms_e2e_lagged * 1e-3), "ms_per_step": ms_e2e_lagged,
                                         "note": "same copies; step n is read back while step n+1 is already enqueued"}},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extras": extras}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity, "extras": extras}
     emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity["ok_all_ranks"]:
+        sys.exit(3)
 
 
 def main():
@@ -596,6 +723,7 @@ def main():
     ap.add_argument("--dx-cluster", type=int, default=0)
     ap.add_argument("--dw-cluster", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-timing parity self-check (developer runs under ncu)")
     ap.add_argument("--graph", type=int, default=-1, help="1/0: replay the backward as a cached CUDA graph (library default: 1)")
     ap.add_argument("--pipe", default="", help="backward chain pipeline: 'on,smG,smDx,smDw,ring' (e.g. 1,56,32,60,3) or 0")
     ap.add_argument("--fwd-overlap", default="", help="fused forward: 'chunks,normalize_blocks_per_sm' (e.g. 6,2)")

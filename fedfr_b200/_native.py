@@ -14,6 +14,7 @@ PATH_TENSOR = 0
 PATH_CHECK = 1
 FEDAVG_F32 = 0
 FEDAVG_I64 = 1
+FEDAVG_KEEP_FIRST_TERM = 0x100
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -46,11 +47,13 @@ SIGNATURES = {
     "pfc_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _i32, _f32, _vp, _vp, _i32, _vp, _sz, _i32, _vp]),
     "pfc_prob_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "pfc_normalize_fwd_prob": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pfc_set_range_flag": (_i32, [_vp, _f32]),
     "pfc_bwd_prob_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "pfc_bwd_prob": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _i32, _f32, _vp, _vp, _i32, _vp, _sz, _vp, _sz, _vp]),
     "pfc_spreadout_workspace_bytes": (_sz, [_i64, _i32]),
     "pfc_spreadout": (_i32, [_vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pfc_cosface_dense": (_i32, [_vp, _vp, _i64, _i64, _f32, _f32, _vp, _vp]),
+    "pfc_arcface_dense": (_i32, [_vp, _vp, _i64, _i64, _f32, _f32, _vp]),
     "pfc_bce_head_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pfc_bce_head_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _vp]),
     "pfc_similar_columns": (_i32, [_vp, _i64, _vp, _i64, _i32, _f32, _vp, _vp]),

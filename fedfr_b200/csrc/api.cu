@@ -32,6 +32,7 @@ void tc_set_clusters(int dx_cs, int dw_cs);
 void tc_set_debug(long long* p);
 void tc_set_logits_pair(int on);
 void tc_set_graph(int on);
+int tc_set_range_flag(int* flag, float limit_nats);
 void tc_set_dx_pair(int on);
 void tc_set_prefetch(int logits, int dx, int dw);
 void tc_set_chunk_mb(int mb);
@@ -178,6 +179,11 @@ int pfc_set_debug_buffer(void* dev_ptr) {
   tc_set_debug(reinterpret_cast<long long*>(dev_ptr));
   return 0;
 }
+
+/* Range guard of the stored-probability path: `flag` = two ints in pinned host (or device) memory, or NULL to disable.
+ * flag[0] is set when s |x_i| of a row exceeds `limit_nats` (or is not finite) in pfc_normalize_fwd_prob, flag[1] when a
+ * row sum is 0 / non-finite in pfc_bwd_prob.  Sticky; applies to the calling thread's current device. */
+int pfc_set_range_flag(int* flag, float limit_nats) { return tc_set_range_flag(flag, limit_nats); }
 
 int pfc_set_graph(int on) {   /* 1 = replay the backward as a cached CUDA graph (default), 0 = launch kernel by kernel */
   tc_set_graph(on);

@@ -22,15 +22,22 @@ struct FedavgTable {          // device-side view of the segment table
 
 constexpr int kFedThreads = 256;
 constexpr int kFedVecPerBlock = kFedThreads;          // one float4 per thread per block
-constexpr int kFedMaxK = 64;
+constexpr int kFedMaxK = 64;                          // clients per launch; more clients = more launches, same sum
+constexpr int kFedUnaligned = 0x200;                 // internal flag in the dtype code: take the scalar path
+
+// How the chain of a segment starts (the reference has both):
+//   START_ZERO  FedPavg, server.py:30-32:       tmp = 0; tmp += w_0 x_0  ->  0.0f + t_0   (so -0.0 becomes +0.0)
+//   START_TERM  FedAvg_on_FC, server.py:38:     aggr = x_0 * w_0          ->  t_0          (sign of zero kept)
+//   START_OUT   clients 64.. of a K > 64 call:  the running sum of the previous launch, re-read from `out` (exact)
+enum { START_ZERO = 0, START_TERM = 1, START_OUT = 2 };
 
 template <int kUnroll>
 __device__ __forceinline__ void fedavg_f32_vec(const void* const* __restrict__ src, const float* __restrict__ w, int K, int64_t v,
-                                               float4* __restrict__ out) {
-  float4 acc;
-  int i = 0;
-  bool first = true;
-  for (; i < K; i += kUnroll) {
+                                               float4* __restrict__ out, int start) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (start == START_OUT) acc = out[v];
+  bool first = start == START_TERM;
+  for (int i = 0; i < K; i += kUnroll) {
     float4 x[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u)
@@ -48,10 +55,23 @@ __device__ __forceinline__ void fedavg_f32_vec(const void* const* __restrict__ s
   st_stream_f4(out + v, acc);
 }
 
-__global__ void __launch_bounds__(kFedThreads) fedavg_kernel(FedavgTable tb, int n_seg, int K, int64_t total_blocks) {
+template <class T>
+__device__ __forceinline__ float fedavg_scalar(const void* const* __restrict__ src, const float* __restrict__ w, int K, int64_t e, float prev, int start) {
+  float acc = start == START_OUT ? prev : 0.f;
+  bool first = start == START_TERM;
+  for (int i = 0; i < K; ++i) {
+    const float t = __fmul_rn(w[i], (float)reinterpret_cast<const T*>(src[i])[e]);
+    if (first) { acc = t; first = false; }
+    else acc = __fadd_rn(acc, t);
+  }
+  return acc;
+}
+
+// clients [k0, k0 + K) of a table whose rows hold k_total pointers
+__global__ void __launch_bounds__(kFedThreads) fedavg_kernel(FedavgTable tb, int n_seg, int k_total, int k0, int K, int64_t total_blocks) {
   __shared__ float sw[kFedMaxK];
   __shared__ const void* sptr[kFedMaxK];
-  if (threadIdx.x < K) sw[threadIdx.x] = tb.w[threadIdx.x];
+  if (threadIdx.x < K) sw[threadIdx.x] = tb.w[k0 + threadIdx.x];
   int cur_seg = -1;
   for (int64_t b = blockIdx.x; b < total_blocks; b += gridDim.x) {
     // locate the segment of block b (binary search over blk_start)
@@ -63,38 +83,32 @@ __global__ void __launch_bounds__(kFedThreads) fedavg_kernel(FedavgTable tb, int
     const int seg = lo;
     __syncthreads();
     if (seg != cur_seg) {
-      if (threadIdx.x < K) sptr[threadIdx.x] = tb.src[(int64_t)seg * K + threadIdx.x];
+      if (threadIdx.x < K) sptr[threadIdx.x] = tb.src[(int64_t)seg * k_total + k0 + threadIdx.x];
       cur_seg = seg;
     }
     __syncthreads();
     const int64_t n = tb.len[seg];
     const int64_t local_blk = b - tb.blk_start[seg];
     float* out = tb.out[seg];
-    if (tb.dtype[seg] == FEDAVG_F32) {
+    const int code = tb.dtype[seg];
+    const int start = k0 > 0 ? START_OUT : ((code & FEDAVG_KEEP_FIRST_TERM) ? START_TERM : START_ZERO);
+    if ((code & 0xff) == FEDAVG_F32) {
       const int64_t n_vec = n >> 2;
       const int64_t v = local_blk * kFedVecPerBlock + threadIdx.x;
-      const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;   // sources checked on the host
-      if (aligned && v < n_vec) fedavg_f32_vec<8>(sptr, sw, K, v, reinterpret_cast<float4*>(out));
+      const bool aligned = !(code & kFedUnaligned);          // out and every source 16-byte aligned (checked on the host)
+      if (aligned && v < n_vec) fedavg_f32_vec<8>(sptr, sw, K, v, reinterpret_cast<float4*>(out), start);
       // scalar tail (and the unaligned fallback): elements [n_vec*4, n) of the segment, done by its last block
       const int64_t tail0 = aligned ? (n_vec << 2) : 0;
       const bool last_blk = (b + 1 == tb.blk_start[seg + 1]);
       if (!aligned || last_blk) {
         const int64_t e0 = aligned ? tail0 + threadIdx.x : local_blk * kFedVecPerBlock * 4 + threadIdx.x;
         const int64_t e1 = aligned ? n : min(n, (local_blk + 1) * (int64_t)kFedVecPerBlock * 4);
-        for (int64_t e = e0; e < e1; e += kFedThreads) {
-          float acc = __fmul_rn(sw[0], reinterpret_cast<const float*>(sptr[0])[e]);
-          for (int i = 1; i < K; ++i) acc = __fadd_rn(acc, __fmul_rn(sw[i], reinterpret_cast<const float*>(sptr[i])[e]));
-          out[e] = acc;
-        }
+        for (int64_t e = e0; e < e1; e += kFedThreads) out[e] = fedavg_scalar<float>(sptr, sw, K, e, start == START_OUT ? out[e] : 0.f, start);
       }
     } else {  // FEDAVG_I64: python_float * int64_tensor promotes to fp32 (server.py:32)
       const int64_t e0 = local_blk * kFedVecPerBlock * 4 + threadIdx.x;
       const int64_t e1 = min(n, (local_blk + 1) * (int64_t)kFedVecPerBlock * 4);
-      for (int64_t e = e0; e < e1; e += kFedThreads) {
-        float acc = __fmul_rn(sw[0], (float)reinterpret_cast<const long long*>(sptr[0])[e]);
-        for (int i = 1; i < K; ++i) acc = __fadd_rn(acc, __fmul_rn(sw[i], (float)reinterpret_cast<const long long*>(sptr[i])[e]));
-        out[e] = acc;
-      }
+      for (int64_t e = e0; e < e1; e += kFedThreads) out[e] = fedavg_scalar<long long>(sptr, sw, K, e, start == START_OUT ? out[e] : 0.f, start);
     }
   }
 }
@@ -123,26 +137,38 @@ int fedavg_weighted_sum(const void* const* seg_src_host, void* const* seg_out_ho
                         int n_seg, const float* weights_host, int K, void* table_dev, size_t table_bytes, void* stream) {
   if (int rc = require_sm100()) return rc;
   PFC_REQUIRE(seg_src_host && seg_out_host && seg_len_host && seg_dtype_host && weights_host && table_dev, PFC_E_ARG, "fedavg_weighted_sum: null argument");
-  PFC_REQUIRE(n_seg > 0 && K > 0 && K <= kFedMaxK, PFC_E_SHAPE, "fedavg_weighted_sum: need 1 <= K <= %d clients (got %d) and n_seg > 0", kFedMaxK, K);
+  PFC_REQUIRE(n_seg > 0 && K > 0, PFC_E_SHAPE, "fedavg_weighted_sum: need K >= 1 clients (got %d) and n_seg > 0", K);
   PFC_REQUIRE(table_bytes >= fedavg_table_bytes(n_seg, K), PFC_E_WORKSPACE, "fedavg_weighted_sum: table buffer too small");
   cudaStream_t st = as_stream(stream);
-  // fp32 sources must be 16-byte aligned for the vector path (torch allocations are); verify on the host
-  for (int s = 0; s < n_seg; ++s) {
-    PFC_REQUIRE(seg_len_host[s] >= 0, PFC_E_ARG, "fedavg_weighted_sum: negative segment length");
-    PFC_REQUIRE(seg_dtype_host[s] == FEDAVG_F32 || seg_dtype_host[s] == FEDAVG_I64, PFC_E_ARG, "fedavg_weighted_sum: unknown dtype code");
-    if (seg_dtype_host[s] == FEDAVG_F32)
-      for (int i = 0; i < K; ++i)
-        PFC_REQUIRE((reinterpret_cast<uintptr_t>(seg_src_host[(size_t)s * K + i]) & 15) == 0 || seg_len_host[s] < 4, PFC_E_ARG,
-                    "fedavg_weighted_sum: fp32 source %d of segment %d is not 16-byte aligned", i, s);
-  }
-  // block table (host, small): vector blocks cover 4*kFedVecPerBlock elements each
+  // host staging (pinned, reused by this thread): block table + dtype codes with the alignment flag
   static thread_local int64_t* blk_host = nullptr;
+  static thread_local int32_t* code_host = nullptr;
   static thread_local int blk_cap = 0;
   if (blk_cap < n_seg + 1) {
     if (blk_host) cudaFreeHost(blk_host);
+    if (code_host) cudaFreeHost(code_host);
+    blk_host = nullptr; code_host = nullptr; blk_cap = 0;
     PFC_CUDA(cudaMallocHost(&blk_host, sizeof(int64_t) * (size_t)(n_seg + 1)));
+    PFC_CUDA(cudaMallocHost(&code_host, sizeof(int32_t) * (size_t)(n_seg + 1)));
     blk_cap = n_seg + 1;
   }
+  // the 128-bit path needs 16-byte aligned pointers (whole torch allocations are; views at odd offsets are not): a segment
+  // with any unaligned source or output takes the scalar path instead
+  for (int s = 0; s < n_seg; ++s) {
+    PFC_REQUIRE(seg_len_host[s] >= 0, PFC_E_ARG, "fedavg_weighted_sum: negative segment length");
+    const int base = seg_dtype_host[s] & 0xff;
+    PFC_REQUIRE((base == FEDAVG_F32 || base == FEDAVG_I64) && (seg_dtype_host[s] & ~(0xff | FEDAVG_KEEP_FIRST_TERM)) == 0, PFC_E_ARG,
+                "fedavg_weighted_sum: unknown dtype code");
+    int code = seg_dtype_host[s];
+    if (base == FEDAVG_F32) {
+      bool ok = (reinterpret_cast<uintptr_t>(seg_out_host[s]) & 15) == 0;
+      for (int i = 0; i < K && ok; ++i) ok = (reinterpret_cast<uintptr_t>(seg_src_host[(size_t)s * K + i]) & 15) == 0;
+      PFC_REQUIRE((reinterpret_cast<uintptr_t>(seg_out_host[s]) & 3) == 0, PFC_E_ARG, "fedavg_weighted_sum: output %d is not 4-byte aligned", s);
+      if (!ok) code |= kFedUnaligned;
+    }
+    code_host[s] = code;
+  }
+  // block table (host, small): vector blocks cover 4*kFedVecPerBlock elements each
   int64_t total = 0;
   const int64_t per_blk = (int64_t)kFedVecPerBlock * 4;
   for (int s = 0; s < n_seg; ++s) {
@@ -164,7 +190,7 @@ int fedavg_weighted_sum(const void* const* seg_src_host, void* const* seg_out_ho
   PFC_CUDA(cudaMemcpyAsync(p, seg_len_host, (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
   p += align256((size_t)n_seg * 8);
   tb.dtype = reinterpret_cast<const int32_t*>(p);
-  PFC_CUDA(cudaMemcpyAsync(p, seg_dtype_host, (size_t)n_seg * 4, cudaMemcpyHostToDevice, st));
+  PFC_CUDA(cudaMemcpyAsync(p, code_host, (size_t)n_seg * 4, cudaMemcpyHostToDevice, st));
   p += align256((size_t)n_seg * 4);
   tb.blk_start = reinterpret_cast<const int64_t*>(p);
   PFC_CUDA(cudaMemcpyAsync(p, blk_host, (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -174,9 +200,12 @@ int fedavg_weighted_sum(const void* const* seg_src_host, void* const* seg_out_ho
   int64_t grid = total;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (grid > cap) grid = cap;
-  fedavg_kernel<<<(int)grid, kFedThreads, 0, st>>>(tb, n_seg, K, total);
-  PFC_LAUNCH_CHECK();
-  // blk_host is reused by the next call on this thread: make sure the copy above has been consumed
+  for (int k0 = 0; k0 < K; k0 += kFedMaxK) {               // K > 64: later launches continue the sums of the earlier ones (same order, same bits)
+    const int kc = K - k0 < kFedMaxK ? K - k0 : kFedMaxK;
+    fedavg_kernel<<<(int)grid, kFedThreads, 0, st>>>(tb, n_seg, K, k0, kc, total);
+    PFC_LAUNCH_CHECK();
+  }
+  // blk_host / code_host are reused by the next call on this thread: make sure the copies above have been consumed
   PFC_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

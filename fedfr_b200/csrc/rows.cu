@@ -60,6 +60,17 @@ __global__ void cosface_margin_kernel(float* cosine, const int64_t* label, int64
     if (y >= 0 && y < n_classes) cosine[i * n_classes + y] -= m;
   }
 }
+// losses.ArcFace.forward on materialised logits (losses.py:38-45), in place like the reference: acos_ over the whole matrix,
+// + m on the target column of rows with label != -1, cos_, mul_(s).  One pass; |cosine| > 1 gives NaN as in the reference.
+__global__ void arcface_dense_kernel(float* __restrict__ cosine, const int64_t* __restrict__ label, int64_t n_rows, int64_t n_classes, float s, float m) {
+  const int64_t n = n_rows * n_classes;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / n_classes, c = i - r * n_classes;
+    float th = acosf(cosine[i]);
+    if (label[r] == c) th += m;
+    cosine[i] = cosf(th) * s;
+  }
+}
 __global__ void scale_kernel(const float* __restrict__ in, float s, int64_t n, float* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i] * s;
 }
@@ -255,6 +266,18 @@ int pfc_cosface_dense(float* cosine, const int64_t* label, int64_t n_rows, int64
   int64_t blocks = (n + 255) / 256;
   if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
   scale_kernel<<<(int)blocks, 256, 0, st>>>(cosine, s, n, out);
+  PFC_LAUNCH_CHECK();
+  return 0;
+}
+
+int pfc_arcface_dense(float* cosine, const int64_t* label, int64_t n_rows, int64_t n_classes, float s, float m, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  PFC_REQUIRE(cosine && label && n_rows >= 0 && n_classes >= 0, PFC_E_ARG, "pfc_arcface_dense: bad argument");
+  if (n_rows == 0 || n_classes == 0) return 0;
+  int64_t n = n_rows * n_classes;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+  arcface_dense_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(cosine, label, n_rows, n_classes, s, m);
   PFC_LAUNCH_CHECK();
   return 0;
 }

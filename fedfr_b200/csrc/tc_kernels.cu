@@ -1430,8 +1430,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
 constexpr float kProbHeadroom = 58.f;      // log2 units: P <= 2^58, so a row sum over < 2^30 classes stays below 2^88
 
 // a_i = s2 |x_hat_i| (1 + 2^-7) - headroom.  |x.w_hat| <= |x| |w_hat| and bf16 rounding leaves |w_hat| <= 1 + 2^-8.
+// range guard (flag = pinned host or device memory, may be null): flag[0] = 1 when s |x_i| of some row leaves the exponent
+// window of the stored-probability path (or is not finite), flag[1] = 1 when a row sum came out 0 / non-finite in the
+// backward.  Sticky plain stores; the host polls them without synchronising (PartialFC switches to the recomputing backward).
 __global__ void __launch_bounds__(256) row_bound_kernel(const __nv_bfloat16* __restrict__ x, int64_t n_rows, int emb, float s2,
-                                                        float* __restrict__ bound) {
+                                                        float* __restrict__ bound, int* __restrict__ range_flag, float limit_log2) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n_rows) return;
@@ -1443,7 +1446,10 @@ __global__ void __launch_bounds__(256) row_bound_kernel(const __nv_bfloat16* __r
     ss = fmaf(a, a, fmaf(b, b, ss));
   }
   ss = warp_sum(ss);
-  if (lane == 0) bound[r] = s2 * sqrtf(ss) * 1.0078125f - kProbHeadroom;
+  if (lane == 0) {
+    bound[r] = s2 * sqrtf(ss) * 1.0078125f - kProbHeadroom;
+    if (range_flag && !(s2 * sqrtf(ss) <= limit_log2)) *reinterpret_cast<volatile int*>(range_flag) = 1;
+  }
 }
 
 // One warp per row: x_scaled_i = bf16(x_hat_i * scale_i), row_scale_i, and the target element of the row (if this
@@ -1453,7 +1459,7 @@ __global__ void __launch_bounds__(256) prob_prep_kernel(const __nv_bfloat16* __r
                                                         const float* __restrict__ row_sum, const float* __restrict__ row_bound,
                                                         const float* __restrict__ target_cos, int64_t n_rows, int emb, int n_rb, int64_t n_classes,
                                                         float s, float m, int margin_kind, float g_scale, __nv_bfloat16* __restrict__ x_scaled,
-                                                        float* __restrict__ row_scale, __nv_bfloat16* __restrict__ scratch) {
+                                                        float* __restrict__ row_scale, __nv_bfloat16* __restrict__ scratch, int* __restrict__ range_flag) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n_rows) return;
@@ -1467,6 +1473,7 @@ __global__ void __launch_bounds__(256) prob_prep_kernel(const __nv_bfloat16* __r
   }
   if (lane == 0) {
     row_scale[r] = sc;
+    if (range_flag && sc == 0.f) *reinterpret_cast<volatile int*>(range_flag + 1) = 1;
     const int64_t y = label[r];
     if (y >= 0 && y < n_classes) {
       const float c = target_cos[r];
@@ -1666,6 +1673,13 @@ size_t tc_bwd_workspace_bytes(int64_t n_rows, int64_t n_classes, int emb) {
   return pl.g_bytes + pl.dxp_bytes + 1024;
 }
 
+static int* g_range_flag[64];                       // per device: range-guard flag of the stored-probability path (tc_set_range_flag)
+static float g_range_limit_nats = 80.f;
+static int* range_flag_of_current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  return g_range_flag[dev];
+}
 static int g_prefetch[3] = {0, 0, 0};               // TMA L2 prefetch knobs: logits (0/1), dx (k-block distance), dw (0/1); measured slower, off
 static long long* g_dbg = nullptr;                   // developer instrumentation buffer (device), see pfc_set_debug_buffer
 static int g_dx_cluster = 2, g_dw_cluster = 2;      // cluster sizes (1, 2 or 4); tuning knobs
@@ -1915,7 +1929,7 @@ static int tc_bwd_enqueue(const void* x, const void* w_hat, const float* inv_nor
 // launches, tensor-map encodes and attribute calls, and the concurrent branches (normalise || logits, dx || dw) become
 // graph branches.  Entries are keyed on every argument and tuning knob; another pointer set captures another graph (LRU).
 struct GraphEntry {
-  unsigned char key[256];
+  unsigned char key[384];
   size_t key_len = 0;
   cudaGraphExec_t exec = nullptr;
   long long launches = 0;
@@ -1929,11 +1943,13 @@ static cudaStream_t g_capture_stream[64];
 static std::mutex g_graph_mutex;
 
 struct KeyBuilder {
-  unsigned char buf[256];
+  unsigned char buf[384];
   size_t len = 0;
   KeyBuilder() { memset(buf, 0, sizeof(buf)); }
+  bool overflow = false;      // a key that does not fit must never alias another one: the caller then launches un-captured
   template <class T> KeyBuilder& add(const T& v) {
     if (len + sizeof(T) <= sizeof(buf)) { memcpy(buf + len, &v, sizeof(T)); len += sizeof(T); }
+    else overflow = true;
     return *this;
   }
 };
@@ -1997,6 +2013,7 @@ int tc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64_
       .add(workspace_bytes).add(emb).add(accumulate_dw).add(s).add(m).add(margin_kind).add(inv_total_batch).add(g_fwd_bn).add(g_logits_pair)
       .add(g_dx_cluster).add(g_dw_cluster).add(make_bwd_plan(n_rows, n_classes, emb).chunk).add(g_pipe).add(g_ring).add(g_split[0])
       .add(g_split[1]).add(g_split[2]).add(g_prefetch[0]).add(g_prefetch[1]).add(g_prefetch[2]).add(g_dx_pair);
+  if (kb.overflow) return enqueue(st);
   return run_cached_graph(kb, st, enqueue);
 }
 
@@ -2056,7 +2073,8 @@ static int tc_normalize_fwd_enqueue(const float* w, const int64_t* index, const 
     target_cos = reinterpret_cast<float*>(prob_ws + L.off_tcos);
     const uint64_t g_rows = (uint64_t)(L.c_pad / 64) * L.n_rb * BM;                        // blocked scratch viewed as [g_rows, 64]
     if (int rc = make_tmap_bf16_2d(&tg, prob_ws, g_rows, 64, 64, 32)) return rc;            // epilogue store boxes [32 rows x 64 classes]
-    row_bound_kernel<<<(int)((n_rows + 7) / 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n_rows, emb, s * kLog2e, row_bound);
+    row_bound_kernel<<<(int)((n_rows + 7) / 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n_rows, emb, s * kLog2e, row_bound,
+                                                              range_flag_of_current_device(), g_range_limit_nats * kLog2e);
     PFC_LAUNCH_CHECK();
   }
   auto chunk_len = [&](int64_t c0) { return (n_classes - c0 < chunk) ? n_classes - c0 : chunk; };
@@ -2107,6 +2125,7 @@ int tc_normalize_fwd(const float* w, const int64_t* index, const void* x, const 
   KeyBuilder kb;
   kb.add(2).add(w).add(index).add(x).add(label).add(n_rows).add(n_classes).add(emb).add(s).add(m).add(margin_kind).add(w_hat).add(inv_norm).add(part_max)
       .add(part_sum).add(target_logit).add(g_fwd_bn).add(g_logits_pair).add(g_fwd_chunks).add(g_norm_blocks_per_sm).add(g_prefetch[0]);
+  if (kb.overflow) return enqueue(st);
   return run_cached_graph(kb, st, enqueue);
 }
 
@@ -2124,7 +2143,9 @@ int tc_normalize_fwd_prob(const float* w, const int64_t* index, const void* x, c
   if (!graph_eligible(st)) return enqueue(st);
   KeyBuilder kb;
   kb.add(3).add(w).add(index).add(x).add(label).add(n_rows).add(n_classes).add(emb).add(s).add(m).add(margin_kind).add(w_hat).add(inv_norm).add(part_max)
-      .add(part_sum).add(target_logit).add(prob_ws).add(g_fwd_bn).add(g_logits_pair).add(g_fwd_chunks).add(g_norm_blocks_per_sm).add(g_prefetch[0]);
+      .add(part_sum).add(target_logit).add(prob_ws).add(g_fwd_bn).add(g_logits_pair).add(g_fwd_chunks).add(g_norm_blocks_per_sm).add(g_prefetch[0])
+      .add(range_flag_of_current_device()).add(g_range_limit_nats);
+  if (kb.overflow) return enqueue(st);
   return run_cached_graph(kb, st, enqueue);
 }
 
@@ -2199,7 +2220,8 @@ static int tc_bwd_prob_enqueue(const void* w_hat, const float* inv_norm, const i
   // (1) per-row prep: scaled x_hat, row scales, target elements of the scratch
   prof_begin(PH_GRAD, st);
   prob_prep_kernel<<<(int)((n_rows + 7) / 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), label, row_sum, row_bound, target_cos, n_rows, emb,
-                                                            n_rb, n_classes, s, m, margin_kind, g_scale, xs, row_scale, scratch);
+                                                            n_rb, n_classes, s, m, margin_kind, g_scale, xs, row_scale, scratch,
+                                                            range_flag_of_current_device());
   PFC_LAUNCH_CHECK();
   prof_end(PH_GRAD, st);
 
@@ -2279,7 +2301,9 @@ int tc_bwd_prob(const void* x, const void* w_hat, const float* inv_norm, const i
   KeyBuilder kb;
   kb.add(4).add(x).add(w_hat).add(inv_norm).add(label).add(row_sum).add(dx).add(dw).add(workspace).add(prob_ws).add(n_rows).add(n_classes)
       .add(workspace_bytes).add(emb).add(accumulate_dw).add(s).add(m).add(margin_kind).add(inv_total_batch).add(g_logits_pair).add(g_dx_cluster)
-      .add(g_dw_cluster).add(g_prob_dx_sms).add(g_prob_dw_rate).add(g_sweep_lead).add(g_prefetch[1]).add(g_prefetch[2]).add(g_dx_pair);
+      .add(g_dw_cluster).add(g_prob_dx_sms).add(g_prob_dw_rate).add(g_sweep_lead).add(g_prefetch[1]).add(g_prefetch[2]).add(g_dx_pair)
+      .add(range_flag_of_current_device());
+  if (kb.overflow) return enqueue(st);
   return run_cached_graph(kb, st, enqueue);
 }
 
@@ -2373,6 +2397,14 @@ void tc_set_fwd_overlap(int chunks, int norm_blocks_per_sm) {
   if (norm_blocks_per_sm >= 1 && norm_blocks_per_sm <= 8) g_norm_blocks_per_sm = norm_blocks_per_sm;
 }
 
+int tc_set_range_flag(int* flag, float limit_nats) {
+  int dev = 0;
+  PFC_CUDA(cudaGetDevice(&dev));
+  PFC_REQUIRE(dev >= 0 && dev < 64, PFC_E_ARG, "device index out of range");
+  g_range_flag[dev] = flag;
+  if (limit_nats > 0.f) g_range_limit_nats = limit_nats;
+  return 0;
+}
 void tc_set_graph(int on) { g_use_graph = on ? 1 : 0; }
 void tc_set_dx_pair(int on) { g_dx_pair = on ? 1 : 0; }
 void tc_set_prefetch(int logits, int dx, int dw) { g_prefetch[0] = logits; g_prefetch[1] = dx; g_prefetch[2] = dw; }

@@ -16,6 +16,7 @@ import torch
 from .losses import margin_params
 
 _OPS = {}
+_PROB_MAX_S = 80.0      # ops_cuda.RANGE_LIMIT_NATS: beyond it the head uses the recomputing backward (no domain limit)
 
 
 def _ops_for(device, check_mode):
@@ -37,11 +38,13 @@ class _MarginCrossEntropy(torch.autograd.Function):
         x32 = x.detach().to(torch.float32)
         norm = x32.norm(dim=1, keepdim=True).clamp_min(1e-12)            # F.normalize(x), client.py:70
         x_unit = x32 / norm
-        w = weight.detach()
+        w = weight.detach().to(torch.float32).contiguous()             # the kernels read raw fp32 [C, E] rows (AMP casts, sliced fc views)
         label = label.to(torch.int64).contiguous()
         x_hat = ops.cast_features(x_unit.contiguous())
+        # the features are unit vectors here, so the stored-probability window (s |x| <= 80 nats) is a condition on s alone
+        mode = "recompute" if s > _PROB_MAX_S else None
         if hasattr(ops, "normalize_fwd_stats"):
-            w_hat, inv_norm, stats = ops.normalize_fwd_stats(w, x_hat, label, s, m, kind)
+            w_hat, inv_norm, stats = ops.normalize_fwd_stats(w, x_hat, label, s, m, kind, **({"bwd_mode": mode} if mode else {}))
         else:
             w_hat, inv_norm = ops.normalize(w)
             stats = ops.fwd_stats(x_hat, w_hat, label, s, m, kind)
@@ -81,10 +84,19 @@ class _MarginCrossEntropy(torch.autograd.Function):
 def margin_cross_entropy(x, weight, label, margin_softmax, check_mode=False, _ops=None):
     """``F.cross_entropy(margin_softmax(F.linear(F.normalize(x), F.normalize(weight)), label), label)`` without the
     logits.  ``x`` [B, E], ``weight`` [C, E] fp32 CUDA tensors (either may require grad), ``label`` int64 [B] in [0, C),
-    ``margin_softmax`` a ``CosFace(s, m)`` / ``ArcFace(s, m)`` descriptor (this package's or the reference's)."""
+    ``margin_softmax`` a ``CosFace(s, m)`` / ``ArcFace(s, m)`` descriptor (this package's or the reference's).
+    One head at a time per device and stream: the step scratch of the kernel provider is shared per device (a second forward
+    in between makes this head's backward rebuild its operands, see ``_MarginCrossEntropy.backward``); heads running
+    concurrently on DIFFERENT CUDA streams of one device are not supported."""
     s, m, kind = margin_params(margin_softmax)
     if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[1] or label.shape[0] != x.shape[0]:
         raise ValueError("margin_cross_entropy: x [B, E], weight [C, E], label [B] expected")
+    if weight.device != x.device or label.device != x.device:
+        raise ValueError("margin_cross_entropy: x, weight and label must live on the same device")
+    if not (weight.is_floating_point() and x.is_floating_point()):
+        raise TypeError("margin_cross_entropy: x and weight must be floating point tensors")
+    if not (s > 0 and s == s and s != float("inf")):
+        raise ValueError("margin_cross_entropy: the scale s must be positive and finite")
     ops = _ops if _ops is not None else _ops_for(x.device, check_mode)
     return _MarginCrossEntropy.apply(x, weight, label, s, m, kind, ops)
 

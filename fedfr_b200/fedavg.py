@@ -10,12 +10,85 @@ Inputs may live on the GPU (the fast path: nothing but the table is copied) or o
 them (client.py:469,558): CPU tensors are staged through pinned memory with async H2D copies and the result is
 returned on the device unless ``out_device`` says otherwise.
 """
-import ctypes as C
 from typing import Dict, List, Sequence
 
 import torch
 
 from . import _native as N
+
+
+class FlatStateDict(dict):
+    """A ``state_dict`` whose tensors are views of ONE flat buffer per dtype (fp32 parameters / buffers, int64 BatchNorm
+    counters).  It is an ordinary ``dict`` for every consumer (``load_state_dict``, ``FedPavg``, pickling of the views), but
+    ``FedPavg`` over K of them with the same layout needs K pointers instead of K x 477: the per-tensor Python work that
+    bounds the plain-dict call (about 10 ms for 40 iresnet50 dicts against a 1.1 ms kernel) disappears.  Build one with
+    ``flatten_state_dict(model.state_dict())`` where the reference does ``copy.deepcopy(model.state_dict())``
+    (client.py:469,558) -- the same copy, laid out contiguously."""
+
+    __slots__ = ("flat_f32", "flat_i64", "layout")
+
+    def __setitem__(self, key, value):          # a replaced entry no longer lives in the flat buffer: plain-dict path from now on
+        self.layout = None
+        dict.__setitem__(self, key, value)
+
+    def __deepcopy__(self, memo):
+        if self.layout is None:
+            return {k: v.clone() for k, v in self.items()}
+        return _rebuild_flat(self.layout[0], self.flat_f32.clone(), self.flat_i64.clone())
+
+    def __reduce__(self):                       # pickle / torch.save: the two buffers + the layout, views rebuilt on load
+        if self.layout is None:
+            return (dict, (dict(self),))
+        return (_rebuild_flat, (self.layout[0], self.flat_f32, self.flat_i64))
+
+
+def _rebuild_flat(items, flat_f32, flat_i64):
+    n_f = sum((_numel(sh) + 3) // 4 * 4 for _, sh, is_int, _ in items if not is_int)
+    n_i = sum(_numel(sh) for _, sh, is_int, _ in items if is_int)
+    out = FlatStateDict()
+    out.flat_f32, out.flat_i64 = flat_f32, flat_i64
+    out.layout = _LAYOUTS.setdefault(items, (items, n_f, n_i))
+    for key, shape, is_int, off in items:
+        dict.__setitem__(out, key, (flat_i64 if is_int else flat_f32)[off:off + _numel(shape)].view(shape))
+    return out
+
+
+_LAYOUTS = {}
+
+
+def _layout_of(sd):
+    """Interned layout: tuple of (key, shape, is_int64, offset) with 4-element (16-byte) aligned fp32 offsets."""
+    items, off_f, off_i = [], 0, 0
+    for k, v in sd.items():
+        if v.dtype is torch.float32:
+            items.append((k, tuple(v.shape), False, off_f))
+            off_f += (v.numel() + 3) // 4 * 4
+        elif v.dtype is torch.int64:
+            items.append((k, tuple(v.shape), True, off_i))
+            off_i += v.numel()
+        else:
+            raise TypeError(f"flatten_state_dict: unsupported dtype {v.dtype} for {k!r} (reference models hold fp32 + int64 counters)")
+    key = tuple(items)
+    return _LAYOUTS.setdefault(key, (key, off_f, off_i))
+
+
+def flatten_state_dict(sd: Dict[str, torch.Tensor], device=None, pin_memory: bool = False) -> FlatStateDict:
+    """Copy ``sd`` into a ``FlatStateDict`` on ``device`` (default: where its first tensor lives)."""
+    layout = _layout_of(sd)
+    items, n_f, n_i = layout
+    first = next(iter(sd.values()))
+    dev = torch.device(device) if device is not None else first.device
+    pin = pin_memory and dev.type == "cpu"
+    out = FlatStateDict()
+    out.flat_f32 = torch.zeros(max(n_f, 4), dtype=torch.float32, device=dev, pin_memory=pin)
+    out.flat_i64 = torch.zeros(max(n_i, 1), dtype=torch.int64, device=dev, pin_memory=pin)
+    out.layout = layout
+    for (k, shape, is_int, off), v in zip(items, sd.values()):
+        n = v.numel()
+        view = (out.flat_i64 if is_int else out.flat_f32)[off:off + n].view(shape)
+        view.copy_(v, non_blocking=True)
+        dict.__setitem__(out, k, view)
+    return out
 
 
 def _normalised_weights(weights: Sequence[float]) -> List[float]:
@@ -78,35 +151,42 @@ def _launch(n_seg, k, device):
                                           n_seg, _tables.w.data_ptr(), k, tab.data_ptr(), tab.numel(), st), "fedavg_weighted_sum")
 
 
-def weighted_sum_segments(srcs: List[List[torch.Tensor]], weights_f32: List[float], device, flat: bool = False):
+def weighted_sum_segments(srcs: List[List[torch.Tensor]], weights_f32: List[float], device, flat: bool = False, keep_first_term: bool = False):
     """srcs[s][i] = tensor of client i for segment s (all on ``device``, contiguous).  Returns fp32 outputs
     (``flat=True``: also the one flat fp32 buffer they are 16-byte-aligned views of, for a single all-reduce)."""
-    return weighted_sum_clients([[group[i] for group in srcs] for i in range(len(weights_f32))], weights_f32, device, flat)
+    return weighted_sum_clients([[group[i] for group in srcs] for i in range(len(weights_f32))], weights_f32, device, flat,
+                                keep_first_term=keep_first_term)
 
 
-def weighted_sum_clients(clients: List[List[torch.Tensor]], weights_f32: List[float], device, flat: bool = False, _staged: bool = False):
+def weighted_sum_clients(clients: List[List[torch.Tensor]], weights_f32: List[float], device, flat: bool = False, _staged: bool = False,
+                         keep_first_term: bool = False):
     """clients[i][s] = tensor of client i for segment s (client-major, the order ``state_dict.values()`` yields).
-    The per-tensor host work is the floor of this call (K x n_seg Python objects): pointers are gathered with one
-    generator pass per client and written into the pinned tables through numpy."""
+    The per-tensor host work is the floor of this call (K x n_seg Python objects): pointers and element counts are
+    gathered with C-level ``map`` passes per client and written into the pinned tables through numpy.
+    ``keep_first_term``: the sum starts at the first term (FedAvg_on_FC) instead of ``0 + first term`` (FedPavg)."""
     import numpy as np
     k, ref = len(weights_f32), clients[0]
     n_seg = len(ref)
     _tables.ensure(n_seg, k)
     f32, i64 = torch.float32, torch.int64
-    numels = [t.numel() for t in ref]
-    codes = []
-    for t in ref:
+    numels = np.fromiter(map(torch.Tensor.numel, ref), dtype=np.int64, count=n_seg)
+    codes = np.empty(n_seg, dtype=np.int32)
+    for s, t in enumerate(ref):
         if t.dtype is f32:
-            codes.append(N.FEDAVG_F32)
+            codes[s] = N.FEDAVG_F32
         elif t.dtype is i64:
-            codes.append(N.FEDAVG_I64)
+            codes[s] = N.FEDAVG_I64
         else:
             raise TypeError(f"FedPavg: unsupported state_dict dtype {t.dtype} (reference models hold fp32 + int64 counters)")
+    dtypes = [t.dtype for t in ref]
+    if keep_first_term:
+        codes |= N.FEDAVG_KEEP_FIRST_TERM
     # one flat output allocation; segments start on 16-byte boundaries (vector path of the kernel)
     offsets = np.zeros(n_seg + 1, dtype=np.int64)
-    np.cumsum([(n + 3) // 4 * 4 for n in numels], out=offsets[1:])
+    np.cumsum((numels + 3) // 4 * 4, out=offsets[1:])
     flat_buf = torch.empty(max(int(offsets[-1]), 4), dtype=torch.float32, device=device)
-    outs = [flat_buf[int(offsets[s]):int(offsets[s]) + numels[s]].view(ref[s].shape) for s in range(n_seg)]
+    offs = offsets.tolist()
+    outs = [flat_buf[offs[s]:offs[s] + int(numels[s])].view(ref[s].shape) for s in range(n_seg)]
     _tables.out_np[:n_seg] = flat_buf.data_ptr() + 4 * offsets[:-1]
     _tables.len_np[:n_seg] = numels
     _tables.dtype_np[:n_seg] = codes
@@ -115,14 +195,67 @@ def weighted_sum_clients(clients: List[List[torch.Tensor]], weights_f32: List[fl
     for i, tensors in enumerate(clients):
         if len(tensors) != n_seg:
             raise ValueError("FedPavg: every client must hold the same keys")
-        for s, t in enumerate(tensors):      # structural checks; the kernel trusts the table (_stage already fixed device/contiguity)
-            if t.numel() != numels[s] or t.dtype is not ref[s].dtype or \
-                    not (_staged or (t.is_contiguous() and t.is_cuda and t.get_device() == dev_index)):
-                raise ValueError("FedPavg: every client must hold the same dtype/shape (contiguous, on the reduction device) per key")
-        src[:, i] = np.fromiter((t.data_ptr() for t in tensors), dtype=np.int64, count=n_seg)
+        # structural checks; the kernel trusts the table (_stage already fixed device / contiguity of staged clients)
+        if i > 0 and (not np.array_equal(np.fromiter(map(torch.Tensor.numel, tensors), dtype=np.int64, count=n_seg), numels)
+                      or [t.dtype for t in tensors] != dtypes):
+            raise ValueError("FedPavg: every client must hold the same dtype/shape per key")
+        if not _staged and not all(t.is_contiguous() and t.is_cuda and t.get_device() == dev_index for t in tensors):
+            raise ValueError("FedPavg: tensors must be contiguous and on the reduction device")
+        src[:, i] = np.fromiter(map(torch.Tensor.data_ptr, tensors), dtype=np.int64, count=n_seg)
     _tables.w_np[:k] = weights_f32
     _launch(n_seg, k, device)
     return (outs, flat_buf) if flat else outs
+
+
+def _weighted_sum_flat(models, weights_f32, device, keep_views=True):
+    """K ``FlatStateDict`` clients of one layout on ``device``: two segments (the fp32 buffer, the int64 buffer), K pointers each."""
+    layout = models[0].layout
+    items, n_f, n_i = layout
+    k = len(models)
+    segs = [("f", n_f)] + ([("i", n_i)] if n_i > 0 else [])
+    n_seg = len(segs)
+    _tables.ensure(n_seg, k)
+    n_f_pad = (max(n_f, 4) + 3) // 4 * 4
+    flat_buf = torch.empty(n_f_pad + max(n_i, 0), dtype=torch.float32, device=device)
+    _tables.out_np[0] = flat_buf.data_ptr()
+    _tables.len_np[0] = n_f
+    _tables.dtype_np[0] = N.FEDAVG_F32
+    src = _tables.src_np[:n_seg * k].reshape(n_seg, k)
+    src[0, :] = [m.flat_f32.data_ptr() for m in models]
+    if n_i > 0:
+        _tables.out_np[1] = flat_buf.data_ptr() + 4 * n_f_pad
+        _tables.len_np[1] = n_i
+        _tables.dtype_np[1] = N.FEDAVG_I64
+        src[1, :] = [m.flat_i64.data_ptr() for m in models]
+    _tables.w_np[:k] = weights_f32
+    _launch(n_seg, k, device)
+    views = _OUT_VIEWS.get(layout)
+    if views is None:           # (key, offset, numel, shape) in the output buffer, computed once per layout
+        views = [(key, (n_f_pad + off) if is_int else off, _numel(shape), shape) for (key, shape, is_int, off) in items]
+        _OUT_VIEWS[layout] = views
+    out = FlatStateDict()
+    out.flat_f32, out.flat_i64, out.layout = flat_buf, None, None
+    for key, off, n, shape in views:
+        dict.__setitem__(out, key, flat_buf[off:off + n].view(shape))
+    return out, flat_buf
+
+
+_OUT_VIEWS = {}
+
+
+def _numel(shape):
+    n = 1
+    for d in shape:
+        n *= d
+    return n
+
+
+def _all_flat(models, dev):
+    first = models[0]
+    if not isinstance(first, FlatStateDict) or first.layout is None:
+        return False
+    lay = first.layout
+    return all(isinstance(m, FlatStateDict) and m.layout is lay and (dev is None or m.flat_f32.device == dev) for m in models)
 
 
 def _stage(sd_values, dev):
@@ -135,6 +268,15 @@ def _stage(sd_values, dev):
     return out
 
 
+def _flat_to(m: "FlatStateDict", dev) -> "FlatStateDict":
+    """One H2D copy per dtype buffer (pinned sources stay asynchronous) instead of one per tensor."""
+    out = FlatStateDict()
+    out.flat_f32 = m.flat_f32.to(dev, non_blocking=True)
+    out.flat_i64 = m.flat_i64.to(dev, non_blocking=True)
+    out.layout = m.layout
+    return out
+
+
 def FedPavg(models: List[Dict[str, torch.Tensor]], weights: Sequence[float], device=None, out_device=None):
     """server.py:25-34."""
     if not torch.cuda.is_available():
@@ -143,6 +285,10 @@ def FedPavg(models: List[Dict[str, torch.Tensor]], weights: Sequence[float], dev
     if dev.index is None:
         dev = torch.device("cuda", torch.cuda.current_device())
     wn = [float(torch.tensor(w, dtype=torch.float64).to(torch.float32)) for w in _normalised_weights(weights)]
+    if _all_flat(models, None):
+        staged = [m if m.flat_f32.device == dev else _flat_to(m, dev) for m in models]
+        out, _ = _weighted_sum_flat(staged, wn, dev)
+        return out if out_device is None else {k: v.to(out_device) for k, v in out.items()}
     keys = list(models[0].keys())
     clients = []
     for sd in models:
@@ -161,7 +307,7 @@ def FedAvg_on_FC(pretrain_fc: torch.Tensor, models: List[torch.Tensor], weights:
     dev = _device_of([{"fc": m} for m in models], device)
     wn = [float(torch.tensor(w, dtype=torch.float64).to(torch.float32)) for w in _normalised_weights(weights)]
     group = [m.to(dev, non_blocking=True).contiguous() for m in models]
-    aggr = weighted_sum_segments([group], wn, dev)[0]
+    aggr = weighted_sum_segments([group], wn, dev, keep_first_term=True)[0]
     if p == 1:
         return aggr
     old = pretrain_fc.to(dev).contiguous()
@@ -203,8 +349,13 @@ def FedPavg_sharded(local_models: List[Dict[str, torch.Tensor]], local_weights: 
     if _segments_fn is None:
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
-        clients = [_stage([sd[name] for name in keys], dev) for sd in local_models]
-        outs, flat_buf = weighted_sum_clients(clients, wn, dev, flat=True, _staged=True)
+        if _all_flat(local_models, None):
+            staged = [m if m.flat_f32.device == dev else _flat_to(m, dev) for m in local_models]
+            out, flat_buf = _weighted_sum_flat(staged, wn, dev)
+            outs = [out[name] for name in keys]
+        else:
+            clients = [_stage([sd[name] for name in keys], dev) for sd in local_models]
+            outs, flat_buf = weighted_sum_clients(clients, wn, dev, flat=True, _staged=True)
     else:
         srcs = [[sd[name].to(dev).contiguous() for sd in local_models] for name in keys]
         outs, flat_buf = _segments_fn(srcs, wn, dev, flat=True)

@@ -28,9 +28,10 @@ class CosFace(torch.nn.Module):
 
 
 class ArcFace(torch.nn.Module):
-    """losses.py:32-45 as a descriptor: ``s * cos(acos(cosine) + m)`` on the target column.  Fused into the same logits
-    epilogues as CosFace (the target cosine is clamped to [-1, 1] first); calling it on dense logits is not offered --
-    the reference's own dense path (client.py:133) goes through ``PartialFC`` here."""
+    """losses.py:32-45: ``s * cos(acos(cosine) + m)`` on the target column.  ``PartialFC`` / ``margin_cross_entropy`` read
+    the object as a descriptor and fuse it into the logits epilogues (target cosine clamped to [-1, 1] first); calling it
+    on materialised logits (client.py:430 with ``--loss ArcFace``) runs the reference's arithmetic in one elementwise
+    kernel, in place on ``cosine`` and returning it, exactly like the reference."""
 
     def __init__(self, s=64.0, m=0.5):
         super().__init__()
@@ -38,7 +39,14 @@ class ArcFace(torch.nn.Module):
         self.m = m
 
     def forward(self, cosine, label):
-        raise NotImplementedError("fedfr_b200.ArcFace is a margin descriptor for PartialFC; it has no dense-logits kernel")
+        from . import _native as N
+        if not cosine.is_cuda:
+            raise RuntimeError("fedfr_b200.losses.ArcFace runs on CUDA tensors only (no CPU fallback)")
+        assert cosine.dtype == torch.float32 and cosine.is_contiguous() and label.dtype == torch.int64
+        st = torch.cuda.current_stream(cosine.device).cuda_stream
+        N.check(N.lib.pfc_arcface_dense(N.ptr(cosine), N.ptr(label.contiguous()), cosine.shape[0], cosine.shape[1], float(self.s),
+                                        float(self.m), st), "pfc_arcface_dense")
+        return cosine
 
 
 _MARGIN_KINDS = {"CosFace": 0, "ArcFace": 1}      # PFC_MARGIN_COSFACE / PFC_MARGIN_ARCFACE

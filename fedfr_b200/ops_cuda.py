@@ -15,6 +15,11 @@ from . import _native as N
 BWD_MODE = os.environ.get("FEDFR_BWD_MODE", "prob")
 
 
+RANGE_LIMIT_NATS = 80.0      # s * |x_i| beyond this leaves the exponent window described in include/fedfr_b200.h
+RANGE_SLOTS = 4
+_RANGE_FLAGS = {}            # device index -> pinned int32[RANGE_SLOTS, 2] shared by every CudaOps of that device
+
+
 def _stream(device):
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -36,6 +41,29 @@ class CudaOps:
             raise ValueError("FEDFR_BWD_MODE must be 'prob' or 'recompute'")
         self._prob = None       # (workspace, offset, bytes, bt, cs, emb, token) of the last stored-probability forward
         self.last_token = 0     # bumped by every forward: step buffers (x_hat, w_hat, inv_norm, P) belong to the newest one
+        # range guard of the stored-probability path: sticky (s |x| out of the exponent window, row sum of 0) int pairs in
+        # pinned host memory that the kernels set every step; RANGE_SLOTS pairs, so that a caller can give every step its
+        # own pair and read it back a fixed number of steps later (the same decision on every rank, no synchronisation)
+        self._range_flag = _RANGE_FLAGS.get(self.device.index or 0)
+        if self._range_flag is None and path == N.PATH_TENSOR:
+            self._range_flag = torch.zeros((RANGE_SLOTS, 2), dtype=torch.int32).pin_memory()
+            _RANGE_FLAGS[self.device.index or 0] = self._range_flag
+        if path == N.PATH_TENSOR:
+            self.set_range_slot(0)
+
+    def set_range_slot(self, slot):
+        """The stored-probability kernels launched from now on report into pair ``slot``."""
+        with torch.cuda.device(self.device):
+            N.check(N.lib.pfc_set_range_flag(self._range_flag.data_ptr() + 8 * int(slot), RANGE_LIMIT_NATS), "pfc_set_range_flag")
+
+    def read_range_slot(self, slot):
+        """Pair ``slot`` as a bit mask (1: s |x| beyond the window, 2: a row sum of 0), cleared.  Plain read of pinned host
+        memory: the caller makes sure the step that wrote it has completed (an event), or accepts a late answer."""
+        f = self._range_flag[int(slot)]
+        v = int(f[0]) | (int(f[1]) << 1)
+        if v:
+            f.zero_()
+        return v
 
     # ------------------------------------------------------------------ helpers
     def _persist(self, name, shape, dtype):
@@ -131,7 +159,7 @@ class CudaOps:
             self._ws[key] = w_hat
         return w_hat
 
-    def normalize_fwd_stats(self, sub_weight, x_hat, label, s, m, margin_kind=0):
+    def normalize_fwd_stats(self, sub_weight, x_hat, label, s, m, margin_kind=0, bwd_mode=None):
         """normalize(sub_weight) fused with fwd_stats (one graph: the normalisation of class chunk k+1 runs under the
         logits kernel of chunk k).  -> (w_hat, inv_norm, stats [Bt, 3])."""
         n, emb = sub_weight.shape
@@ -143,7 +171,7 @@ class CudaOps:
         tz = self._persist("target_logit", (bt,), torch.float32)
         st = _stream(self.device)
         self._prob = None
-        if self.bwd_mode == "prob":
+        if (bwd_mode or self.bwd_mode) == "prob":
             pws, off, nbytes = self._prob_ws(bt, n, emb)
             N.check(N.lib.pfc_normalize_fwd_prob(N.ptr(sub_weight), None, N.ptr(x_hat), N.ptr(label), bt, n, emb, float(s), float(m), int(margin_kind),
                                                  N.ptr(w_hat), N.ptr(inv), N.ptr(part[0]), N.ptr(part[1]), N.ptr(tz), pws.data_ptr() + off, nbytes, st),
@@ -171,7 +199,7 @@ class CudaOps:
                                          _stream(self.device)), "pfc_cast_rows_bf16")
         return x
 
-    def fwd_stats(self, x_hat, w_hat, label, s, m, margin_kind=0):
+    def fwd_stats(self, x_hat, w_hat, label, s, m, margin_kind=0, bwd_mode=None):
         """-> stats [Bt, 3] = (row max, sum-exp at that max, target logit) of this shard."""
         bt, emb = x_hat.shape
         cs = w_hat.shape[0]
@@ -180,7 +208,7 @@ class CudaOps:
         tz = self._persist("target_logit", (bt,), torch.float32)
         st = _stream(self.device)
         self._prob = None
-        if self.bwd_mode == "prob":     # w == NULL: w_hat / inv_norm are already valid
+        if (bwd_mode or self.bwd_mode) == "prob":     # w == NULL: w_hat / inv_norm are already valid
             pws, off, nbytes = self._prob_ws(bt, cs, emb)
             inv = self._persist("inv_norm", (cs,), torch.float32)
             N.check(N.lib.pfc_normalize_fwd_prob(None, None, N.ptr(x_hat), N.ptr(label), bt, cs, emb, float(s), float(m), int(margin_kind), N.ptr(w_hat),

@@ -88,7 +88,9 @@ class PartialFC(Module):
         else:
             self.sub_weight = Parameter(torch.empty((0, 0), device=self.device))
         self._norm = None       # (w_hat, inv_norm) of the current step
-        self._range_checks = 0  # forward_backward calls since the last s * |x| range check (stored-probability path)
+        self._range_checks = 0  # forward_backward calls seen by the range guard of the stored-probability path
+        self._range_events = None
+        self._range_slot = None
         self._prenorm = None    # (w_hat, inv_norm, weight ptr, weight version) left behind by step(prenormalize=True)
         self._label_buf = None
 
@@ -164,28 +166,47 @@ class PartialFC(Module):
 
     # ------------------------------------------------------------------ range guard of the stored-probability path
     _RANGE_LIMIT = 80.0         # nats: s * max|x_i| beyond this leaves the exponent window of include/fedfr_b200.h
-    _RANGE_PERIOD = 256         # calls between checks (callers either always or never normalise their embeddings)
+
+    def _to_recompute(self, why):
+        logging.getLogger('FL_face.partial').warning(
+            "PartialFC: %s is outside the stored-probability range; using the recomputing backward from now on "
+            "(normalise the embeddings, as partial_fc.py's callers do, to get the faster path)", why)
+        self._ops.bwd_mode = "recompute"
 
     def _check_logit_range(self, features):
-        """The stored-probability forward references every row to the bound s |x_i| (no row maximum is known before
-        the GEMM); with un-normalised embeddings of large norm that bound is hundreds of nats above the real logits and
-        they would underflow.  The first call, and every 256th after it, looks at max |x_i| (one small reduction and one
-        host read) and switches this head to the recomputing backward for good if the bound is out of range -- all
-        ranks together, so that the shards keep one reference point per row."""
+        """The stored-probability forward references every row to the bound s |x_i| (no row maximum is known before the
+        GEMM); with un-normalised embeddings of large norm that bound is hundreds of nats above the real logits and they
+        would underflow.  Two guards:
+        * the FIRST call reads max |x_i| back (one small reduction, one host read) and decides before anything runs;
+        * EVERY later step is checked on the device at no cost: its kernels raise a sticky flag pair in pinned host memory
+          when s |x_i| leaves the window or a row sum comes out 0 (``pfc_set_range_flag``).  Step n reports into pair
+          n mod 4 and the pair is read at the start of step n + 2, after an event recorded behind step n (long complete
+          by then: no stall) -- every rank sees the same gathered batch, hence takes the same decision at the same step.
+          A violation therefore switches the head to the recomputing backward two steps after it happened, with a log
+          line (the offending rows of those steps had zero gradients), instead of going unnoticed for up to 255 steps."""
         ops = self._ops
         if getattr(ops, "bwd_mode", None) != "prob":
             return
+        n = self._range_checks
         self._range_checks += 1
-        if self._range_checks != 1 and self._range_checks % self._RANGE_PERIOD:
+        if n == 0:
+            worst = features.detach().to(torch.float32).norm(dim=1).max() * self._s
+            if self.world_size > 1:
+                dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+            if not float(worst) <= self._RANGE_LIMIT:          # also catches NaN
+                self._to_recompute("s * |x| = %.1f" % float(worst))
+                return
+        if not hasattr(ops, "read_range_slot"):
             return
-        worst = features.detach().to(torch.float32).norm(dim=1).max() * self._s
-        if self.world_size > 1:
-            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
-        if not float(worst) <= self._RANGE_LIMIT:          # also catches NaN
-            logging.getLogger('FL_face.partial').warning(
-                "PartialFC: s * |x| = %.1f is outside the stored-probability range; using the recomputing backward "
-                "(normalise the embeddings, as partial_fc.py's callers do, to get the faster path)", float(worst))
-            ops.bwd_mode = "recompute"
+        if self._range_events is None:
+            self._range_events = [torch.cuda.Event() for _ in range(4)]
+        if n >= 2:
+            self._range_events[(n - 2) % 4].synchronize()
+            if ops.read_range_slot((n - 2) % 4):
+                self._to_recompute("a batch two steps ago (s * |x| beyond %.0f nats, or an underflowed row)" % self._RANGE_LIMIT)
+                return
+        ops.set_range_slot(n % 4)
+        self._range_slot = n % 4
 
     # ------------------------------------------------------------------ collectives
     def _all_gather(self, out, inp):
@@ -263,6 +284,9 @@ class PartialFC(Module):
         dx_total = ops.bwd(x_hat, w_hat, inv_norm, total_label, row_max, row_sum, self._s, self._m, 1.0 / (B * W),
                            self.sub_weight.grad, accumulate, self._margin_kind)
 
+        if self._range_slot is not None:            # the range guard reads this step's flag pair two steps from now
+            self._range_events[self._range_slot].record()
+            self._range_slot = None
         if W == 1:
             x_grad = dx_total.clone()               # dx_total is step scratch with a stable address
         else:

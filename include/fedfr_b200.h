@@ -109,7 +109,8 @@ int pfc_fwd_num_partials(int64_t n_rows, int64_t n_classes, int emb, int path);
  *   x, w_hat     bf16 (PFC_PATH_TENSOR) or fp32 (PFC_PATH_CHECK), [n_rows, emb] / [n_classes, emb]
  *   label        int64 [n_rows], -1 = class not in this shard
  *   part_max/part_sum  fp32 [pfc_fwd_num_partials(...), n_rows]
- *   target_logit fp32 [n_rows], must be zero-filled by the caller (only owning rows are written) */
+ *   target_logit fp32 [n_rows]; the library zero-fills target_logit and part_sum itself before the launch (only owning
+ *                rows are then written), so the caller may pass a persistent, un-cleared buffer */
 int pfc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes,
                   int emb, float s, float m, int margin_kind, float* part_max, float* part_sum, float* target_logit,
                   int path, void* stream);
@@ -171,6 +172,14 @@ int pfc_normalize_fwd_prob(const float* w, const int64_t* index, const void* x, 
                            float* inv_norm, float* part_max, float* part_sum, float* target_logit,
                            void* prob_ws, size_t prob_ws_bytes, void* stream);
 
+/* Range guard of the stored-probability path.  `flag` = two ints in pinned host memory (or device memory), NULL disables:
+ *   flag[0] := 1 by pfc_normalize_fwd_prob when s |x_i| of some row exceeds `limit_nats` (<= 0: keep the default 80) or is
+ *              not finite -- the row would be referenced to a bound far above its real logits and underflow;
+ *   flag[1] := 1 by pfc_bwd_prob when a row's sum of probabilities is 0 or not finite (its gradients are then zero).
+ * Sticky plain stores, checked EVERY step on the device at no cost; the host polls them without synchronising and switches
+ * to pfc_normalize_fwd_stats + pfc_bwd (no such domain limit).  Applies to the calling thread's current device. */
+int pfc_set_range_flag(int* flag, float limit_nats);
+
 /* Backward of pfc_normalize_fwd_prob: same outputs as pfc_bwd.  row_sum = the GLOBAL sum_j P_ij of
  * pfc_finalize_stats.  G_ij = (s / (row_sum_i total_batch)) P_ij is never formed: dx = row-scaled P . w_hat,
  * dwh = P^T . (row-scaled x); the radial term w_hat_j . dwh_j of the normalize backward is taken from the dw accumulator. */
@@ -198,12 +207,19 @@ int pfc_spreadout(const void* w_hat, int64_t n, int emb, float margin, float* pa
 int pfc_cosface_dense(float* cosine, const int64_t* label, int64_t n_rows, int64_t n_classes, float s, float m,
                       float* out, void* stream);
 
+/* losses.ArcFace.forward on materialised logits (client.py:430 with --loss ArcFace): IN PLACE, like the reference,
+ * cosine = s * cos(acos(cosine) + m [label_i == j]) (rows with label -1 get no margin).              losses.py:38-45 */
+int pfc_arcface_dense(float* cosine, const int64_t* label, int64_t n_rows, int64_t n_classes, float s, float m,
+                      void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * FedAvg                                                                server.py:25-46
  * ---------------------------------------------------------------------------------------------- */
 
 #define FEDAVG_F32  0
 #define FEDAVG_I64  1
+#define FEDAVG_KEEP_FIRST_TERM 0x100   /* OR into a dtype code: the sum starts AT the first term (FedAvg_on_FC, server.py:38)
+                                          instead of 0 + first term (FedPavg, server.py:30-32: -0.0 becomes +0.0) */
 
 /* One segment = one state_dict entry: K source tensors of n elements and one fp32 output.
  * out[e] = sum_i fl32(w_i) * fl32(src_i[e]) evaluated as separate round-to-nearest multiply and add in
@@ -211,7 +227,8 @@ int pfc_cosface_dense(float* cosine, const int64_t* label, int64_t n_rows, int64
  *   seg_src_host   [n_seg * K] device pointers, client-minor (segment s, client i -> s*K + i)
  *   seg_out_host   [n_seg]     device pointers (fp32)
  *   seg_len_host   [n_seg]     element counts
- *   seg_dtype_host [n_seg]     FEDAVG_F32 / FEDAVG_I64
+ *   seg_dtype_host [n_seg]     FEDAVG_F32 / FEDAVG_I64 [| FEDAVG_KEEP_FIRST_TERM]; fp32 segments with a source or output that is
+ *                              not 16-byte aligned take a scalar path; K > 64 clients run as ceil(K / 64) launches, same sum order
  *   weights_host   [K]         already normalised (w_i / sum w), rounded to fp32 by the caller
  * table_dev: device scratch of at least fedavg_table_bytes(n_seg, K) bytes; the host arrays are copied
  * into it with cudaMemcpyAsync on `stream` (so they must stay valid until the stream reaches the copy;

@@ -214,6 +214,77 @@ def forward_backward(features: Sequence[torch.Tensor], labels: Sequence[torch.Te
                    [pr[0].numpy() for pr in per_rank])
 
 
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.float32).to(torch.bfloat16).to(torch.float64)
+
+
+def forward_backward_bf16(features: Sequence[torch.Tensor], labels: Sequence[torch.Tensor], weights: Sequence[torch.Tensor],
+                          num_classes: int, s: float = 64.0, m: float = 0.4, sample_rate: float = 1.0,
+                          perms: Optional[Sequence[np.ndarray]] = None, margin: str = "cosface",
+                          w_hats: Optional[Sequence[torch.Tensor]] = None) -> StepOut:
+    """``forward_backward`` with the operand roundings of the bf16 tensor path written out, everything else in fp64
+    (so that a kernel on the same rounded operands differs by accumulation order only and can be compared ROW BY ROW at
+    ~1e-3 instead of 1e-2 on a whole-tensor norm).  Same reference lines as ``forward_backward``; the roundings are those
+    of ``fedfr_b200/csrc/tc_kernels.cu``'s stored-probability path:
+
+        x_hat = bf16(x)                     w_hat = bf16(w / max(|w|, eps))   (or ``w_hats[r]``, the kernel's own operand)
+        a_i   = s2 |x_hat_i| (1 + 2^-7) - 58                                   (log2 units; any finite a_i is exact maths)
+        P_ij  = bf16(fp32(exp2(s2 cos_ij - a_i)))    S_i = sum_j fp32 P_ij (target with margin, before bf16)
+        scale_i = fp32(s / (Bt S_i))       xs_i = bf16(x_hat_i scale_i)
+        v_i   = bf16(fp32((p_iy S_i - S_i) slope_i))                           (target element of the scratch)
+        dx_i  = scale_i sum_j P'_ij w_hat_j        dW_hat_j = sum_i P'_ij xs_i        dW_j = (dW_hat_j - w_hat_j t_j) fp32(1/n_j)
+    """
+    W = len(weights)
+    B = features[0].shape[0]
+    Bt = B * W
+    s2 = s * math.log2(math.e)
+    x = _bf16(torch.cat([f for f in features], dim=0))
+    y_all = torch.cat([l.to(torch.int64) for l in labels], dim=0).numpy()
+    a = (torch.tensor(s2, dtype=torch.float32) * x.norm(dim=1).float() * 1.0078125 - 58.0).double()
+    per_rank, S = [], torch.zeros(Bt, dtype=torch.float64)
+    for r in range(W):
+        num_local, class_start = shard_geometry(num_classes, W, r)
+        y = remap_labels(y_all, class_start, num_local)
+        index = None
+        w = weights[r].to(torch.float32)
+        if int(sample_rate) != 1:
+            index = sample_index(y, perms[r], num_sample_of(sample_rate, num_local))
+            y = relabel_to_sample(y, index)
+            w = w[torch.from_numpy(index)]
+        n = w.norm(dim=1, keepdim=True).clamp_min(NORMALIZE_EPS)
+        w_hat = _bf16(w_hats[r]) if w_hats is not None else _bf16(w * (1.0 / n))
+        yt = torch.from_numpy(y)
+        rows = torch.nonzero(yt >= 0, as_tuple=True)[0]
+        cos = x @ w_hat.t()
+        c_t = cos[rows, yt[rows]].float()
+        if margin == "cosface":
+            mc_t, slope = c_t - m, torch.ones_like(c_t)
+        else:
+            cc = c_t.clamp(-1.0, 1.0)
+            mc_t, slope = torch.cos(torch.acos(cc) + m), torch.sin(torch.acos(cc) + m) / torch.sqrt((1.0 - cc * cc).clamp_min(1e-12))
+        cos[rows, yt[rows]] = mc_t.double()
+        P = torch.exp2(cos * s2 - a[:, None]).float()
+        S += P.double().sum(dim=1)
+        per_rank.append((yt, index, rows, w_hat, n, P, mc_t, slope))
+    scale = (torch.tensor(s / Bt, dtype=torch.float64) / S).float().double()
+    xs = _bf16(x * scale[:, None])
+    dx_sum = torch.zeros(Bt, x.shape[1], dtype=torch.float64)
+    logp = torch.zeros(Bt, dtype=torch.float64)
+    dws = []
+    for (yt, index, rows, w_hat, n, P, mc_t, slope) in per_rank:
+        pS = torch.exp2(mc_t.double() * s2 - a[rows])
+        logp[rows] = (mc_t.double() * s2 - a[rows]) * math.log(2.0) - torch.log(S[rows])
+        Pq = _bf16(P)
+        Pq[rows, yt[rows]] = _bf16(((pS - S[rows]) * slope.double()).float())
+        dx_sum += (Pq @ w_hat) * scale[:, None]
+        dw_hat = Pq.t() @ xs
+        t = (w_hat * dw_hat).sum(dim=1, keepdim=True)
+        dws.append((dw_hat - w_hat * t) * (1.0 / n).float().double())
+    loss = torch.minimum(-logp, torch.full_like(logp, -math.log(PROB_FLOOR))).mean()
+    x_grad = [dx_sum[r * B:(r + 1) * B] * W for r in range(W)]
+    return StepOut(loss, x_grad, dws, [pr[1] for pr in per_rank], [pr[0].numpy() for pr in per_rank])
+
+
 def dense_twin_grads(x, w, label, s, m):
     """Second, independent statement of the same maths through autograd: client.py:69-74 (FC_module with
     pre-normalised features) + losses.py:23-29 + F.cross_entropy (client.py:433).  Returns (loss, dx, dw)."""

@@ -142,3 +142,42 @@ def test_two_gpu_roc_histogram():
     for r in (0, 1):
         for c in "abc":
             assert np.array_equal(ret[r][c].reshape(-1), z[c + "/hist"]), (r, c)
+
+
+def _selfcheck_worker(rank, world, port, sr, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import fedfr_b200
+        from fedfr_b200 import selfcheck as SC
+        dev = torch.device("cuda", rank)
+        B, C, E = 512, 200_001, 512                       # ragged shards, the kernels' production tile shapes
+        torch.manual_seed(100 + rank)
+        head = fedfr_b200.PartialFC(rank, rank, world, B, False, fedfr_b200.CosFace(64.0, 0.4), C, sample_rate=sr, embedding_size=E, prefix="/tmp")
+        x = torch.nn.functional.normalize(torch.randn(B, E, device=dev))
+        y = torch.randint(0, C, (B,), device=dev)
+        opt = torch.optim.SGD([{"params": head.parameters()}], lr=0.1, momentum=0.9)
+        for _ in range(2):
+            head.sub_weight.grad = None
+            xg, loss = head.forward_backward(y, x, opt)
+        out = SC.check_head_step(head, y, x, xg, loss)
+        ret[rank] = out
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("sr,port", [(1.0, 29771), (0.1, 29772)])
+def test_two_gpu_selfcheck_at_production_tiles(sr, port):
+    """The check bench.py runs after its timed loops (fedfr_b200/selfcheck.py: reference arithmetic at 1e-2, bf16-emulating
+    restatement row by row, identical loss bits on every rank) on 2 NCCL ranks, unsampled and sampled."""
+    import __graft_entry__ as g
+    g.build()
+    ret = mp.Manager().dict()
+    mp.spawn(_selfcheck_worker, args=(2, port, sr, ret), nprocs=2, join=True)
+    for r in (0, 1):
+        assert ret[r]["ok"] and ret[r]["ok_all_ranks"] and ret[r]["loss_identical_on_all_ranks"], dict(ret[r])
