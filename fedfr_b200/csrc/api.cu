@@ -32,6 +32,7 @@ void tc_set_clusters(int dx_cs, int dw_cs);
 void tc_set_debug(long long* p);
 void tc_set_logits_pair(int on);
 void tc_set_graph(int on);
+void tc_set_dw4(int on);
 int tc_set_range_flag(int* flag, float limit_nats);
 void tc_set_dx_pair(int on);
 void tc_set_prefetch(int logits, int dx, int dw);
@@ -184,6 +185,11 @@ int pfc_set_debug_buffer(void* dev_ptr) {
  * flag[0] is set when s |x_i| of a row exceeds `limit_nats` (or is not finite) in pfc_normalize_fwd_prob, flag[1] when a
  * row sum is 0 / non-finite in pfc_bwd_prob.  Sticky; applies to the calling thread's current device. */
 int pfc_set_range_flag(int* flag, float limit_nats) { return tc_set_range_flag(flag, limit_nats); }
+
+int pfc_set_dw4(int on) {   /* 1 = 4-CTA-cluster dw kernel for E = 512 (opt-in), 0 = e-split pair kernel (default) */
+  tc_set_dw4(on);
+  return 0;
+}
 
 int pfc_set_graph(int on) {   /* 1 = replay the backward as a cached CUDA graph (default), 0 = launch kernel by kernel */
   tc_set_graph(on);

@@ -8,6 +8,7 @@
 // HBM bound: algorithmic bytes = (K + 1) * 4 per fp32 element.  Every thread keeps K independent
 // 128-bit loads in flight (one per client) before the dependent add chain starts.
 #include "common.cuh"
+#include <string.h>
 
 namespace pfc {
 
@@ -140,18 +141,33 @@ int fedavg_weighted_sum(const void* const* seg_src_host, void* const* seg_out_ho
   PFC_REQUIRE(n_seg > 0 && K > 0, PFC_E_SHAPE, "fedavg_weighted_sum: need K >= 1 clients (got %d) and n_seg > 0", K);
   PFC_REQUIRE(table_bytes >= fedavg_table_bytes(n_seg, K), PFC_E_WORKSPACE, "fedavg_weighted_sum: table buffer too small");
   cudaStream_t st = as_stream(stream);
-  // host staging (pinned, reused by this thread): block table + dtype codes with the alignment flag
-  static thread_local int64_t* blk_host = nullptr;
-  static thread_local int32_t* code_host = nullptr;
-  static thread_local int blk_cap = 0;
-  if (blk_cap < n_seg + 1) {
-    if (blk_host) cudaFreeHost(blk_host);
-    if (code_host) cudaFreeHost(code_host);
-    blk_host = nullptr; code_host = nullptr; blk_cap = 0;
-    PFC_CUDA(cudaMallocHost(&blk_host, sizeof(int64_t) * (size_t)(n_seg + 1)));
-    PFC_CUDA(cudaMallocHost(&code_host, sizeof(int32_t) * (size_t)(n_seg + 1)));
-    blk_cap = n_seg + 1;
+  // host staging: a ring of pinned images of the whole device table (+ one event each).  The caller's arrays are copied
+  // into the image before this call returns, so they may be reused at once, and consecutive calls do not wait for each
+  // other's kernels (a slot is only waited for when the ring wraps around to it).
+  struct Slot { char* host = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; };
+  constexpr int kRing = 4;
+  static thread_local Slot ring[kRing];
+  static thread_local unsigned ring_pos = 0;
+  Slot& slot = ring[ring_pos++ % kRing];
+  const size_t need = fedavg_table_bytes(n_seg, K);
+  if (slot.ev) PFC_CUDA(cudaEventSynchronize(slot.ev));
+  else PFC_CUDA(cudaEventCreateWithFlags(&slot.ev, cudaEventDisableTiming));
+  if (slot.cap < need) {
+    if (slot.host) cudaFreeHost(slot.host);
+    slot.host = nullptr; slot.cap = 0;
+    PFC_CUDA(cudaMallocHost(&slot.host, need));
+    slot.cap = need;
   }
+  // image layout == device layout
+  char* h = slot.host;
+  const size_t off_out = align256((size_t)n_seg * K * 8), off_len = off_out + align256((size_t)n_seg * 8), off_code = off_len + align256((size_t)n_seg * 8);
+  const size_t off_blk = off_code + align256((size_t)n_seg * 4), off_w = off_blk + align256((size_t)(n_seg + 1) * 8);
+  int64_t* blk_host = reinterpret_cast<int64_t*>(h + off_blk);
+  int32_t* code_host = reinterpret_cast<int32_t*>(h + off_code);
+  memcpy(h, seg_src_host, (size_t)n_seg * K * 8);
+  memcpy(h + off_out, seg_out_host, (size_t)n_seg * 8);
+  memcpy(h + off_len, seg_len_host, (size_t)n_seg * 8);
+  memcpy(h + off_w, weights_host, (size_t)K * 4);
   // the 128-bit path needs 16-byte aligned pointers (whole torch allocations are; views at odd offsets are not): a segment
   // with any unaligned source or output takes the scalar path instead
   for (int s = 0; s < n_seg; ++s) {
@@ -181,22 +197,12 @@ int fedavg_weighted_sum(const void* const* seg_src_host, void* const* seg_out_ho
   char* p = reinterpret_cast<char*>(table_dev);
   FedavgTable tb;
   tb.src = reinterpret_cast<const void* const*>(p);
-  PFC_CUDA(cudaMemcpyAsync(p, seg_src_host, (size_t)n_seg * K * 8, cudaMemcpyHostToDevice, st));
-  p += align256((size_t)n_seg * K * 8);
-  tb.out = reinterpret_cast<float* const*>(p);
-  PFC_CUDA(cudaMemcpyAsync(p, seg_out_host, (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
-  p += align256((size_t)n_seg * 8);
-  tb.len = reinterpret_cast<const int64_t*>(p);
-  PFC_CUDA(cudaMemcpyAsync(p, seg_len_host, (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
-  p += align256((size_t)n_seg * 8);
-  tb.dtype = reinterpret_cast<const int32_t*>(p);
-  PFC_CUDA(cudaMemcpyAsync(p, code_host, (size_t)n_seg * 4, cudaMemcpyHostToDevice, st));
-  p += align256((size_t)n_seg * 4);
-  tb.blk_start = reinterpret_cast<const int64_t*>(p);
-  PFC_CUDA(cudaMemcpyAsync(p, blk_host, (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
-  p += align256((size_t)(n_seg + 1) * 8);
-  tb.w = reinterpret_cast<const float*>(p);
-  PFC_CUDA(cudaMemcpyAsync(p, weights_host, (size_t)K * 4, cudaMemcpyHostToDevice, st));
+  tb.out = reinterpret_cast<float* const*>(p + off_out);
+  tb.len = reinterpret_cast<const int64_t*>(p + off_len);
+  tb.dtype = reinterpret_cast<const int32_t*>(p + off_code);
+  tb.blk_start = reinterpret_cast<const int64_t*>(p + off_blk);
+  tb.w = reinterpret_cast<const float*>(p + off_w);
+  PFC_CUDA(cudaMemcpyAsync(p, h, off_w + (size_t)K * 4, cudaMemcpyHostToDevice, st));
   int64_t grid = total;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (grid > cap) grid = cap;
@@ -205,8 +211,7 @@ int fedavg_weighted_sum(const void* const* seg_src_host, void* const* seg_out_ho
     fedavg_kernel<<<(int)grid, kFedThreads, 0, st>>>(tb, n_seg, K, k0, kc, total);
     PFC_LAUNCH_CHECK();
   }
-  // blk_host / code_host are reused by the next call on this thread: make sure the copies above have been consumed
-  PFC_CUDA(cudaStreamSynchronize(st));
+  PFC_CUDA(cudaEventRecord(slot.ev, st));          // the image (and the device table) are free again once this has passed
   return 0;
 }
 

@@ -54,7 +54,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // cluster-scope acquire variant (used when remote CTAs arrive on this barrier)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
+  uint32_t ok, spins = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -63,6 +63,10 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    if (!ok && ++spins == (1u << 26)) {
+      printf("fedfr_b200: cluster mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
   } while (!ok);
 }
 
@@ -168,6 +172,20 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 16 lanes x 32 columns of fp32 in the "quad per sector" layout (the mma.sync C-fragment layout): thread t of the warp
+// receives, for each of the 4 column chunks k (8 columns each), r[4k+0..1] = row (lane base + t/4), columns 8k + 2(t%4) + {0,1}
+// and r[4k+2..3] = row (lane base + 8 + t/4), same columns.  A quad of threads therefore holds 8 consecutive columns (32
+// bytes) of one row: stores from this layout write whole 32-byte sectors, no shared-memory transposition needed.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 
 // ---------------------------------------------------------------- 2-CTA (cta_group::2) variants
 // A CTA pair (cluster ranks 2k, 2k+1 on one TPC) issues ONE MMA of M = 256: each CTA supplies its 128 rows of A and half

@@ -1418,6 +1418,286 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
 }
 
 // ================================================================================================
+// dw4 kernel (E = 512): the dw GEMM + normalize backward on a cluster of FOUR CTAs = two cta_group::2 pairs.
+//   pair h (cluster ranks 2h, 2h+1) computes e-slice h (256 columns); the CTA of parity c in each pair owns class tile
+//   2g + c of the cluster's item g.  One tcgen05.mma covers M = 256 (both class tiles) x N = 256 (the e-slice), K = rows.
+// Why (measured, profiles/README.md r02a/b): the single-CTA kernel above is bound by shared-memory / L2->SM bytes per MMA
+// cycle, not by HBM or the tensor pipe -- 48 KB of operand fill per 512 MMA cycles plus the fp32 staging of the epilogue.
+//   * A = P^T tile [128 classes x 64 rows] is needed by the same-parity CTA of BOTH pairs: each loads one 64-class box and
+//     multicasts it to the other (8 KB from L2 per CTA per k-block instead of 16).
+//   * B = x_scaled: a cta_group::2 MMA takes HALF of the N columns from each CTA (128 e), so with Bt <= 512 the whole
+//     [512 rows x 128 e] operand (128 KB) stays RESIDENT in shared memory (STAT) -- no B traffic at all, where the old
+//     kernel re-streamed 256 KB per class tile; for larger batches the half is streamed (16 KB per k-block instead of 32).
+//   * MMA operand reads: 8 KB per 128-cycle MMA per CTA (cta_group::2) instead of 12 KB.
+//   * Epilogue without shared-memory staging: the accumulator is read with tcgen05.ld.16x256b, whose register layout puts
+//     8 consecutive columns of a row into a quad of threads, so dw leaves in full 32-byte sectors straight from registers
+//     (st.global.v2) and w_hat arrives by 4-byte loads in the same layout; the radial dot is reduced inside the quad, then
+//     over the four column-group warps and the two e-slice CTAs (DSMEM) exactly like the kernel above.
+// Barriers: TMA bytes (own + multicast from the partner CTA) are credited to every CTA's OWN full barrier; the non-leader
+// CTA of a pair relays "my operands have landed" to its leader (mbarrier remote arrive), which issues the MMAs; stage
+// release (tcgen05.commit) is multicast to all four CTAs because a stage is written by two of them.
+// ================================================================================================
+struct Dw4Params {
+  int n_rows, n_classes;
+  int n_rb;                      // row blocks of the P / G scratch
+  int n_tp;                      // pairs of class tiles = ceil(n_classes / 256)
+  const float* inv_norm;         // [n_classes]
+  const __nv_bfloat16* w_hat;    // [n_classes, 512]
+  float* dw;                     // [n_classes, 512]
+  int accumulate;
+  long long* dbg;
+};
+constexpr int kDw4EpiWarps = 16;                 // four per TMEM lane quadrant, 64 accumulator columns each
+constexpr int kDw4Threads = (kDw4EpiWarps + 2) * 32;
+constexpr int kDw4E = 512;
+
+template <bool STAT, int STAGES>
+__global__ void __launch_bounds__(kDw4Threads, 1) dw4_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                                                             const Dw4Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kABytes = 2 * kBoxBytes;                    // 128 classes x 64 rows
+  constexpr int kBBytes = 2 * kBoxBytes;                    // 64 rows x 128 e (this CTA's half of the e-slice)
+  constexpr int kStageBytes = kABytes + (STAT ? 0 : kBBytes);
+  constexpr int kMaxKb = 8;                                 // STAT: n_rows <= 512
+  uint8_t* smem_b = smem;                                   // STAT: [n_kb][2 boxes]
+  uint8_t* smem_st = smem + (STAT ? kMaxKb * kBBytes : 0);
+  float* tpart = reinterpret_cast<float*>(smem_st + STAGES * kStageBytes);     // [2][8 contributors][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tpart + 2 * 8 * 128);
+  uint64_t* full = bars;                          // [STAGES]  own + multicast bytes of this CTA's stage
+  uint64_t* empty = bars + STAGES;                // [STAGES]  2 arrivals: the commit of each pair's leader
+  uint64_t* peer_full = bars + 2 * STAGES;        // [STAGES]  leader only: the other CTA of the pair has its stage
+  uint64_t* tmem_full = bars + 3 * STAGES;        // [2]
+  uint64_t* tmem_empty = bars + 3 * STAGES + 2;   // [2]       leader only: epilogue warps of both CTAs
+  uint64_t* tbar = bars + 3 * STAGES + 4;         // [2][4]    partial dots of a lane quadrant: 4 warps x 2 e-slice CTAs
+  uint64_t* b_full = bars + 3 * STAGES + 12;
+  uint64_t* peer_b_full = bars + 3 * STAGES + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int hs = (int)(crank >> 1), cpar = (int)(crank & 1);      // e-slice of the pair, class-tile parity inside the pair
+  const bool leader = cpar == 0;
+  const uint32_t leader_rank = crank & ~1u, partner = crank ^ 2u;  // partner: same class tile, other e-slice
+  const int n_clusters = gridDim.x >> 2, cid = blockIdx.x >> 2;
+  const int n_kb = (p.n_rows + BK - 1) / BK;
+  constexpr int kProducerWarp = kDw4EpiWarps, kMmaWarp = kDw4EpiWarps + 1;
+  const uint16_t pair_mask = (uint16_t)(3u << (2 * hs));
+  const uint16_t a_mask = (uint16_t)((1u << cpar) | (1u << (cpar + 2)));
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); mbar_init(&peer_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kDw4EpiWarps); }
+    for (int i = 0; i < 8; ++i) mbar_init(&tbar[i], 8);
+    mbar_init(b_full, 1);
+    mbar_init(peer_b_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == kProducerWarp && lane == 0) { prefetch_tmap(&tmap_g); prefetch_tmap(&tmap_x); }
+  if (warp == kMmaWarp) tmem_alloc_2cta<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      const int e_half = hs * 256 + cpar * 128;               // this CTA's half of the pair's B operand
+      if (STAT) {
+        mbar_arrive_expect_tx(b_full, n_kb * kBBytes);
+        for (int kb = 0; kb < n_kb; ++kb)
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb) tma_load_2d(smem_b + kb * kBBytes + nb * kBoxBytes, &tmap_x, b_full, e_half + nb * 64, kb * BK);
+      }
+      PipeState ps;
+      for (int i = 0; i * n_clusters + cid < p.n_tp; ++i) {
+        const int ct = 2 * (i * n_clusters + cid) + cpar;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait_cluster(&empty[ps.stage], ps.phase ^ 1);
+          uint8_t* sa = smem_st + ps.stage * kStageBytes;
+          mbar_arrive_expect_tx(&full[ps.stage], kStageBytes);
+          // class half `hs` of the tile, for this CTA and its partner in the other pair
+          tma_load_2d_mc(sa + hs * kBoxBytes, &tmap_g, &full[ps.stage], 0, ((2 * ct + hs) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64, a_mask);
+          if (!STAT) {
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) tma_load_2d(sa + kABytes + nb * kBoxBytes, &tmap_x, &full[ps.stage], e_half + nb * 64, kb * BK);
+          }
+          ps.advance(STAGES);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, 256, true, true);
+      PipeState ps;
+      long long t_we = 0, t_wf = 0, t_all = clock64();
+      if (STAT) { mbar_wait(b_full, 0); mbar_wait_cluster(peer_b_full, 0); }
+      for (int it = 0; it * n_clusters + cid < p.n_tp; ++it) {
+        const int acc = it & 1;
+        long long c0 = clock64();
+        mbar_wait_cluster(&tmem_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+        t_we += clock64() - c0;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          c0 = clock64();
+          mbar_wait(&full[ps.stage], ps.phase);
+          mbar_wait_cluster(&peer_full[ps.stage], ps.phase);
+          t_wf += clock64() - c0;
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_st + ps.stage * kStageBytes);
+          const uint32_t b_addr = STAT ? smem_u32(smem_b + kb * kBBytes) : a_addr + kABytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t da = make_desc_sw128(a_addr + kk * 2048, kBoxBytes, 1024);
+            const uint64_t db = make_desc_sw128(b_addr + kk * 2048, kBoxBytes, 1024);
+            umma_bf16_ss_2cta(d_tmem, da, db, idesc, (kb | kk) != 0);
+          }
+          umma_commit_2cta(&empty[ps.stage], 0xF);          // the stage is written by CTAs of both pairs
+          ps.advance(STAGES);
+        }
+        umma_commit_2cta(&tmem_full[acc], pair_mask);
+      }
+      if (p.dbg && blockIdx.x == 0) { p.dbg[0] = t_we; p.dbg[1] = t_wf; p.dbg[2] = clock64() - t_all; }
+    } else if (lane == 0) {
+      // relay: tell the leader of this pair when this CTA's operands of a stage have landed
+      PipeState ps;
+      if (STAT) { mbar_wait(b_full, 0); mbar_arrive_remote(peer_b_full, leader_rank); }
+      for (int it = 0; it * n_clusters + cid < p.n_tp; ++it)
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&full[ps.stage], ps.phase);
+          mbar_arrive_remote(&peer_full[ps.stage], leader_rank);
+          ps.advance(STAGES);
+        }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: warp (quad, cg) owns classes [32 quad, +32) of the
+    // tile and accumulator columns [64 cg, +64).  Fragment layout of tcgen05.ld.16x256b: see tmem_ld_16x256b_x4.
+    const int quad = warp & 3, cg = warp >> 2;
+    const int lr = lane >> 2, lc = (lane & 3) * 2;
+    const int e0 = hs * 256 + cg * 64 + lc;                 // first e column of this thread
+    const int contrib = hs * 4 + cg;
+    const uint32_t tmem_leader_empty0 = mapa_u32(smem_u32(&tmem_empty[0]), leader_rank);
+    for (int it = 0; it * n_clusters + cid < p.n_tp; ++it) {
+      const int ct = 2 * (it * n_clusters + cid) + cpar;
+      const int acc = it & 1, buf = it & 1;
+      // rows of this thread: 32 quad + 16 hl + 8 j + lr
+      uint32_t wreg[2][2][8];
+      float inv[2][2];
+#pragma unroll
+      for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int cls = ct * BM + quad * 32 + hl * 16 + j * 8 + lr;
+          const bool ok = cls < p.n_classes;
+          const uint32_t* wp = reinterpret_cast<const uint32_t*>(p.w_hat + (int64_t)cls * kDw4E + e0);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) wreg[hl][j][k] = ok ? __ldg(wp + 4 * k) : 0u;
+          inv[hl][j] = ok ? __ldg(p.inv_norm + cls) : 0.f;
+        }
+      mbar_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      // ---- pass 1: partial dots w_hat_j . acc_j over this thread's columns
+      float dot[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+      for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+        for (int c4 = 0; c4 < 2; ++c4) {
+          uint32_t v[16];
+          tmem_ld_16x256b_x4(tmem_base + ((uint32_t)(quad * 32 + hl * 16) << 16) + acc * 256 + cg * 64 + c4 * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t w0 = wreg[hl][0][c4 * 4 + kk], w1 = wreg[hl][1][c4 * 4 + kk];
+            dot[hl][0] = fmaf(__uint_as_float(v[4 * kk + 0]), __uint_as_float(w0 << 16), dot[hl][0]);
+            dot[hl][0] = fmaf(__uint_as_float(v[4 * kk + 1]), __uint_as_float(w0 & 0xffff0000u), dot[hl][0]);
+            dot[hl][1] = fmaf(__uint_as_float(v[4 * kk + 2]), __uint_as_float(w1 << 16), dot[hl][1]);
+            dot[hl][1] = fmaf(__uint_as_float(v[4 * kk + 3]), __uint_as_float(w1 & 0xffff0000u), dot[hl][1]);
+          }
+        }
+#pragma unroll
+      for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          dot[hl][j] += __shfl_xor_sync(0xffffffffu, dot[hl][j], 1);
+          dot[hl][j] += __shfl_xor_sync(0xffffffffu, dot[hl][j], 2);
+        }
+      // ---- exchange: 8 contributors per class row (4 column-group warps x 2 e-slice CTAs), summed in a fixed order
+      if ((lane & 3) == 0) {
+#pragma unroll
+        for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            float* slot = tpart + (buf * 8 + contrib) * 128 + quad * 32 + hl * 16 + j * 8 + lr;
+            *slot = dot[hl][j];
+            st_cluster_f32(mapa_u32(smem_u32(slot), partner), dot[hl][j]);
+          }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&tbar[buf * 4 + quad]);
+        mbar_arrive_remote(&tbar[buf * 4 + quad], partner);
+      }
+      mbar_wait_cluster(&tbar[buf * 4 + quad], (uint32_t)((it >> 1) & 1));
+      float c1[2][2];
+#pragma unroll
+      for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float* all = tpart + buf * 8 * 128 + quad * 32 + hl * 16 + j * 8 + lr;
+          float t = all[0];
+#pragma unroll
+          for (int c = 1; c < 8; ++c) t += all[c * 128];
+          c1[hl][j] = -t * inv[hl][j];
+        }
+      // ---- pass 2: dw = acc * inv_norm - w_hat * (t * inv_norm), straight from registers in full 32-byte sectors
+#pragma unroll
+      for (int hl = 0; hl < 2; ++hl) {
+        const int cls_a = ct * BM + quad * 32 + hl * 16 + lr, cls_b = cls_a + 8;
+        float* oa = p.dw + (int64_t)cls_a * kDw4E + e0;
+        float* ob = p.dw + (int64_t)cls_b * kDw4E + e0;
+        const bool ok_a = cls_a < p.n_classes, ok_b = cls_b < p.n_classes;
+#pragma unroll
+        for (int c4 = 0; c4 < 2; ++c4) {
+          uint32_t v[16];
+          tmem_ld_16x256b_x4(tmem_base + ((uint32_t)(quad * 32 + hl * 16) << 16) + acc * 256 + cg * 64 + c4 * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int k = c4 * 4 + kk;
+            const uint32_t w0 = wreg[hl][0][k], w1 = wreg[hl][1][k];
+            float2 ra, rb;
+            ra.x = fmaf(__uint_as_float(w0 << 16), c1[hl][0], __uint_as_float(v[4 * kk + 0]) * inv[hl][0]);
+            ra.y = fmaf(__uint_as_float(w0 & 0xffff0000u), c1[hl][0], __uint_as_float(v[4 * kk + 1]) * inv[hl][0]);
+            rb.x = fmaf(__uint_as_float(w1 << 16), c1[hl][1], __uint_as_float(v[4 * kk + 2]) * inv[hl][1]);
+            rb.y = fmaf(__uint_as_float(w1 & 0xffff0000u), c1[hl][1], __uint_as_float(v[4 * kk + 3]) * inv[hl][1]);
+            if (ok_a) {
+              float2* d = reinterpret_cast<float2*>(oa + 8 * k);
+              if (p.accumulate) { const float2 o = *d; ra.x += o.x; ra.y += o.y; }
+              *d = ra;
+            }
+            if (ok_b) {
+              float2* d = reinterpret_cast<float2*>(ob + 8 * k);
+              if (p.accumulate) { const float2 o = *d; rb.x += o.x; rb.y += o.y; }
+              *d = rb;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_cluster_addr_relaxed(tmem_leader_empty0 + acc * 8);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == kMmaWarp) tmem_dealloc_2cta<512>(tmem_base);
+}
+
+// ================================================================================================
 // Stored-probability backward (MODE_PROB forward): the forward kept P_ij = exp2(s2 cos_ij - a_i) (bf16, blocked
 // scratch, target column zero), so   G_ij = scale_i P_ij   with   scale_i = s / (S_i Bt)   (S_i = global sum of P_i.)
 // and no logits are recomputed:
@@ -1767,6 +2047,51 @@ static int launch_dw(const CUtensorMap& tg, const CUtensorMap& tx, const CUtenso
     }
     return launch_dw_cs<EMB, 1>(tg, tx, twh, tdw, p, grid, st);
   }
+}
+
+static int g_dw4 = 0;                                // 1: 4-CTA-cluster dw4 kernel for E = 512 (opt-in, pfc_set_dw4); 0: the e-split pair kernel
+template <bool STAT, int STAGES>
+static size_t dw4_smem_bytes() {
+  return (size_t)(STAT ? 8 * 2 * kBoxBytes : 0) + (size_t)STAGES * (2 * kBoxBytes + (STAT ? 0 : 2 * kBoxBytes)) + 2 * 8 * 128 * 4 + 1024 + 1024;
+}
+constexpr int kDw4StagesStat = 5, kDw4StagesStream = 6;
+static bool dw4_stationary(int64_t n_rows) { return n_rows <= 512; }
+// clusters that can be resident at once (GPC packing of 4-CTA clusters leaves a few SMs unused); cached per variant
+static int dw4_resident_clusters(bool stat) {
+  static int cached[2] = {0, 0};
+  if (cached[stat]) return cached[stat];
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(4 * 64);
+  cfg.blockDim = dim3(kDw4Threads);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  cudaError_t e;
+  if (stat) {
+    cfg.dynamicSmemBytes = dw4_smem_bytes<true, kDw4StagesStat>();
+    cudaFuncSetAttribute(dw4_kernel<true, kDw4StagesStat>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+    e = cudaOccupancyMaxActiveClusters(&n, dw4_kernel<true, kDw4StagesStat>, &cfg);
+  } else {
+    cfg.dynamicSmemBytes = dw4_smem_bytes<false, kDw4StagesStream>();
+    cudaFuncSetAttribute(dw4_kernel<false, kDw4StagesStream>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+    e = cudaOccupancyMaxActiveClusters(&n, dw4_kernel<false, kDw4StagesStream>, &cfg);
+  }
+  if (e != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = sm_count() / 4 * 9 / 10; }
+  cached[stat] = n;
+  return n;
+}
+
+static int launch_dw4(const CUtensorMap& tg, const CUtensorMap& tx, const Dw4Params& p, int sms, cudaStream_t st) {
+  const bool stat = dw4_stationary(p.n_rows);
+  int clusters = sms / 4;
+  const int cap = dw4_resident_clusters(stat);
+  if (clusters > cap) clusters = cap;
+  if (clusters > p.n_tp) clusters = p.n_tp;
+  if (clusters < 1) clusters = 1;
+  if (stat) return launch_cluster_threads(dw4_kernel<true, kDw4StagesStat>, kDw4Threads, clusters * 4, 4, dw4_smem_bytes<true, kDw4StagesStat>(), st, tg, tx, p);
+  return launch_cluster_threads(dw4_kernel<false, kDw4StagesStream>, kDw4Threads, clusters * 4, 4, dw4_smem_bytes<false, kDw4StagesStream>(), st, tg, tx, p);
 }
 
 // side streams of the pipelined backward (per device)
@@ -2247,34 +2572,55 @@ static int tc_bwd_prob_enqueue(const void* w_hat, const float* inv_norm, const i
   if (paced) dp.sweep = SweepSync{sweep_ctr, sweep_ctr + 1, g_sweep_lead};
   dp.n_rows = (int)n_rows; dp.n_classes = (int)n_classes; dp.emb = emb; dp.n_rb = n_rb; dp.n_eh = pl.n_eh; dp.ksplit = pl.ksplit;
   dp.dx_part = dx_part; dp.accumulate = 0; dp.prefetch = g_prefetch[1]; dp.strided = pl.side_by_side ? 1 : 0;
-  int rc = 0;
   static const int exp_mode = getenv("FEDFR_EXP") ? atoi(getenv("FEDFR_EXP")) : 0;      // timing experiments only (wrong results)
-  prof_begin(PH_DX, sX);
-  if (exp_mode == 3) rc = 0;                   // dw alone
-  else if (pl.dx_pair) rc = launch_dx2(tg_k, tw_mn, dp, pl.dx_ctas, sX);
-  else switch (pl.dx_bn) {
-    case 256: rc = launch_dx<256>(tg_k, tw_mn, dp, pl.dx_ctas, pl.dcs, sX); break;
-    case 128: rc = launch_dx<128>(tg_k, tw_mn, dp, pl.dx_ctas, pl.dcs, sX); break;
-    default: rc = launch_dx<64>(tg_k, tw_mn, dp, pl.dx_ctas, pl.dcs, sX); break;
+  auto enqueue_dx = [&]() -> int {
+    int rc = 0;
+    prof_begin(PH_DX, sX);
+    if (exp_mode == 3) rc = 0;                   // dw alone
+    else if (pl.dx_pair) rc = launch_dx2(tg_k, tw_mn, dp, pl.dx_ctas, sX);
+    else switch (pl.dx_bn) {
+      case 256: rc = launch_dx<256>(tg_k, tw_mn, dp, pl.dx_ctas, pl.dcs, sX); break;
+      case 128: rc = launch_dx<128>(tg_k, tw_mn, dp, pl.dx_ctas, pl.dcs, sX); break;
+      default: rc = launch_dx<64>(tg_k, tw_mn, dp, pl.dx_ctas, pl.dcs, sX); break;
+    }
+    if (rc) return rc;
+    prof_end(PH_DX, sX);
+    return 0;
+  };
+  const bool use_dw4 = emb == 512 && g_dw4;
+  auto enqueue_dw = [&]() -> int {
+    int rc = 0;
+    DwParams wp{};
+    if (paced) wp.sweep = SweepSync{sweep_ctr + 1, sweep_ctr, g_sweep_lead};
+    wp.n_rows = (int)n_rows; wp.n_classes = (int)n_classes; wp.emb = emb; wp.n_ct = (int)((n_classes + BM - 1) / BM); wp.n_rb = n_rb;
+    wp.inv_norm = inv_norm; wp.accumulate = accumulate_dw; wp.dbg = g_dbg; wp.prefetch = g_prefetch[2];
+    static const int dw_exp = getenv("FEDFR_DW_EXP") ? atoi(getenv("FEDFR_DW_EXP")) : 0;
+    wp.exp = dw_exp;
+    prof_begin(PH_DW, sW);
+    if (exp_mode == 4) rc = 0;                   // dx alone
+    else if (use_dw4) {
+      Dw4Params qp{};
+      qp.n_rows = (int)n_rows; qp.n_classes = (int)n_classes; qp.n_rb = n_rb; qp.n_tp = (int)((n_classes + 255) / 256);
+      qp.inv_norm = inv_norm; qp.w_hat = wh; qp.dw = dw; qp.accumulate = accumulate_dw; qp.dbg = g_dbg;
+      rc = launch_dw4(tg_mn, tx_mn, qp, pl.sm_dw, sW);
+    } else switch (emb) {
+      case 512: rc = launch_dw<512>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
+      case 256: rc = launch_dw<256>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
+      case 128: rc = launch_dw<128>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
+      default: rc = launch_dw<64>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
+    }
+    if (rc) return rc;
+    prof_end(PH_DW, sW);
+    return 0;
+  };
+  // the 4-CTA clusters of dw4 are placed first (they need four free SMs of one GPC), the dx pairs fill what is left
+  if (use_dw4) {
+    if (int rc = enqueue_dw()) return rc;
+    if (int rc = enqueue_dx()) return rc;
+  } else {
+    if (int rc = enqueue_dx()) return rc;
+    if (int rc = enqueue_dw()) return rc;
   }
-  if (rc) return rc;
-  prof_end(PH_DX, sX);
-  DwParams wp{};
-  if (paced) wp.sweep = SweepSync{sweep_ctr + 1, sweep_ctr, g_sweep_lead};
-  wp.n_rows = (int)n_rows; wp.n_classes = (int)n_classes; wp.emb = emb; wp.n_ct = (int)((n_classes + BM - 1) / BM); wp.n_rb = n_rb;
-  wp.inv_norm = inv_norm; wp.accumulate = accumulate_dw; wp.dbg = g_dbg; wp.prefetch = g_prefetch[2];
-  static const int dw_exp = getenv("FEDFR_DW_EXP") ? atoi(getenv("FEDFR_DW_EXP")) : 0;
-  wp.exp = dw_exp;
-  prof_begin(PH_DW, sW);
-  if (exp_mode == 4) rc = 0;                   // dx alone
-  else switch (emb) {
-    case 512: rc = launch_dw<512>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
-    case 256: rc = launch_dw<256>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
-    case 128: rc = launch_dw<128>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
-    default: rc = launch_dw<64>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
-  }
-  if (rc) return rc;
-  prof_end(PH_DW, sW);
   if (pl.side_by_side) {
     PFC_EDGE(sX, st);
     PFC_EDGE(sW, st);
@@ -2302,7 +2648,7 @@ int tc_bwd_prob(const void* x, const void* w_hat, const float* inv_norm, const i
   kb.add(4).add(x).add(w_hat).add(inv_norm).add(label).add(row_sum).add(dx).add(dw).add(workspace).add(prob_ws).add(n_rows).add(n_classes)
       .add(workspace_bytes).add(emb).add(accumulate_dw).add(s).add(m).add(margin_kind).add(inv_total_batch).add(g_logits_pair).add(g_dx_cluster)
       .add(g_dw_cluster).add(g_prob_dx_sms).add(g_prob_dw_rate).add(g_sweep_lead).add(g_prefetch[1]).add(g_prefetch[2]).add(g_dx_pair)
-      .add(range_flag_of_current_device());
+      .add(range_flag_of_current_device()).add(g_dw4);
   if (kb.overflow) return enqueue(st);
   return run_cached_graph(kb, st, enqueue);
 }
@@ -2406,6 +2752,7 @@ int tc_set_range_flag(int* flag, float limit_nats) {
   return 0;
 }
 void tc_set_graph(int on) { g_use_graph = on ? 1 : 0; }
+void tc_set_dw4(int on) { g_dw4 = on ? 1 : 0; }
 void tc_set_dx_pair(int on) { g_dx_pair = on ? 1 : 0; }
 void tc_set_prefetch(int logits, int dx, int dw) { g_prefetch[0] = logits; g_prefetch[1] = dx; g_prefetch[2] = dw; }
 void tc_set_pipeline(int on, int sm_g, int sm_dx, int sm_dw, int ring) {

@@ -93,6 +93,8 @@ class PartialFC(Module):
         self._range_slot = None
         self._prenorm = None    # (w_hat, inv_norm, weight ptr, weight version) left behind by step(prenormalize=True)
         self._label_buf = None
+        self._bufs = {}
+        self._flat_collectives = self._flat_rs = self._coalesce = None      # None = untried, True / False = backend support
 
     # ------------------------------------------------------------------ shard I/O (partial_fc.py:71-87)
     def save_params(self):
@@ -209,26 +211,80 @@ class PartialFC(Module):
         self._range_slot = n % 4
 
     # ------------------------------------------------------------------ collectives
+    def _buffer(self, name, shape, dtype):
+        """Step scratch with a stable address (gather targets are arguments of the replayed forward / backward graphs)."""
+        key = (name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
     def _all_gather(self, out, inp):
+        """out [W * n, ...] <- the W ranks' inp [n, ...] in rank order: ONE collective on the flat tensor (no per-rank chunk
+        lists); backends without all_gather_into_tensor get the list form."""
         if self.world_size == 1:
             out.copy_(inp.reshape(out.shape))
-        else:
-            dist.all_gather(list(out.chunk(self.world_size, dim=0)), inp)
+            return
+        if self._flat_collectives is not False:
+            try:
+                dist.all_gather_into_tensor(out, inp.contiguous())
+                self._flat_collectives = True
+                return
+            except (RuntimeError, NotImplementedError, AttributeError):
+                if self._flat_collectives:
+                    raise
+                self._flat_collectives = False
+        dist.all_gather(list(out.chunk(self.world_size, dim=0)), inp)
+
+    def _all_gather_pair(self, out_a, in_a, out_b, in_b):
+        """The label gather (partial_fc.py:122) and the feature gather (:134) as ONE NCCL group launch: they have no
+        dependence on each other and are latency bound at these sizes."""
+        if self.world_size > 1 and self.device.type == "cuda" and self._coalesce is not False:
+            try:
+                with dist._coalescing_manager(device=self.device):
+                    dist.all_gather_into_tensor(out_a, in_a)
+                    dist.all_gather_into_tensor(out_b, in_b)
+                self._coalesce = True
+                return
+            except (RuntimeError, NotImplementedError, AttributeError, ValueError):
+                if self._coalesce:
+                    raise
+                self._coalesce = False
+        self._all_gather(out_a, in_a)
+        self._all_gather(out_b, in_b)
+
+    def _reduce_scatter(self, out, inp):
+        if self._flat_rs is not False:
+            try:
+                dist.reduce_scatter_tensor(out, inp)
+                self._flat_rs = True
+                return
+            except (RuntimeError, NotImplementedError, AttributeError):
+                if self._flat_rs:
+                    raise
+                self._flat_rs = False
+        dist.reduce_scatter(out, list(inp.chunk(self.world_size, dim=0)))
+
+    def _rewire(self, optimizer):
+        """partial_fc.py:124-126: the optimizer's last param group follows ``sub_weight`` and its momentum buffer."""
+        optimizer.state.pop(optimizer.param_groups[-1]['params'][0], None)
+        optimizer.param_groups[-1]['params'][0] = self.sub_weight
+        optimizer.state[self.sub_weight]['momentum_buffer'] = self.sub_weight_mom
 
     @torch.no_grad()
     def prepare(self, label, optimizer, _defer_normalize=False):
         """partial_fc.py:118-128: gather labels, sample, rewire the optimizer onto ``sub_weight`` and its
         momentum buffer, normalise the sub-shard.  Returns ``(total_label, norm_weight)``.
-        (``forward_backward`` defers the normalisation: it is fused with the logits kernel.)"""
+        (``forward_backward`` gathers labels and features together and defers the normalisation: it is fused with the
+        logits kernel.)"""
         if self.world_size == 1:        # nothing to gather: the copy the reference's sample() mutates in place
             total_label = label.to(self.device, dtype=torch.long, copy=True)
         else:
             total_label = torch.zeros(size=[self.batch_size * self.world_size], device=self.device, dtype=torch.long)
-            self._all_gather(total_label, label.to(self.device))
+            self._all_gather(total_label, label.to(self.device, dtype=torch.long))
         self.sample(total_label)
-        optimizer.state.pop(optimizer.param_groups[-1]['params'][0], None)
-        optimizer.param_groups[-1]['params'][0] = self.sub_weight
-        optimizer.state[self.sub_weight]['momentum_buffer'] = self.sub_weight_mom
+        self._rewire(optimizer)
         if _defer_normalize:
             return total_label, None
         self._norm = self._ops.normalize(self.sub_weight.data)
@@ -245,17 +301,27 @@ class PartialFC(Module):
         ops = self._ops
         fused = hasattr(ops, "normalize_fwd_stats")
         self._check_logit_range(features)
-        total_label, w_hat = self.prepare(label, optimizer, _defer_normalize=fused)
-        if self._label_buf is None or self._label_buf.shape != total_label.shape:
-            self._label_buf = torch.empty_like(total_label)
-        self._label_buf.copy_(total_label)          # stable address for the replayed backward graph
-        total_label = self._label_buf
-        if W == 1:                      # nothing to gather (partial_fc.py:132-134 with one rank is a copy): read the features in place
-            total_features = features.data.to(device=self.device, dtype=torch.float32).contiguous()
+        w_hat = None
+        if W == 1:
+            total_label, w_hat = self.prepare(label, optimizer, _defer_normalize=fused)
+            if self._label_buf is None or self._label_buf.shape != total_label.shape:
+                self._label_buf = torch.empty_like(total_label)
+            self._label_buf.copy_(total_label)          # stable address for the replayed backward graph
+            total_label = self._label_buf
+            # nothing to gather (partial_fc.py:132-134 with one rank is a copy): read the features in place
+            x_hat = ops.cast_features(features.data.to(device=self.device, dtype=torch.float32).contiguous())
         else:
-            total_features = torch.zeros(size=[B * W, E], device=self.device)
-            self._all_gather(total_features, features.data.to(torch.float32))
-        x_hat = ops.cast_features(total_features)
+            # partial_fc.py:120-122 and :132-134 in one group launch.  The features travel as the operand the kernels
+            # consume (bf16 on the tensor path: cast(gather(x)) == gather(cast(x)), half the bytes), into step scratch
+            x_loc = ops.cast_features(features.data.to(device=self.device, dtype=torch.float32).contiguous())
+            total_label = self._buffer("total_label", (B * W,), torch.long)
+            x_hat = self._buffer("x_hat_total", (B * W, E), x_loc.dtype)
+            self._all_gather_pair(total_label, label.to(self.device, dtype=torch.long).contiguous(), x_hat, x_loc)
+            self.sample(total_label)
+            self._rewire(optimizer)
+            if not fused:
+                self._norm = ops.normalize(self.sub_weight.data)
+                w_hat = self._norm[0]
 
         # forward: per-shard (max, sum-exp, target logit), then one exchange instead of three all-reduces
         pre = self._prenorm
@@ -273,8 +339,8 @@ class PartialFC(Module):
         if W == 1:
             gathered = stats.unsqueeze(0)
         else:
-            gathered = torch.empty((W,) + tuple(stats.shape), dtype=stats.dtype, device=self.device)
-            dist.all_gather(list(gathered.unbind(0)), stats)
+            gathered = self._buffer("stats_all", (W,) + tuple(stats.shape), stats.dtype)
+            self._all_gather(gathered.view(W * stats.shape[0], stats.shape[1]), stats)
         row_max, row_sum, loss_v = ops.finalize(gathered)
 
         # backward: dx partial of this shard + sub_weight.grad
@@ -290,7 +356,7 @@ class PartialFC(Module):
         if W == 1:
             x_grad = dx_total.clone()               # dx_total is step scratch with a stable address
         else:
-            x_grad = torch.zeros_like(features, dtype=torch.float32, device=self.device)
-            dist.reduce_scatter(x_grad, list(dx_total.chunk(W, dim=0)))
-            x_grad = x_grad * W                     # partial_fc.py:174
+            x_grad = torch.empty((B, E), dtype=torch.float32, device=self.device)
+            self._reduce_scatter(x_grad, dx_total)  # partial_fc.py:171-173
+            x_grad.mul_(W)                          # partial_fc.py:174
         return x_grad, loss_v

@@ -167,6 +167,11 @@ static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t
 template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = (T*)malloc(n); return *p ? 0 : 2; }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+typedef void* cudaEvent_t;
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (void*)1; return 0; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 

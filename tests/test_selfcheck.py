@@ -42,7 +42,7 @@ def test_reference_step_matches_oracle(margin, s, m):
     # same roundings, fp32 vs fp64 GEMMs in between: a few bf16 roundings flip to the other neighbour (one ulp = 2^-8 on a
     # row dominated by that element), nothing systematic (rms over the rows far below)
     for got_t, ref_t in ((gotb["dx_total"], refb.x_grad[0]), (gotb["dw"], refb.dw[0])):
-        assert SC._rows_err(got_t, ref_t) < 6e-3 and SC._rows_err(got_t, ref_t, rms=True) < 1e-3
+        assert SC._rows_err(got_t, ref_t) < 1e-2 and SC._rows_err(got_t, ref_t, rms=True) < 1e-3
     # and the emulation stays within the bf16 tolerance of the exact arithmetic
     assert rel(refb.x_grad[0], ref.x_grad[0]) < 1e-2 and rel(refb.dw[0], ref.dw[0]) < 1e-2
 

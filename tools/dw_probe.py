@@ -17,6 +17,8 @@ x_hat = ops.cast_features(x)
 dw = torch.empty_like(w)
 dbg = torch.zeros(16, dtype=torch.int64, device=dev)
 N.lib.pfc_set_debug_buffer.argtypes = [C.c_void_p]
+if os.environ.get("PROBE_DX_SMS"):          # SM budget of the dx kernel; dw gets the rest (set PROBE_CLUSTERS = (148 - dx_sms) / 2)
+    N.lib.pfc_set_prob_split(int(os.environ["PROBE_DX_SMS"]), 0.0, -1)
 
 
 def step():
