@@ -85,7 +85,7 @@ lib.pfc_set_pipeline.restype = _i32
 lib.pfc_set_pipeline.argtypes = [_i32, _i32, _i32, _i32, _i32]
 lib.pfc_set_prob_split.restype = _i32
 lib.pfc_set_prob_split.argtypes = [_i32, _f32, _i32]
-for _knob in ("pfc_set_dw4", "pfc_set_dx_pair", "pfc_set_graph", "pfc_set_chunk_mb", "pfc_set_logits_pair", "pfc_set_roc_mode"):
+for _knob in ("pfc_set_nvtx", "pfc_set_dw4", "pfc_set_dx_pair", "pfc_set_graph", "pfc_set_chunk_mb", "pfc_set_logits_pair", "pfc_set_roc_mode"):
     getattr(lib, _knob).restype = _i32
     getattr(lib, _knob).argtypes = [_i32]
 

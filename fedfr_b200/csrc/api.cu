@@ -60,6 +60,7 @@ int pfc_fwd_num_partials(int64_t n_rows, int64_t n_classes, int emb, int path) {
 int pfc_fwd_stats(const void* x, const void* w_hat, const int64_t* label, int64_t n_rows, int64_t n_classes, int emb, float s, float m, int margin_kind,
                   float* part_max, float* part_sum, float* target_logit, int path, void* stream) {
   if (int rc = require_sm100()) return rc;
+  NvtxScope nvtx_scope("pfc_fwd_stats");
   PFC_REQUIRE(x && w_hat && label && part_max && part_sum && target_logit, PFC_E_ARG, "pfc_fwd_stats: null argument");
   PFC_REQUIRE(n_rows > 0 && n_classes > 0 && emb > 0, PFC_E_ARG, "pfc_fwd_stats: empty shape (rows=%lld classes=%lld)", (long long)n_rows,
               (long long)n_classes);
@@ -74,6 +75,7 @@ int pfc_normalize_fwd_stats(const float* w, const int64_t* index, const void* x,
                             float s, float m, int margin_kind, void* w_hat, float* inv_norm, float* part_max, float* part_sum, float* target_logit, int path,
                             void* stream) {
   if (int rc = require_sm100()) return rc;
+  NvtxScope nvtx_scope("pfc_normalize_fwd_stats");
   PFC_REQUIRE(w && x && w_hat && inv_norm && label && part_max && part_sum && target_logit, PFC_E_ARG, "pfc_normalize_fwd_stats: null argument");
   PFC_REQUIRE(n_rows > 0 && n_classes > 0 && emb > 0, PFC_E_ARG, "pfc_normalize_fwd_stats: empty shape (rows=%lld classes=%lld)",
               (long long)n_rows, (long long)n_classes);
@@ -98,6 +100,7 @@ int pfc_normalize_fwd_prob(const float* w, const int64_t* index, const void* x, 
                            float s, float m, int margin_kind, void* w_hat, float* inv_norm, float* part_max, float* part_sum, float* target_logit,
                            void* prob_ws, size_t prob_ws_bytes, void* stream) {
   if (int rc = require_sm100()) return rc;
+  NvtxScope nvtx_scope("pfc_normalize_fwd_prob");
   PFC_REQUIRE(x && w_hat && inv_norm && label && part_max && part_sum && target_logit && prob_ws, PFC_E_ARG, "pfc_normalize_fwd_prob: null argument");
   PFC_REQUIRE(n_rows > 0 && n_classes > 0 && emb > 0, PFC_E_ARG, "pfc_normalize_fwd_prob: empty shape (rows=%lld classes=%lld)", (long long)n_rows,
               (long long)n_classes);
@@ -114,6 +117,7 @@ int pfc_bwd_prob(const void* x, const void* w_hat, const float* inv_norm, const 
                  int emb, float s, float m, int margin_kind, float inv_total_batch, float* dx, float* dw, int accumulate_dw, void* prob_ws,
                  size_t prob_ws_bytes, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = require_sm100()) return rc;
+  NvtxScope nvtx_scope("pfc_bwd_prob");
   PFC_REQUIRE(x && w_hat && inv_norm && label && row_sum && dx && dw && prob_ws && workspace, PFC_E_ARG, "pfc_bwd_prob: null argument");
   PFC_REQUIRE(n_rows > 0 && n_classes > 0 && emb > 0, PFC_E_ARG, "pfc_bwd_prob: empty shape");
   return tc_bwd_prob(x, w_hat, inv_norm, label, row_sum, n_rows, n_classes, emb, s, m, margin_kind, inv_total_batch, dx, dw, accumulate_dw, prob_ws,
@@ -135,6 +139,7 @@ size_t pfc_spreadout_workspace_bytes(int64_t n, int emb) {
 int pfc_spreadout(const void* w_hat, int64_t n, int emb, float margin, float* part_max, float* part_sum, float* hw_out, void* workspace,
                   size_t workspace_bytes, void* stream) {
   if (int rc = require_sm100()) return rc;
+  NvtxScope nvtx_scope("pfc_spreadout");
   PFC_REQUIRE(w_hat && part_max && part_sum && hw_out && workspace, PFC_E_ARG, "pfc_spreadout: null argument");
   PFC_REQUIRE(n > 0 && emb > 0, PFC_E_ARG, "pfc_spreadout: empty shape");
   return tc_spreadout(w_hat, n, emb, margin, part_max, part_sum, hw_out, workspace, workspace_bytes, as_stream(stream));
@@ -154,6 +159,7 @@ int pfc_bwd(const void* x, const void* w_hat, const float* inv_norm, const int64
             int64_t n_rows, int64_t n_classes, int emb, float s, float m, int margin_kind, float inv_total_batch, float* dx, float* dw, int accumulate_dw,
             void* workspace, size_t workspace_bytes, int path, void* stream) {
   if (int rc = require_sm100()) return rc;
+  NvtxScope nvtx_scope("pfc_bwd");
   PFC_REQUIRE(x && w_hat && inv_norm && label && row_max && row_sum && dx && dw && workspace, PFC_E_ARG, "pfc_bwd: null argument");
   PFC_REQUIRE(n_rows > 0 && n_classes > 0 && emb > 0, PFC_E_ARG, "pfc_bwd: empty shape");
   if (path == PFC_PATH_CHECK)

@@ -46,6 +46,14 @@ bool prof_enabled();
     }                                                                                  \
   } while (0)
 
+// NVTX range around a C-ABI entry (host side, for nsys / ncu timelines).  Off unless FEDFR_NVTX=1 or pfc_set_nvtx(1).
+void nvtx_push(const char* name);
+void nvtx_pop();
+struct NvtxScope {
+  explicit NvtxScope(const char* name) { nvtx_push(name); }
+  ~NvtxScope() { nvtx_pop(); }
+};
+
 // Checks once per process that the current device is compute capability 10.x.
 int require_sm100();
 int sm_count();

@@ -137,6 +137,7 @@ size_t fedavg_table_bytes(int n_seg, int K) {
 int fedavg_weighted_sum(const void* const* seg_src_host, void* const* seg_out_host, const int64_t* seg_len_host, const int32_t* seg_dtype_host,
                         int n_seg, const float* weights_host, int K, void* table_dev, size_t table_bytes, void* stream) {
   if (int rc = require_sm100()) return rc;
+  NvtxScope nvtx_scope("fedavg_weighted_sum");
   PFC_REQUIRE(seg_src_host && seg_out_host && seg_len_host && seg_dtype_host && weights_host && table_dev, PFC_E_ARG, "fedavg_weighted_sum: null argument");
   PFC_REQUIRE(n_seg > 0 && K > 0, PFC_E_SHAPE, "fedavg_weighted_sum: need K >= 1 clients (got %d) and n_seg > 0", K);
   PFC_REQUIRE(table_bytes >= fedavg_table_bytes(n_seg, K), PFC_E_WORKSPACE, "fedavg_weighted_sum: table buffer too small");

@@ -191,6 +191,7 @@ extern "C" {
 int pfc_normalize_rows(const float* w, const int64_t* index, int64_t n_rows, int emb, void* w_hat_bf16, float* w_hat_f32,
                        float* inv_norm, void* stream) {
   if (int rc = require_sm100()) return rc;
+  NvtxScope nvtx_scope("pfc_normalize_rows");
   cudaStream_t st = as_stream(stream);
   prof_begin(PH_NORMALIZE, st);
   if (int rc = launch_normalize_rows(w, index, n_rows, emb, reinterpret_cast<__nv_bfloat16*>(w_hat_bf16), w_hat_f32, inv_norm, 0, st)) return rc;
@@ -201,6 +202,7 @@ int pfc_normalize_rows(const float* w, const int64_t* index, int64_t n_rows, int
 int pfc_sgd_step(float* weight, float* weight_mom, const float* grad, const int64_t* index, int64_t n_rows, int emb, float lr, float momentum,
                  float dampening, float weight_decay, int nesterov, void* w_hat_bf16, float* inv_norm, void* stream) {
   if (int rc = require_sm100()) return rc;
+  NvtxScope nvtx_scope("pfc_sgd_step");
   PFC_REQUIRE(weight && weight_mom && grad && n_rows >= 0 && emb > 0, PFC_E_ARG, "pfc_sgd_step: bad argument");
   PFC_REQUIRE(emb % 4 == 0 && emb <= 2048, PFC_E_SHAPE, "pfc_sgd_step: emb=%d must be a multiple of 4 and <= 2048", emb);
   PFC_REQUIRE(!(index && (w_hat_bf16 || inv_norm)), PFC_E_ARG, "pfc_sgd_step: the normalised output is for unsampled steps (index == NULL)");
@@ -236,6 +238,7 @@ int pfc_cast_rows_bf16(const float* x, int64_t n_rows, int emb, void* x_bf16, vo
 int pfc_gather_rows2(const float* weight, const float* weight_mom, const int64_t* index, int64_t n_index, int emb,
                      float* sub_weight, float* sub_weight_mom, void* stream) {
   if (int rc = require_sm100()) return rc;
+  NvtxScope nvtx_scope("pfc_gather_rows2");
   PFC_REQUIRE(weight && index && sub_weight && n_index >= 0 && emb > 0 && emb % 4 == 0, PFC_E_ARG, "pfc_gather_rows2: bad argument");
   if (n_index == 0) return 0;
   move_rows2_kernel<true><<<row_grid(n_index), 256, 0, as_stream(stream)>>>(const_cast<float*>(weight), const_cast<float*>(weight_mom), index,
@@ -247,6 +250,7 @@ int pfc_gather_rows2(const float* weight, const float* weight_mom, const int64_t
 int pfc_scatter_rows2(float* weight, float* weight_mom, const int64_t* index, int64_t n_index, int emb, const float* sub_weight,
                       const float* sub_weight_mom, void* stream) {
   if (int rc = require_sm100()) return rc;
+  NvtxScope nvtx_scope("pfc_scatter_rows2");
   PFC_REQUIRE(weight && index && sub_weight && n_index >= 0 && emb > 0 && emb % 4 == 0, PFC_E_ARG, "pfc_scatter_rows2: bad argument");
   if (n_index == 0) return 0;
   move_rows2_kernel<false><<<row_grid(n_index), 256, 0, as_stream(stream)>>>(weight, weight_mom, index, n_index, emb,

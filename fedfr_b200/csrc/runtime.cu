@@ -1,6 +1,8 @@
 // Error plumbing + device query for the C ABI (include/fedfr_b200.h).
 #include "common.cuh"
 #include <mutex>
+#include <stdlib.h>
+#include <nvtx3/nvToolsExt.h>      // header-only: resolves the injection library at run time, nothing to link
 
 namespace pfc {
 
@@ -14,6 +16,7 @@ static ProfSpan g_spans[4096];
 static int g_n_spans = 0;
 static cudaEvent_t g_open[PH_COUNT];
 bool prof_enabled() { return g_prof_on != 0; }
+void nvtx_set(int on);
 void prof_begin(int phase, cudaStream_t st) {
   if (!g_prof_on || g_n_spans >= 4096) return;
   cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); g_open[phase] = e;
@@ -23,6 +26,15 @@ void prof_end(int phase, cudaStream_t st) {
   cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
   g_spans[g_n_spans++] = ProfSpan{g_open[phase], e, phase};
 }
+
+static int g_nvtx = -1;          // -1: read FEDFR_NVTX on first use
+static inline bool nvtx_on() {
+  if (g_nvtx < 0) { const char* e = getenv("FEDFR_NVTX"); g_nvtx = (e && atoi(e) != 0) ? 1 : 0; }
+  return g_nvtx == 1;
+}
+void nvtx_push(const char* name) { if (nvtx_on()) nvtxRangePushA(name); }
+void nvtx_pop() { if (nvtx_on()) nvtxRangePop(); }
+void nvtx_set(int on) { g_nvtx = on ? 1 : 0; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -88,6 +100,9 @@ int pfc_profile_collect(float* ms_out /*[5]*/, int* count_out /*[5]*/) {
   pfc::g_n_spans = 0;
   return 0;
 }
+
+/* NVTX ranges around every compute entry of this library (default: the FEDFR_NVTX environment variable) */
+int pfc_set_nvtx(int on) { pfc::nvtx_set(on); return 0; }
 
 const char* pfc_last_error(void) { return pfc::g_err; }
 

@@ -238,6 +238,7 @@ size_t pfc_sample_workspace_bytes(int64_t num_local) {
 int pfc_sample_index(int64_t* label, int64_t n_label, float* perm, int64_t num_local, int64_t num_sample, int64_t* index_out,
                      int64_t* n_index_out, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = require_sm100()) return rc;
+  NvtxScope nvtx_scope("pfc_sample_index");
   PFC_REQUIRE(label && perm && index_out && workspace && n_label >= 0 && num_local > 0 && num_sample >= 0, PFC_E_ARG,
               "pfc_sample_index: bad argument");
   PFC_REQUIRE(num_local < (1ll << 31) && num_sample <= num_local, PFC_E_SHAPE, "pfc_sample_index: num_local/num_sample out of range");

@@ -203,6 +203,38 @@ __device__ __forceinline__ float warp_colsum32(const float (&h)[32], int lane) {
   return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
+// same on fp32 bit patterns held in uint32 registers (the caller's TMEM load buffer, products written in place)
+__device__ __forceinline__ float warp_colsum32_bits(const uint32_t (&h)[32], int lane) {
+  float a[16];
+  bool up = lane & 16;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float send = __uint_as_float(up ? h[k] : h[k + 16]), keep = __uint_as_float(up ? h[k + 16] : h[k]);
+    a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  up = lane & 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float send = up ? a[k] : a[k + 8], keep = up ? a[k + 8] : a[k];
+    a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  up = lane & 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float send = up ? a[k] : a[k + 4], keep = up ? a[k + 4] : a[k];
+    a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  up = lane & 2;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float send = up ? a[k] : a[k + 2], keep = up ? a[k + 2] : a[k];
+    a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  up = lane & 1;
+  const float send = up ? a[0] : a[1], keep = up ? a[1] : a[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
 struct PipeState {
   int stage = 0;
   uint32_t phase = 0;
@@ -1418,21 +1450,26 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
 }
 
 // ================================================================================================
-// dw4 kernel (E = 512): the dw GEMM + normalize backward on a cluster of FOUR CTAs = two cta_group::2 pairs.
-//   pair h (cluster ranks 2h, 2h+1) computes e-slice h (256 columns); the CTA of parity c in each pair owns class tile
-//   2g + c of the cluster's item g.  One tcgen05.mma covers M = 256 (both class tiles) x N = 256 (the e-slice), K = rows.
-// Why (measured, profiles/README.md r02a/b): the single-CTA kernel above is bound by shared-memory / L2->SM bytes per MMA
-// cycle, not by HBM or the tensor pipe -- 48 KB of operand fill per 512 MMA cycles plus the fp32 staging of the epilogue.
-//   * A = P^T tile [128 classes x 64 rows] is needed by the same-parity CTA of BOTH pairs: each loads one 64-class box and
-//     multicasts it to the other (8 KB from L2 per CTA per k-block instead of 16).
-//   * B = x_scaled: a cta_group::2 MMA takes HALF of the N columns from each CTA (128 e), so with Bt <= 512 the whole
-//     [512 rows x 128 e] operand (128 KB) stays RESIDENT in shared memory (STAT) -- no B traffic at all, where the old
-//     kernel re-streamed 256 KB per class tile; for larger batches the half is streamed (16 KB per k-block instead of 32).
-//   * MMA operand reads: 8 KB per 128-cycle MMA per CTA (cta_group::2) instead of 12 KB.
-//   * Epilogue without shared-memory staging: the accumulator is read with tcgen05.ld.16x256b, whose register layout puts
-//     8 consecutive columns of a row into a quad of threads, so dw leaves in full 32-byte sectors straight from registers
-//     (st.global.v2) and w_hat arrives by 4-byte loads in the same layout; the radial dot is reduced inside the quad, then
-//     over the four column-group warps and the two e-slice CTAs (DSMEM) exactly like the kernel above.
+// dw4 kernel (E = 512): the dw GEMM + normalize backward, TRANSPOSED, on a cluster of FOUR CTAs = two cta_group::2 pairs.
+//   D^T[e, class] = sum_rows x_scaled[row, e] P[row, class]:   M = e, N = classes, K = rows.
+//   pair h (cluster ranks 2h, 2h+1) owns e-slice h (256 of the 512 e); inside a pair CTA c supplies A = its 128 e-rows of
+//   x_scaled^T and the N-half c of B = the P tile of class tile 2g + c (g = the cluster's item), and receives
+//   D^T[its 128 e, all 256 classes] in TMEM (lane = e, column = class).
+// Why (measured, profiles/README.md r02): every kernel here is bound by ONE per-SM resource, the 128 B/clk shared-memory /
+// L1 data pipe, which TMA fills, tcgen05.mma operand reads, ld/st.shared AND every global load/store wavefront share.  In
+// 128-byte slots per 4096-cycle item the e-split pair kernel above needs 3072 (fill) + 3072 (cta_group::1 operand reads)
+// + 3584 (w_hat boxes, fp32 staging, TMA store) = 9728 -> 42 % of the tensor rate, which is what it measures.  Here:
+//   * cta_group::2 halves the operand reads per CTA (2048 slots) and the B fill;
+//   * the P tile of a class tile is needed by the same-parity CTA of BOTH pairs: each loads one 64-class box and
+//     multicasts it to the other (1024 slots of fill, 8 KB from L2 per CTA per k-block);
+//   * x_scaled^T, the M-side operand, is the SAME for every item: with Bt <= 512 its [512 rows x 128 e] slice (128 KB)
+//     stays resident in shared memory (STAT, no fill at all); larger batches stream it (16 KB per k-block);
+//   * lane = e means a warp's 32 lanes hold 32 CONSECUTIVE e of one class per register: dw leaves in full 128-byte
+//     lines straight from registers (st.global, 1024 slots) and w_hat arrives the same way (64-byte lines, 1024 slots) --
+//     no staging boxes, no shared-memory capacity for the epilogue, which is what makes the resident operand fit;
+//   * the radial term t_j = w_hat_j . dW_hat_j is a sum over e = over lanes: a shuffle transpose-reduction per 32 x 32
+//     block (warp_colsum32), then over the 4 lane quadrants (shared memory) and the 4 CTAs (DSMEM), fixed order.
+//   Budget: 1024 + 2048 + ~2600 = ~5700 slots -> ~72 % (STAT), ~62 % streamed.
 // Barriers: TMA bytes (own + multicast from the partner CTA) are credited to every CTA's OWN full barrier; the non-leader
 // CTA of a pair relays "my operands have landed" to its leader (mbarrier remote arrive), which issues the MMAs; stage
 // release (tcgen05.commit) is multicast to all four CTAs because a stage is written by two of them.
@@ -1446,8 +1483,9 @@ struct Dw4Params {
   float* dw;                     // [n_classes, 512]
   int accumulate;
   long long* dbg;
+  int exp;                       // timing experiments only (FEDFR_DW_EXP, wrong results): 1 no w_hat loads, 2 no dw stores, 4 no lane reduction
 };
-constexpr int kDw4EpiWarps = 16;                 // four per TMEM lane quadrant, 64 accumulator columns each
+constexpr int kDw4EpiWarps = 16;                 // warp (quad, cgp): e rows [32 quad, +32) of this CTA, classes [64 cgp, +64) of the item
 constexpr int kDw4Threads = (kDw4EpiWarps + 2) * 32;
 constexpr int kDw4E = 512;
 
@@ -1456,41 +1494,43 @@ __global__ void __launch_bounds__(kDw4Threads, 1) dw4_kernel(const __grid_consta
                                                              const Dw4Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int kABytes = 2 * kBoxBytes;                    // 128 classes x 64 rows
-  constexpr int kBBytes = 2 * kBoxBytes;                    // 64 rows x 128 e (this CTA's half of the e-slice)
-  constexpr int kStageBytes = kABytes + (STAT ? 0 : kBBytes);
+  constexpr int kPBytes = 2 * kBoxBytes;                    // P half tile: 64 rows x 128 classes
+  constexpr int kXBytes = 2 * kBoxBytes;                    // x_scaled: 64 rows x 128 e (this CTA's M rows)
+  constexpr int kStageBytes = kPBytes + (STAT ? 0 : kXBytes);
   constexpr int kMaxKb = 8;                                 // STAT: n_rows <= 512
-  uint8_t* smem_b = smem;                                   // STAT: [n_kb][2 boxes]
-  uint8_t* smem_st = smem + (STAT ? kMaxKb * kBBytes : 0);
-  float* tpart = reinterpret_cast<float*>(smem_st + STAGES * kStageBytes);     // [2][8 contributors][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tpart + 2 * 8 * 128);
+  uint8_t* smem_x = smem;                                   // STAT: [n_kb][2 boxes]
+  uint8_t* smem_st = smem + (STAT ? kMaxKb * kXBytes : 0);
+  float* part = reinterpret_cast<float*>(smem_st + STAGES * kStageBytes);     // [4 quadrants][256 classes]  partial dots of this CTA
+  float* tsum = part + 4 * 256;                                                // [2][4 CTAs][256]            per-CTA sums, all CTAs
+  float2* scal = reinterpret_cast<float2*>(tsum + 2 * 4 * 256);                // [256]                       (1/n_j, -t_j/n_j)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scal + 256);
   uint64_t* full = bars;                          // [STAGES]  own + multicast bytes of this CTA's stage
   uint64_t* empty = bars + STAGES;                // [STAGES]  2 arrivals: the commit of each pair's leader
   uint64_t* peer_full = bars + 2 * STAGES;        // [STAGES]  leader only: the other CTA of the pair has its stage
   uint64_t* tmem_full = bars + 3 * STAGES;        // [2]
   uint64_t* tmem_empty = bars + 3 * STAGES + 2;   // [2]       leader only: epilogue warps of both CTAs
-  uint64_t* tbar = bars + 3 * STAGES + 4;         // [2][4]    partial dots of a lane quadrant: 4 warps x 2 e-slice CTAs
-  uint64_t* b_full = bars + 3 * STAGES + 12;
-  uint64_t* peer_b_full = bars + 3 * STAGES + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 14);
+  uint64_t* tbar = bars + 3 * STAGES + 4;         // [2]       per-CTA sums of all four CTAs have landed
+  uint64_t* x_full = bars + 3 * STAGES + 6;
+  uint64_t* peer_x_full = bars + 3 * STAGES + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
-  const int hs = (int)(crank >> 1), cpar = (int)(crank & 1);      // e-slice of the pair, class-tile parity inside the pair
+  const int hs = (int)(crank >> 1), cpar = (int)(crank & 1);      // e-slice of the pair; N-half (class tile parity) inside the pair
   const bool leader = cpar == 0;
   const uint32_t leader_rank = crank & ~1u, partner = crank ^ 2u;  // partner: same class tile, other e-slice
   const int n_clusters = gridDim.x >> 2, cid = blockIdx.x >> 2;
   const int n_kb = (p.n_rows + BK - 1) / BK;
   constexpr int kProducerWarp = kDw4EpiWarps, kMmaWarp = kDw4EpiWarps + 1;
   const uint16_t pair_mask = (uint16_t)(3u << (2 * hs));
-  const uint16_t a_mask = (uint16_t)((1u << cpar) | (1u << (cpar + 2)));
+  const uint16_t p_mask = (uint16_t)((1u << cpar) | (1u << (cpar + 2)));
+  const int e_cta = hs * 256 + cpar * 128;                        // first e of this CTA's 128 M rows
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); mbar_init(&peer_full[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kDw4EpiWarps); }
-    for (int i = 0; i < 8; ++i) mbar_init(&tbar[i], 8);
-    mbar_init(b_full, 1);
-    mbar_init(peer_b_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kDw4EpiWarps); mbar_init(&tbar[i], 4 * 8); }
+    mbar_init(x_full, 1);
+    mbar_init(peer_x_full, 1);
     fence_barrier_init();
   }
   if (warp == kProducerWarp && lane == 0) { prefetch_tmap(&tmap_g); prefetch_tmap(&tmap_x); }
@@ -1502,25 +1542,24 @@ __global__ void __launch_bounds__(kDw4Threads, 1) dw4_kernel(const __grid_consta
 
   if (warp == kProducerWarp) {
     if (lane == 0) {
-      const int e_half = hs * 256 + cpar * 128;               // this CTA's half of the pair's B operand
       if (STAT) {
-        mbar_arrive_expect_tx(b_full, n_kb * kBBytes);
+        mbar_arrive_expect_tx(x_full, n_kb * kXBytes);
         for (int kb = 0; kb < n_kb; ++kb)
 #pragma unroll
-          for (int nb = 0; nb < 2; ++nb) tma_load_2d(smem_b + kb * kBBytes + nb * kBoxBytes, &tmap_x, b_full, e_half + nb * 64, kb * BK);
+          for (int nb = 0; nb < 2; ++nb) tma_load_2d(smem_x + kb * kXBytes + nb * kBoxBytes, &tmap_x, x_full, e_cta + nb * 64, kb * BK);
       }
       PipeState ps;
       for (int i = 0; i * n_clusters + cid < p.n_tp; ++i) {
         const int ct = 2 * (i * n_clusters + cid) + cpar;
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait_cluster(&empty[ps.stage], ps.phase ^ 1);
-          uint8_t* sa = smem_st + ps.stage * kStageBytes;
+          uint8_t* sp = smem_st + ps.stage * kStageBytes;
           mbar_arrive_expect_tx(&full[ps.stage], kStageBytes);
-          // class half `hs` of the tile, for this CTA and its partner in the other pair
-          tma_load_2d_mc(sa + hs * kBoxBytes, &tmap_g, &full[ps.stage], 0, ((2 * ct + hs) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64, a_mask);
+          // 64-class box `hs` of the P tile, for this CTA and its partner in the other pair
+          tma_load_2d_mc(sp + hs * kBoxBytes, &tmap_g, &full[ps.stage], 0, ((2 * ct + hs) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64, p_mask);
           if (!STAT) {
 #pragma unroll
-            for (int nb = 0; nb < 2; ++nb) tma_load_2d(sa + kABytes + nb * kBoxBytes, &tmap_x, &full[ps.stage], e_half + nb * 64, kb * BK);
+            for (int nb = 0; nb < 2; ++nb) tma_load_2d(sp + kPBytes + nb * kBoxBytes, &tmap_x, &full[ps.stage], e_cta + nb * 64, kb * BK);
           }
           ps.advance(STAGES);
         }
@@ -1531,7 +1570,7 @@ __global__ void __launch_bounds__(kDw4Threads, 1) dw4_kernel(const __grid_consta
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, 256, true, true);
       PipeState ps;
       long long t_we = 0, t_wf = 0, t_all = clock64();
-      if (STAT) { mbar_wait(b_full, 0); mbar_wait_cluster(peer_b_full, 0); }
+      if (STAT) { mbar_wait(x_full, 0); mbar_wait_cluster(peer_x_full, 0); }
       for (int it = 0; it * n_clusters + cid < p.n_tp; ++it) {
         const int acc = it & 1;
         long long c0 = clock64();
@@ -1545,12 +1584,12 @@ __global__ void __launch_bounds__(kDw4Threads, 1) dw4_kernel(const __grid_consta
           mbar_wait_cluster(&peer_full[ps.stage], ps.phase);
           t_wf += clock64() - c0;
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_st + ps.stage * kStageBytes);
-          const uint32_t b_addr = STAT ? smem_u32(smem_b + kb * kBBytes) : a_addr + kABytes;
+          const uint32_t p_addr = smem_u32(smem_st + ps.stage * kStageBytes);
+          const uint32_t x_addr = STAT ? smem_u32(smem_x + kb * kXBytes) : p_addr + kPBytes;
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t da = make_desc_sw128(a_addr + kk * 2048, kBoxBytes, 1024);
-            const uint64_t db = make_desc_sw128(b_addr + kk * 2048, kBoxBytes, 1024);
+            const uint64_t da = make_desc_sw128(x_addr + kk * 2048, kBoxBytes, 1024);     // A = x_scaled^T  (M = e, MN-major)
+            const uint64_t db = make_desc_sw128(p_addr + kk * 2048, kBoxBytes, 1024);     // B = P           (N = classes, MN-major)
             umma_bf16_ss_2cta(d_tmem, da, db, idesc, (kb | kk) != 0);
           }
           umma_commit_2cta(&empty[ps.stage], 0xF);          // the stage is written by CTAs of both pairs
@@ -1562,7 +1601,7 @@ __global__ void __launch_bounds__(kDw4Threads, 1) dw4_kernel(const __grid_consta
     } else if (lane == 0) {
       // relay: tell the leader of this pair when this CTA's operands of a stage have landed
       PipeState ps;
-      if (STAT) { mbar_wait(b_full, 0); mbar_arrive_remote(peer_b_full, leader_rank); }
+      if (STAT) { mbar_wait(x_full, 0); mbar_arrive_remote(peer_x_full, leader_rank); }
       for (int it = 0; it * n_clusters + cid < p.n_tp; ++it)
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&full[ps.stage], ps.phase);
@@ -1571,116 +1610,123 @@ __global__ void __launch_bounds__(kDw4Threads, 1) dw4_kernel(const __grid_consta
         }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: warp (quad, cg) owns classes [32 quad, +32) of the
-    // tile and accumulator columns [64 cg, +64).  Fragment layout of tcgen05.ld.16x256b: see tmem_ld_16x256b_x4.
-    const int quad = warp & 3, cg = warp >> 2;
-    const int lr = lane >> 2, lc = (lane & 3) * 2;
-    const int e0 = hs * 256 + cg * 64 + lc;                 // first e column of this thread
-    const int contrib = hs * 4 + cg;
+    // ------------------------------------------------------------------ epilogue: thread = e row, register = class
+    // warp (quad, cgp): e rows [32 quad, +32) of this CTA, classes [64 cgp, +64) of the 256 of the item (tile cgp >> 1)
+    const int quad = warp & 3, cgp = warp >> 2;
+    const int tid = threadIdx.x;                            // < 256: also the class slot this thread sums / scales
+    const int e_glob = e_cta + quad * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
     const uint32_t tmem_leader_empty0 = mapa_u32(smem_u32(&tmem_empty[0]), leader_rank);
+    const unsigned short* wbase = reinterpret_cast<const unsigned short*>(p.w_hat) + e_glob;
+    unsigned t_wfull = 0, t_p1 = 0, t_ex = 0, t_p2 = 0;      // 32-bit cycle counters of CTA 0 / thread 0 (developer probe)
     for (int it = 0; it * n_clusters + cid < p.n_tp; ++it) {
-      const int ct = 2 * (it * n_clusters + cid) + cpar;
+      const int tp = it * n_clusters + cid;
       const int acc = it & 1, buf = it & 1;
-      // rows of this thread: 32 quad + 16 hl + 8 j + lr
-      uint32_t wreg[2][2][8];
-      float inv[2][2];
+      const int cls_w = 2 * tp * BM + cgp * 64;             // first class of this warp's 64
+      // w_hat of this thread's e for its 64 classes, two bf16 per register (64-byte lines per warp and class)
+      uint32_t wpk[32];
+      const int n_ok = p.n_classes - cls_w;                 // classes of this group that exist (>= 64 for all but the last tiles)
+      const unsigned short* wt = wbase + (int64_t)cls_w * kDw4E;
+      if (p.exp & 1) {
 #pragma unroll
-      for (int hl = 0; hl < 2; ++hl)
+        for (int j = 0; j < 32; ++j) wpk[j] = 0x3f803f80u;
+      } else if (n_ok >= 64) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int cls = ct * BM + quad * 32 + hl * 16 + j * 8 + lr;
-          const bool ok = cls < p.n_classes;
-          const uint32_t* wp = reinterpret_cast<const uint32_t*>(p.w_hat + (int64_t)cls * kDw4E + e0);
+        for (int j = 0; j < 32; ++j) wpk[j] = (uint32_t)__ldg(wt + (2 * j) * kDw4E) | ((uint32_t)__ldg(wt + (2 * j + 1) * kDw4E) << 16);
+      } else {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) wreg[hl][j][k] = ok ? __ldg(wp + 4 * k) : 0u;
-          inv[hl][j] = ok ? __ldg(p.inv_norm + cls) : 0.f;
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t lo = 2 * j < n_ok ? (uint32_t)__ldg(wt + (2 * j) * kDw4E) : 0u;
+          const uint32_t hi = 2 * j + 1 < n_ok ? (uint32_t)__ldg(wt + (2 * j + 1) * kDw4E) : 0u;
+          wpk[j] = lo | (hi << 16);
         }
+      }
+      unsigned c0 = clock();
       mbar_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1));
+      t_wfull += clock() - c0;
+      c0 = clock();
       tc_fence_after();
-      // ---- pass 1: partial dots w_hat_j . acc_j over this thread's columns
-      float dot[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+      // ---- pass 1: per class, the sum over this warp's 32 e of w_hat * acc (a transpose-reduction across the lanes)
 #pragma unroll
-      for (int hl = 0; hl < 2; ++hl)
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_base + t_lane + acc * 256 + cgp * 64 + c * 32, v);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c4 = 0; c4 < 2; ++c4) {
-          uint32_t v[16];
-          tmem_ld_16x256b_x4(tmem_base + ((uint32_t)(quad * 32 + hl * 16) << 16) + acc * 256 + cg * 64 + c4 * 32, v);
-          tmem_ld_wait();
+        for (int j = 0; j < 32; j += 2) {
+          const uint32_t w2 = wpk[c * 16 + (j >> 1)];
+          const float2 pr = __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                                       make_float2(__uint_as_float(w2 << 16), __uint_as_float(w2 & 0xffff0000u)));
+          v[j] = __float_as_uint(pr.x);
+          v[j + 1] = __float_as_uint(pr.y);
+        }
+        part[quad * 256 + cgp * 64 + c * 32 + lane] = (p.exp & 4) ? __uint_as_float(v[0]) : warp_colsum32_bits(v, lane);
+      }
+      t_p1 += clock() - c0;
+      c0 = clock();
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      // ---- the CTA's sum over its 128 e for class slot `tid`, published to all four CTAs (warps 0..7)
+      if (tid < 256) {
+        const float s4 = ((part[tid] + part[256 + tid]) + part[512 + tid]) + part[768 + tid];
+        float* slot = tsum + (buf * 4 + (int)crank) * 256 + tid;
+        const uint32_t slot_addr = smem_u32(slot);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint32_t w0 = wreg[hl][0][c4 * 4 + kk], w1 = wreg[hl][1][c4 * 4 + kk];
-            dot[hl][0] = fmaf(__uint_as_float(v[4 * kk + 0]), __uint_as_float(w0 << 16), dot[hl][0]);
-            dot[hl][0] = fmaf(__uint_as_float(v[4 * kk + 1]), __uint_as_float(w0 & 0xffff0000u), dot[hl][0]);
-            dot[hl][1] = fmaf(__uint_as_float(v[4 * kk + 2]), __uint_as_float(w1 << 16), dot[hl][1]);
-            dot[hl][1] = fmaf(__uint_as_float(v[4 * kk + 3]), __uint_as_float(w1 & 0xffff0000u), dot[hl][1]);
+        for (uint32_t r = 0; r < 4; ++r) {
+          if (r == crank) *slot = s4;
+          else st_cluster_f32(mapa_u32(slot_addr, r), s4);
+        }
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (uint32_t r = 0; r < 4; ++r) {
+            if (r == crank) mbar_arrive(&tbar[buf]);
+            else mbar_arrive_remote(&tbar[buf], r);
           }
         }
+        mbar_wait_cluster(&tbar[buf], (uint32_t)((it >> 1) & 1));
+        const float* ts = tsum + buf * 4 * 256 + tid;
+        const float t = ((ts[0] + ts[256]) + ts[512]) + ts[768];          // fixed order: identical bits in all four CTAs
+        const int cls = 2 * tp * BM + tid;
+        const float inv = cls < p.n_classes ? __ldg(p.inv_norm + cls) : 0.f;
+        scal[tid] = make_float2(inv, -t * inv);
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      t_ex += clock() - c0;
+      c0 = clock();
+      // ---- pass 2: dw[class][e] = acc / n - w_hat (t / n): one full 128-byte line per warp and class, straight from registers
+      const bool plain = n_ok >= 64 && !p.accumulate && !(p.exp & 2);      // the common case: no per-class predicates at all
 #pragma unroll
-      for (int hl = 0; hl < 2; ++hl)
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_base + t_lane + acc * 256 + cgp * 64 + c * 32, v);
+        tmem_ld_wait();
+        const float4* sc4 = reinterpret_cast<const float4*>(scal + cgp * 64 + c * 32);
+        float* out = p.dw + (int64_t)(cls_w + c * 32) * kDw4E + e_glob;
+        if (plain) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          dot[hl][j] += __shfl_xor_sync(0xffffffffu, dot[hl][j], 1);
-          dot[hl][j] += __shfl_xor_sync(0xffffffffu, dot[hl][j], 2);
-        }
-      // ---- exchange: 8 contributors per class row (4 column-group warps x 2 e-slice CTAs), summed in a fixed order
-      if ((lane & 3) == 0) {
-#pragma unroll
-        for (int hl = 0; hl < 2; ++hl)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            float* slot = tpart + (buf * 8 + contrib) * 128 + quad * 32 + hl * 16 + j * 8 + lr;
-            *slot = dot[hl][j];
-            st_cluster_f32(mapa_u32(smem_u32(slot), partner), dot[hl][j]);
+          for (int j = 0; j < 32; j += 2) {
+            const float4 sc = sc4[j >> 1];                   // (1/n_j, -t_j/n_j, 1/n_j+1, -t_j+1/n_j+1): same address in every lane
+            const uint32_t w2 = wpk[c * 16 + (j >> 1)];
+            const float2 r = __ffma2_rn(make_float2(__uint_as_float(w2 << 16), __uint_as_float(w2 & 0xffff0000u)), make_float2(sc.y, sc.w),
+                                        __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(sc.x, sc.z)));
+            out[j * kDw4E] = r.x;
+            out[(j + 1) * kDw4E] = r.y;
           }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&tbar[buf * 4 + quad]);
-        mbar_arrive_remote(&tbar[buf * 4 + quad], partner);
-      }
-      mbar_wait_cluster(&tbar[buf * 4 + quad], (uint32_t)((it >> 1) & 1));
-      float c1[2][2];
+        } else {
 #pragma unroll
-      for (int hl = 0; hl < 2; ++hl)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float* all = tpart + buf * 8 * 128 + quad * 32 + hl * 16 + j * 8 + lr;
-          float t = all[0];
-#pragma unroll
-          for (int c = 1; c < 8; ++c) t += all[c * 128];
-          c1[hl][j] = -t * inv[hl][j];
-        }
-      // ---- pass 2: dw = acc * inv_norm - w_hat * (t * inv_norm), straight from registers in full 32-byte sectors
-#pragma unroll
-      for (int hl = 0; hl < 2; ++hl) {
-        const int cls_a = ct * BM + quad * 32 + hl * 16 + lr, cls_b = cls_a + 8;
-        float* oa = p.dw + (int64_t)cls_a * kDw4E + e0;
-        float* ob = p.dw + (int64_t)cls_b * kDw4E + e0;
-        const bool ok_a = cls_a < p.n_classes, ok_b = cls_b < p.n_classes;
-#pragma unroll
-        for (int c4 = 0; c4 < 2; ++c4) {
-          uint32_t v[16];
-          tmem_ld_16x256b_x4(tmem_base + ((uint32_t)(quad * 32 + hl * 16) << 16) + acc * 256 + cg * 64 + c4 * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const int k = c4 * 4 + kk;
-            const uint32_t w0 = wreg[hl][0][k], w1 = wreg[hl][1][k];
-            float2 ra, rb;
-            ra.x = fmaf(__uint_as_float(w0 << 16), c1[hl][0], __uint_as_float(v[4 * kk + 0]) * inv[hl][0]);
-            ra.y = fmaf(__uint_as_float(w0 & 0xffff0000u), c1[hl][0], __uint_as_float(v[4 * kk + 1]) * inv[hl][0]);
-            rb.x = fmaf(__uint_as_float(w1 << 16), c1[hl][1], __uint_as_float(v[4 * kk + 2]) * inv[hl][1]);
-            rb.y = fmaf(__uint_as_float(w1 & 0xffff0000u), c1[hl][1], __uint_as_float(v[4 * kk + 3]) * inv[hl][1]);
-            if (ok_a) {
-              float2* d = reinterpret_cast<float2*>(oa + 8 * k);
-              if (p.accumulate) { const float2 o = *d; ra.x += o.x; ra.y += o.y; }
-              *d = ra;
+          for (int j = 0; j < 32; j += 2) {
+            const float4 sc = sc4[j >> 1];
+            const uint32_t w2 = wpk[c * 16 + (j >> 1)];
+            float2 r = __ffma2_rn(make_float2(__uint_as_float(w2 << 16), __uint_as_float(w2 & 0xffff0000u)), make_float2(sc.y, sc.w),
+                                  __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(sc.x, sc.z)));
+            float* d = out + j * kDw4E;
+            if (p.exp & 2) { if (r.x == 1.2345f && r.y == 5.4321f) d[0] = r.x; continue; }
+            if (p.accumulate) {
+              if (c * 32 + j < n_ok) r.x += d[0];
+              if (c * 32 + j + 1 < n_ok) r.y += d[kDw4E];
             }
-            if (ok_b) {
-              float2* d = reinterpret_cast<float2*>(ob + 8 * k);
-              if (p.accumulate) { const float2 o = *d; rb.x += o.x; rb.y += o.y; }
-              *d = rb;
-            }
+            if (c * 32 + j < n_ok) d[0] = r.x;
+            if (c * 32 + j + 1 < n_ok) d[kDw4E] = r.y;
           }
         }
       }
@@ -1690,7 +1736,9 @@ __global__ void __launch_bounds__(kDw4Threads, 1) dw4_kernel(const __grid_consta
         if (leader) mbar_arrive(&tmem_empty[acc]);
         else mbar_arrive_cluster_addr_relaxed(tmem_leader_empty0 + acc * 8);
       }
+      t_p2 += clock() - c0;
     }
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[3] = t_wfull; p.dbg[4] = 0; p.dbg[5] = t_p1 + t_ex + t_p2; p.dbg[6] = t_p1; p.dbg[7] = t_p1 + t_ex; p.dbg[8] = t_p1 + t_ex + t_p2; }
   }
   tc_fence_before();
   cluster_sync_all();
@@ -2049,10 +2097,11 @@ static int launch_dw(const CUtensorMap& tg, const CUtensorMap& tx, const CUtenso
   }
 }
 
-static int g_dw4 = 0;                                // 1: 4-CTA-cluster dw4 kernel for E = 512 (opt-in, pfc_set_dw4); 0: the e-split pair kernel
+static int g_dw4 = getenv("FEDFR_DW4") ? atoi(getenv("FEDFR_DW4")) : 0;      // 1: 4-CTA-cluster dw4 kernel for E = 512 (pfc_set_dw4 / FEDFR_DW4); 0: the e-split pair kernel
 template <bool STAT, int STAGES>
 static size_t dw4_smem_bytes() {
-  return (size_t)(STAT ? 8 * 2 * kBoxBytes : 0) + (size_t)STAGES * (2 * kBoxBytes + (STAT ? 0 : 2 * kBoxBytes)) + 2 * 8 * 128 * 4 + 1024 + 1024;
+  return (size_t)(STAT ? 8 * 2 * kBoxBytes : 0) + (size_t)STAGES * (2 * kBoxBytes + (STAT ? 0 : 2 * kBoxBytes)) + 4 * 256 * 4 /* part */ +
+         2 * 4 * 256 * 4 /* tsum */ + 256 * 8 /* scal */ + 512 /* barriers */ + 1024 /* alignment */;
 }
 constexpr int kDw4StagesStat = 5, kDw4StagesStream = 6;
 static bool dw4_stationary(int64_t n_rows) { return n_rows <= 512; }
@@ -2601,7 +2650,7 @@ static int tc_bwd_prob_enqueue(const void* w_hat, const float* inv_norm, const i
     else if (use_dw4) {
       Dw4Params qp{};
       qp.n_rows = (int)n_rows; qp.n_classes = (int)n_classes; qp.n_rb = n_rb; qp.n_tp = (int)((n_classes + 255) / 256);
-      qp.inv_norm = inv_norm; qp.w_hat = wh; qp.dw = dw; qp.accumulate = accumulate_dw; qp.dbg = g_dbg;
+      qp.inv_norm = inv_norm; qp.w_hat = wh; qp.dw = dw; qp.accumulate = accumulate_dw; qp.dbg = g_dbg; qp.exp = dw_exp;
       rc = launch_dw4(tg_mn, tx_mn, qp, pl.sm_dw, sW);
     } else switch (emb) {
       case 512: rc = launch_dw<512>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;

@@ -40,6 +40,7 @@ class CudaOps:
         if self.bwd_mode not in ("prob", "recompute"):
             raise ValueError("FEDFR_BWD_MODE must be 'prob' or 'recompute'")
         self._prob = None       # (workspace, offset, bytes, bt, cs, emb, token) of the last stored-probability forward
+        self._sub_rows = None   # row count of the persistent sampled sub-shard buffers
         self.last_token = 0     # bumped by every forward: step buffers (x_hat, w_hat, inv_norm, P) belong to the newest one
         # range guard of the stored-probability path: sticky (s |x| out of the exponent window, row sum of 0) int pairs in
         # pinned host memory that the kernels set every step; RANGE_SLOTS pairs, so that a caller can give every step its
@@ -90,12 +91,19 @@ class CudaOps:
                                        _stream(self.device)), "pfc_remap_labels")
         return out
 
+    def remap_labels_(self, total_label, class_start, num_local):
+        """In place (the kernel is elementwise): what partial_fc.py:91-93 does to the gathered labels."""
+        N.check(N.lib.pfc_remap_labels(N.ptr(total_label), total_label.numel(), int(class_start), int(num_local), N.ptr(total_label),
+                                       _stream(self.device)), "pfc_remap_labels")
+        return total_label
+
     def sample(self, local_label, perm, num_sample):
-        """In place on ``local_label`` and ``perm``; returns the sorted ``index`` tensor (partial_fc.py:95-104)."""
+        """In place on ``local_label`` and ``perm``; returns the sorted ``index`` tensor (partial_fc.py:95-104).  The index
+        lives in step scratch (valid until the next call), like every other per-step buffer of this provider."""
         num_local = perm.numel()
         cap = max(int(num_sample), min(local_label.numel(), num_local))
-        index = torch.empty(cap, dtype=torch.int64, device=self.device)
-        n_index = torch.zeros(1, dtype=torch.int64, device=self.device)
+        index = self._persist("sample_index", (cap,), torch.int64)
+        n_index = self._persist("sample_n_index", (1,), torch.int64)
         ws = self._buf("sample", N.lib.pfc_sample_workspace_bytes(num_local))
         N.check(N.lib.pfc_sample_index(N.ptr(local_label), local_label.numel(), N.ptr(perm), num_local, int(num_sample), N.ptr(index),
                                        N.ptr(n_index), N.ptr(ws), ws.numel(), _stream(self.device)), "pfc_sample_index")
@@ -104,9 +112,17 @@ class CudaOps:
         return index[: int(n_index.item())]
 
     def gather_rows2(self, weight, weight_mom, index):
+        """(weight[index], weight_mom[index]) into step scratch with stable addresses (a new Parameter wraps the same storage
+        every step: the forward / backward graphs keyed on these pointers are captured once)."""
         emb = weight.shape[1]
-        sub_w = torch.empty((index.numel(), emb), dtype=torch.float32, device=self.device)
-        sub_m = torch.empty_like(sub_w)
+        n = index.numel()
+        if self._sub_rows in (None, n):         # the planned num_sample; a positives-overflow step (other sizes) gets fresh tensors
+            self._sub_rows = n
+            sub_w = self._persist("sub_w", (n, emb), torch.float32)
+            sub_m = self._persist("sub_m", (n, emb), torch.float32)
+        else:
+            sub_w = torch.empty((n, emb), dtype=torch.float32, device=self.device)
+            sub_m = torch.empty_like(sub_w)
         N.check(N.lib.pfc_gather_rows2(N.ptr(weight), N.ptr(weight_mom), N.ptr(index), index.numel(), emb, N.ptr(sub_w), N.ptr(sub_m),
                                        _stream(self.device)), "pfc_gather_rows2")
         return sub_w, sub_m

@@ -24,6 +24,7 @@ from torch.nn import Module
 from torch.nn.parameter import Parameter
 
 from .losses import margin_params
+from ._nvtx import nvtx_range
 
 
 class PartialFC(Module):
@@ -120,15 +121,20 @@ class PartialFC(Module):
     @torch.no_grad()
     def sample(self, total_label):
         """In place on ``total_label`` (global ids -> shard-local / sampled column ids, -1 elsewhere)."""
-        local = self._ops.remap_labels(total_label, self.class_start, self.num_local)
+        ops = self._ops
+        if hasattr(ops, "remap_labels_"):
+            local = ops.remap_labels_(total_label, self.class_start, self.num_local)
+        else:
+            local = ops.remap_labels(total_label, self.class_start, self.num_local)
         if int(self.sample_rate) != 1:
             perm = torch.rand(size=[self.num_local], device=self.device)       # same draw as partial_fc.py:95
-            index = self._ops.sample(local, perm, self.num_sample)
+            index = ops.sample(local, perm, self.num_sample)
             self.index = index
-            sub_w, sub_m = self._ops.gather_rows2(self.weight, self.weight_mom, index)
+            sub_w, sub_m = ops.gather_rows2(self.weight, self.weight_mom, index)
             self.sub_weight = Parameter(sub_w)
             self.sub_weight_mom = sub_m
-        total_label.copy_(local)
+        if local is not total_label:
+            total_label.copy_(local)
 
     def forward(self, total_features, norm_weight):
         """The reference materialises ``logits = linear(total_features, norm_weight)`` here (partial_fc.py:108-111).
@@ -302,6 +308,8 @@ class PartialFC(Module):
         fused = hasattr(ops, "normalize_fwd_stats")
         self._check_logit_range(features)
         w_hat = None
+        nvtx_prep = nvtx_range("pfc.prepare(gather+sample)")
+        nvtx_prep.__enter__()
         if W == 1:
             total_label, w_hat = self.prepare(label, optimizer, _defer_normalize=fused)
             if self._label_buf is None or self._label_buf.shape != total_label.shape:
@@ -323,7 +331,10 @@ class PartialFC(Module):
                 self._norm = ops.normalize(self.sub_weight.data)
                 w_hat = self._norm[0]
 
+        nvtx_prep.__exit__()
         # forward: per-shard (max, sum-exp, target logit), then one exchange instead of three all-reduces
+        nvtx_fwd = nvtx_range("pfc.forward(normalize+logits+stats)")
+        nvtx_fwd.__enter__()
         pre = self._prenorm
         self._prenorm = None
         if pre is not None and int(self.sample_rate) == 1 and pre[2] == self.weight.data_ptr() and pre[3] == self.weight._version:
@@ -342,8 +353,11 @@ class PartialFC(Module):
             gathered = self._buffer("stats_all", (W,) + tuple(stats.shape), stats.dtype)
             self._all_gather(gathered.view(W * stats.shape[0], stats.shape[1]), stats)
         row_max, row_sum, loss_v = ops.finalize(gathered)
+        nvtx_fwd.__exit__()
 
         # backward: dx partial of this shard + sub_weight.grad
+        nvtx_bwd = nvtx_range("pfc.backward(dx+dw+reduce_scatter)")
+        nvtx_bwd.__enter__()
         accumulate = self.sub_weight.grad is not None
         if not accumulate:
             self.sub_weight.grad = torch.empty_like(self.sub_weight.data)
@@ -359,4 +373,5 @@ class PartialFC(Module):
             x_grad = torch.empty((B, E), dtype=torch.float32, device=self.device)
             self._reduce_scatter(x_grad, dx_total)  # partial_fc.py:171-173
             x_grad.mul_(W)                          # partial_fc.py:174
+        nvtx_bwd.__exit__()
         return x_grad, loss_v

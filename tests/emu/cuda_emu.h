@@ -182,6 +182,7 @@ static char g_emu_err[512];
 static inline void set_error(const char* fmt, ...) { (void)fmt; snprintf(g_emu_err, sizeof(g_emu_err), "%s", fmt); }
 static long long g_launch_count = 0;
 static inline int require_sm100() { return 0; }
+struct NvtxScope { explicit NvtxScope(const char*) {} };
 enum { PH_NORMALIZE = 0, PH_FWD = 1, PH_GRAD = 2, PH_DX = 3, PH_DW = 4, PH_COUNT = 5 };
 static inline void prof_begin(int, cudaStream_t) {}
 static inline void prof_end(int, cudaStream_t) {}

@@ -31,6 +31,21 @@ def test_every_declared_symbol_is_exported(native):
     assert native.lib.pfc_version() >= 100
 
 
+def test_every_developer_hook_is_declared_and_exported(native):
+    """include/fedfr_b200_dev.h lists the tuning / profiling hooks; every pfc_set_* / pfc_profile_* / pfc_launch_count the
+    library exports is declared in one of the two headers (no undeclared exports)."""
+    import subprocess
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "fedfr_b200_dev.h")).read(), flags=re.S)
+    dev = set(re.findall(r"\b(pfc_[a-z0-9_]+)\s*\(", text))
+    assert len(dev) >= 15
+    for s in dev:
+        assert hasattr(native.lib, s), f"{s} declared in include/fedfr_b200_dev.h but not exported"
+    out = subprocess.run(["nm", "-D", "--defined-only", native.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T ((?:pfc|fedavg)_[a-z0-9_]+)$", out, flags=re.M))
+    undeclared = exported - dev - set(_declared_symbols())
+    assert not undeclared, f"exported but declared in neither header: {sorted(undeclared)}"
+
+
 def test_pure_host_entries(native):
     assert native.lib.fedavg_table_bytes(475, 40) > 475 * 40 * 8
     assert native.lib.pfc_sample_workspace_bytes(250000) > 1024

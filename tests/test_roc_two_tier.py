@@ -1,5 +1,5 @@
-"""The opt-in two-tier ROC kernel (pfc_set_roc_mode(1): fp32 FMA filter + exact chain near bin edges, csrc/roc.cu) must
-return the same integers as the exact kernel and as the reference golden -- on the GPU.  (Its CPU twin is
+"""The two-tier ROC kernel (the default since round 2, pfc_set_roc_mode(1): fp32 FMA filter + exact chain near bin edges,
+csrc/roc.cu) must return the same integers as the exact kernel (mode 0) and as the reference golden -- on the GPU.  (Its CPU twin is
 tests/test_kernel_emulation.py::test_two_tier_roc_kernel_is_integer_identical.)"""
 import os
 import sys
@@ -21,7 +21,7 @@ def two_tier():
     def set_mode(m):
         N.check(N.lib.pfc_set_roc_mode(m), "pfc_set_roc_mode")
     yield set_mode
-    set_mode(0)
+    set_mode(1)
 
 
 def test_two_tier_matches_golden_and_exact_kernel(two_tier):
