@@ -672,8 +672,17 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get("prob" if prob else "recompute", {}).get(dom.split("(")[0])
         except Exception:                                 # noqa: BLE001
             traffic = None
-    # HBM view of the whole step: bytes this design moves per step, not the minimum any design needs
+    # HBM view of the whole step: bytes this design moves per step, not the minimum any design needs.
+    # Formula: every tensor counted once per kernel that touches it.  Measured (ncu --graph-profiling graph, the forward and
+    # the backward graph each as one unit, profiles/traffic.json "step_graphs", c3 at N=1): 9.73 GB -- the P / w_hat tiles dx
+    # and dw both read are fetched from DRAM once because the two kernels run side by side and share them through L2.
     design_bytes = (16.0 * Cs * E + 6.0 * Bt * Cs) if prob else (18.0 * Cs * E + 6.0 * Bt * Cs)
+    measured_bytes = None
+    if world == 1 and args.workload == "c3" and prob and os.path.exists(tpath):
+        try:
+            measured_bytes = json.load(open(tpath)).get("step_graphs", {}).get("step_total")
+        except Exception:                                 # noqa: BLE001
+            measured_bytes = None
     roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
             "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside the step loop); burst {peaks['tflops']}",
@@ -683,7 +692,9 @@ def run_ours(args):
             "step_tflops": 6.0 * Bt * Cs * E / (ms_step * 1e-3) / 1e12 / 1.0,
             "step_frac_of_burst_peak_per_gpu": 6.0 * Bt * Cs * E / (ms_step * 1e-3) / 1e12 / peaks["tflops"],
             "step_hbm": {"design_bytes_per_step": design_bytes, "gbs": design_bytes / (ms_step * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
-                         "frac": design_bytes / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                         "frac": design_bytes / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "measured_dram_bytes_per_step": measured_bytes,
+                         "measured_frac": None if not measured_bytes else measured_bytes / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"]},
             "backward": "stored probabilities (3 GEMMs)" if prob else "recompute (4 GEMMs)"}
 
     cpu = None

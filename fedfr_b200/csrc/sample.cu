@@ -58,9 +58,21 @@ __global__ void __launch_bounds__(kSampleThreads) sample_radix_kernel(const floa
   const unsigned int hi_mask = pass == 3 ? 0u : (0xffffffffu << (shift + 8));
   const unsigned int prefix = st->prefix;
   const unsigned int* bits = reinterpret_cast<const unsigned int*>(perm);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_local; i += (int64_t)gridDim.x * blockDim.x) {
-    const unsigned int v = bits[i];
-    if ((v & hi_mask) == prefix) atomicAdd(&sh[(v >> shift) & 0xffu], 1u);
+  // warp-aggregated counting: torch.rand values crowd into a handful of top bytes (half of them share 0x3f), so one
+  // shared-memory atomic per element serialises 32 ways; lanes with the same digit elect one to add their count
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n_iter = (num_local + stride - 1) / stride;          // the same for every thread: match is warp-convergent
+  for (int64_t it = 0; it < n_iter; ++it) {
+    const int64_t i = first + it * stride;
+    unsigned int key = 0x100u + (unsigned int)lane;                   // not counted: a key of its own
+    if (i < num_local) {
+      const unsigned int v = bits[i];
+      if ((v & hi_mask) == prefix) key = (v >> shift) & 0xffu;
+    }
+    const unsigned int peers = __match_any_sync(0xffffffffu, key);
+    if (key < 0x100u && lane == __ffs((int)peers) - 1) atomicAdd(&sh[key], (unsigned int)__popc(peers));
   }
   __syncthreads();
   if (sh[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], sh[threadIdx.x]);
@@ -126,16 +138,31 @@ __global__ void __launch_bounds__(kSampleThreads) sample_count_kernel(const floa
   if (threadIdx.x == 0) { blk_gt[blockIdx.x] = s_gt; blk_eq[blockIdx.x] = s_eq; }
 }
 
-// Exclusive scan over blocks (single block).
-__global__ void sample_scan_kernel(int n_blocks, unsigned int* blk_gt, unsigned int* blk_eq) {
-  if (threadIdx.x == 0) {
-    unsigned int a = 0, b = 0;
-    for (int i = 0; i < n_blocks; ++i) {
-      unsigned int g = blk_gt[i], e = blk_eq[i];
-      blk_gt[i] = a; blk_eq[i] = b;
-      a += g; b += e;
-    }
+// Exclusive scan of the per-block counts (one block of kMaxCompactBlocks threads, one count pair per thread).
+__global__ void __launch_bounds__(kMaxCompactBlocks) sample_scan_kernel(int n_blocks, unsigned int* blk_gt, unsigned int* blk_eq) {
+  __shared__ unsigned int wsum_g[32], wsum_e[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const unsigned int g = t < n_blocks ? blk_gt[t] : 0u, e = t < n_blocks ? blk_eq[t] : 0u;
+  unsigned int ig = g, ie = e;                                        // inclusive scan inside the warp
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int a = __shfl_sync(0xffffffffu, ig, lane >= o ? lane - o : lane);
+    const unsigned int b = __shfl_sync(0xffffffffu, ie, lane >= o ? lane - o : lane);
+    if (lane >= o) { ig += a; ie += b; }
   }
+  if (lane == 31) { wsum_g[w] = ig; wsum_e[w] = ie; }
+  __syncthreads();
+  if (w == 0) {                                                       // scan of the warp totals
+    unsigned int sg = wsum_g[lane], se = wsum_e[lane];
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int a = __shfl_sync(0xffffffffu, sg, lane >= o ? lane - o : lane);
+      const unsigned int b = __shfl_sync(0xffffffffu, se, lane >= o ? lane - o : lane);
+      if (lane >= o) { sg += a; se += b; }
+    }
+    wsum_g[lane] = sg; wsum_e[lane] = se;
+  }
+  __syncthreads();
+  const unsigned int base_g = w > 0 ? wsum_g[w - 1] : 0u, base_e = w > 0 ? wsum_e[w - 1] : 0u;
+  if (t < n_blocks) { blk_gt[t] = base_g + ig - g; blk_eq[t] = base_e + ie - e; }
 }
 
 // Ordered compaction: ids leave in ascending order.
@@ -261,7 +288,7 @@ int pfc_sample_index(int64_t* label, int64_t n_label, float* perm, int64_t num_l
   const int nb = compact_blocks(num_local, &chunk);
   sample_count_kernel<<<nb, kSampleThreads, 0, st>>>(perm, num_local, chunk, state, blk_gt, blk_eq);
   PFC_LAUNCH_CHECK();
-  sample_scan_kernel<<<1, 32, 0, st>>>(nb, blk_gt, blk_eq);
+  sample_scan_kernel<<<1, kMaxCompactBlocks, 0, st>>>(nb, blk_gt, blk_eq);
   PFC_LAUNCH_CHECK();
   sample_compact_kernel<<<nb, kSampleThreads, 0, st>>>(perm, num_local, chunk, state, blk_gt, blk_eq, index_out);
   PFC_LAUNCH_CHECK();

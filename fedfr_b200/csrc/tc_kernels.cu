@@ -1489,7 +1489,10 @@ constexpr int kDw4EpiWarps = 16;                 // warp (quad, cgp): e rows [32
 constexpr int kDw4Threads = (kDw4EpiWarps + 2) * 32;
 constexpr int kDw4E = 512;
 
-template <bool STAT, int STAGES>
+// LITE: no cross-pair multicast and no relay -- every CTA loads the whole P tile of its class tile itself and the TMA bytes
+// of both CTAs of a pair are credited straight to the leader's full barrier (the dx2 kernel's producer); the two pairs of a
+// cluster then only meet in the radial-dot exchange.  16 KB more from L2 per CTA and k-block, no coupling between the pairs.
+template <bool STAT, int STAGES, bool LITE = false>
 __global__ void __launch_bounds__(kDw4Threads, 1) dw4_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
                                                              const Dw4Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -1527,7 +1530,7 @@ __global__ void __launch_bounds__(kDw4Threads, 1) dw4_kernel(const __grid_consta
   const int e_cta = hs * 256 + cpar * 128;                        // first e of this CTA's 128 M rows
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); mbar_init(&peer_full[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], LITE ? 1 : 2); mbar_init(&peer_full[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kDw4EpiWarps); mbar_init(&tbar[i], 4 * 8); }
     mbar_init(x_full, 1);
     mbar_init(peer_x_full, 1);
@@ -1542,11 +1545,16 @@ __global__ void __launch_bounds__(kDw4Threads, 1) dw4_kernel(const __grid_consta
 
   if (warp == kProducerWarp) {
     if (lane == 0) {
+      const uint32_t x_full_leader = mapa_u32(smem_u32(x_full), leader_rank);
       if (STAT) {
-        mbar_arrive_expect_tx(x_full, n_kb * kXBytes);
+        if (LITE) { if (leader) mbar_arrive_expect_tx(x_full, 2 * n_kb * kXBytes); }
+        else mbar_arrive_expect_tx(x_full, n_kb * kXBytes);
         for (int kb = 0; kb < n_kb; ++kb)
 #pragma unroll
-          for (int nb = 0; nb < 2; ++nb) tma_load_2d(smem_x + kb * kXBytes + nb * kBoxBytes, &tmap_x, x_full, e_cta + nb * 64, kb * BK);
+          for (int nb = 0; nb < 2; ++nb) {
+            if (LITE) tma_load_2d_2cta(smem_x + kb * kXBytes + nb * kBoxBytes, &tmap_x, x_full_leader, e_cta + nb * 64, kb * BK);
+            else tma_load_2d(smem_x + kb * kXBytes + nb * kBoxBytes, &tmap_x, x_full, e_cta + nb * 64, kb * BK);
+          }
       }
       PipeState ps;
       for (int i = 0; i * n_clusters + cid < p.n_tp; ++i) {
@@ -1554,12 +1562,24 @@ __global__ void __launch_bounds__(kDw4Threads, 1) dw4_kernel(const __grid_consta
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait_cluster(&empty[ps.stage], ps.phase ^ 1);
           uint8_t* sp = smem_st + ps.stage * kStageBytes;
-          mbar_arrive_expect_tx(&full[ps.stage], kStageBytes);
-          // 64-class box `hs` of the P tile, for this CTA and its partner in the other pair
-          tma_load_2d_mc(sp + hs * kBoxBytes, &tmap_g, &full[ps.stage], 0, ((2 * ct + hs) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64, p_mask);
-          if (!STAT) {
+          if (LITE) {
+            const uint32_t full_leader = mapa_u32(smem_u32(&full[ps.stage]), leader_rank);
+            if (leader) mbar_arrive_expect_tx(&full[ps.stage], 2 * kStageBytes);
 #pragma unroll
-            for (int nb = 0; nb < 2; ++nb) tma_load_2d(sp + kPBytes + nb * kBoxBytes, &tmap_x, &full[ps.stage], e_cta + nb * 64, kb * BK);
+            for (int hb = 0; hb < 2; ++hb)
+              tma_load_2d_2cta(sp + hb * kBoxBytes, &tmap_g, full_leader, 0, ((2 * ct + hb) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64);
+            if (!STAT) {
+#pragma unroll
+              for (int nb = 0; nb < 2; ++nb) tma_load_2d_2cta(sp + kPBytes + nb * kBoxBytes, &tmap_x, full_leader, e_cta + nb * 64, kb * BK);
+            }
+          } else {
+            mbar_arrive_expect_tx(&full[ps.stage], kStageBytes);
+            // 64-class box `hs` of the P tile, for this CTA and its partner in the other pair
+            tma_load_2d_mc(sp + hs * kBoxBytes, &tmap_g, &full[ps.stage], 0, ((2 * ct + hs) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64, p_mask);
+            if (!STAT) {
+#pragma unroll
+              for (int nb = 0; nb < 2; ++nb) tma_load_2d(sp + kPBytes + nb * kBoxBytes, &tmap_x, &full[ps.stage], e_cta + nb * 64, kb * BK);
+            }
           }
           ps.advance(STAGES);
         }
@@ -1570,7 +1590,7 @@ __global__ void __launch_bounds__(kDw4Threads, 1) dw4_kernel(const __grid_consta
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, 256, true, true);
       PipeState ps;
       long long t_we = 0, t_wf = 0, t_all = clock64();
-      if (STAT) { mbar_wait(x_full, 0); mbar_wait_cluster(peer_x_full, 0); }
+      if (STAT) { mbar_wait_cluster(x_full, 0); if (!LITE) mbar_wait_cluster(peer_x_full, 0); }
       for (int it = 0; it * n_clusters + cid < p.n_tp; ++it) {
         const int acc = it & 1;
         long long c0 = clock64();
@@ -1580,8 +1600,8 @@ __global__ void __launch_bounds__(kDw4Threads, 1) dw4_kernel(const __grid_consta
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int kb = 0; kb < n_kb; ++kb) {
           c0 = clock64();
-          mbar_wait(&full[ps.stage], ps.phase);
-          mbar_wait_cluster(&peer_full[ps.stage], ps.phase);
+          if (LITE) mbar_wait_cluster(&full[ps.stage], ps.phase);
+          else { mbar_wait(&full[ps.stage], ps.phase); mbar_wait_cluster(&peer_full[ps.stage], ps.phase); }
           t_wf += clock64() - c0;
           tc_fence_after();
           const uint32_t p_addr = smem_u32(smem_st + ps.stage * kStageBytes);
@@ -1592,13 +1612,13 @@ __global__ void __launch_bounds__(kDw4Threads, 1) dw4_kernel(const __grid_consta
             const uint64_t db = make_desc_sw128(p_addr + kk * 2048, kBoxBytes, 1024);     // B = P           (N = classes, MN-major)
             umma_bf16_ss_2cta(d_tmem, da, db, idesc, (kb | kk) != 0);
           }
-          umma_commit_2cta(&empty[ps.stage], 0xF);          // the stage is written by CTAs of both pairs
+          umma_commit_2cta(&empty[ps.stage], LITE ? pair_mask : (uint16_t)0xF);          // (not LITE: the stage is written by CTAs of both pairs)
           ps.advance(STAGES);
         }
         umma_commit_2cta(&tmem_full[acc], pair_mask);
       }
       if (p.dbg && blockIdx.x == 0) { p.dbg[0] = t_we; p.dbg[1] = t_wf; p.dbg[2] = clock64() - t_all; }
-    } else if (lane == 0) {
+    } else if (lane == 0 && !LITE) {
       // relay: tell the leader of this pair when this CTA's operands of a stage have landed
       PipeState ps;
       if (STAT) { mbar_wait(x_full, 0); mbar_arrive_remote(peer_x_full, leader_rank); }
@@ -2097,7 +2117,16 @@ static int launch_dw(const CUtensorMap& tg, const CUtensorMap& tx, const CUtenso
   }
 }
 
-static int g_dw4 = getenv("FEDFR_DW4") ? atoi(getenv("FEDFR_DW4")) : 0;      // 1: 4-CTA-cluster dw4 kernel for E = 512 (pfc_set_dw4 / FEDFR_DW4); 0: the e-split pair kernel
+// dw kernel choice for E = 512 (pfc_set_dw4 / FEDFR_DW4):  -1 (default) automatic: the 4-CTA-cluster transposed kernel with
+// independent pairs (LITE) from 2048 gathered rows on -- there its shared-memory-pipe savings in the mainloop win (measured
+// r02i: 0.72 vs 0.85 ms at Bt = 4096) --, the e-split pair kernel below that, where dw4's longer epilogue chain is not yet
+// amortised by the K loop (1.73 vs 1.02 ms at Bt = 512);  0: never;  1: dw4 with cross-pair multicast;  2: dw4 LITE always.
+static int g_dw4 = getenv("FEDFR_DW4") ? atoi(getenv("FEDFR_DW4")) : -1;
+static int dw4_mode(int64_t n_rows, int emb) {       // 0 = pair kernel, 1 = multicast, 2 = LITE
+  if (emb != 512 || g_dw4 == 0) return 0;
+  if (g_dw4 < 0) return n_rows >= 2048 ? 2 : 0;
+  return g_dw4;
+}
 template <bool STAT, int STAGES>
 static size_t dw4_smem_bytes() {
   return (size_t)(STAT ? 8 * 2 * kBoxBytes : 0) + (size_t)STAGES * (2 * kBoxBytes + (STAT ? 0 : 2 * kBoxBytes)) + 4 * 256 * 4 /* part */ +
@@ -2139,6 +2168,10 @@ static int launch_dw4(const CUtensorMap& tg, const CUtensorMap& tx, const Dw4Par
   if (clusters > cap) clusters = cap;
   if (clusters > p.n_tp) clusters = p.n_tp;
   if (clusters < 1) clusters = 1;
+  if (dw4_mode(p.n_rows, 512) == 2) {      // LITE: independent pairs (no cross-pair multicast, no relay)
+    if (stat) return launch_cluster_threads(dw4_kernel<true, kDw4StagesStat, true>, kDw4Threads, clusters * 4, 4, dw4_smem_bytes<true, kDw4StagesStat>(), st, tg, tx, p);
+    return launch_cluster_threads(dw4_kernel<false, kDw4StagesStream, true>, kDw4Threads, clusters * 4, 4, dw4_smem_bytes<false, kDw4StagesStream>(), st, tg, tx, p);
+  }
   if (stat) return launch_cluster_threads(dw4_kernel<true, kDw4StagesStat>, kDw4Threads, clusters * 4, 4, dw4_smem_bytes<true, kDw4StagesStat>(), st, tg, tx, p);
   return launch_cluster_threads(dw4_kernel<false, kDw4StagesStream>, kDw4Threads, clusters * 4, 4, dw4_smem_bytes<false, kDw4StagesStream>(), st, tg, tx, p);
 }
@@ -2530,6 +2563,7 @@ struct ProbBwdPlan {
 };
 static int g_prob_dx_sms = 0;            // 0 = choose from the shape; > 0: SM budget of the dx kernel (tuning knob)
 static float g_prob_dw_rate = 0.42f;     // measured per-SM throughput of the dw kernel relative to the dx kernel
+static float g_prob_dw4_rate = 0.65f;    // the same for the dw4 kernel at the shapes it is chosen for (r02i: 0.62 at Bt = 2048, 0.79 at 4096)
 static int g_sweep_lead = 0;             // classes the faster of dx / dw may run ahead of the other (0 = not paced: measured no gain)
 
 static ProbBwdPlan make_prob_bwd_plan(int64_t n_rows, int64_t n_classes, int emb) {
@@ -2547,8 +2581,9 @@ static ProbBwdPlan make_prob_bwd_plan(int64_t n_rows, int64_t n_classes, int emb
   // dx and dw run side by side on disjoint SMs; pick the k-split whose slower side finishes first
   int64_t best = 0;
   float best_t = 0.f;
+  const float dw_rate = dw4_mode(n_rows, emb) ? g_prob_dw4_rate : g_prob_dw_rate;
   for (int64_t ks = 1; ks <= max_ks && units * ks <= sms - 16; ++ks) {
-    const float t_dx = 1.f / (float)(units * ks), t_dw = 1.f / (g_prob_dw_rate * (float)(sms - units * ks));
+    const float t_dx = 1.f / (float)(units * ks), t_dw = 1.f / (dw_rate * (float)(sms - units * ks));
     const float t = g_prob_dx_sms > 0 ? fabsf((float)(units * ks - g_prob_dx_sms)) : (t_dx > t_dw ? t_dx : t_dw);
     if (best == 0 || t < best_t) { best = ks; best_t = t; }
   }
@@ -2636,7 +2671,7 @@ static int tc_bwd_prob_enqueue(const void* w_hat, const float* inv_norm, const i
     prof_end(PH_DX, sX);
     return 0;
   };
-  const bool use_dw4 = emb == 512 && g_dw4;
+  const bool use_dw4 = dw4_mode(n_rows, emb) != 0;
   auto enqueue_dw = [&]() -> int {
     int rc = 0;
     DwParams wp{};
@@ -2801,7 +2836,7 @@ int tc_set_range_flag(int* flag, float limit_nats) {
   return 0;
 }
 void tc_set_graph(int on) { g_use_graph = on ? 1 : 0; }
-void tc_set_dw4(int on) { g_dw4 = on ? 1 : 0; }
+void tc_set_dw4(int on) { g_dw4 = on < 0 ? -1 : (on > 2 ? 2 : on); }
 void tc_set_dx_pair(int on) { g_dx_pair = on ? 1 : 0; }
 void tc_set_prefetch(int logits, int dx, int dw) { g_prefetch[0] = logits; g_prefetch[1] = dx; g_prefetch[2] = dw; }
 void tc_set_pipeline(int on, int sm_g, int sm_dx, int sm_dw, int ring) {

@@ -90,6 +90,17 @@ static inline unsigned __ballot_sync(unsigned, bool pred) {
   const int lanes = ((w + 1) * 32 <= (int)g_blockDim.x) ? 32 : (int)g_blockDim.x - w * 32;
   return lanes == 32 ? m : (m & ((1u << lanes) - 1u));
 }
+static inline unsigned __match_any_sync(unsigned, unsigned key) {          // mask of the lanes of this warp holding the same key
+  unsigned m = 0;
+  const int t = (int)g_fibers[g_cur].tid.x, w = t / 32;
+  const int lanes = ((w + 1) * 32 <= (int)g_blockDim.x) ? 32 : (int)g_blockDim.x - w * 32;
+  for (int b = 0; b < 32; ++b) {
+    const unsigned other = emu_shfl_exchange<unsigned>(key, 0, b);
+    if (b < lanes && other == key) m |= 1u << b;
+  }
+  return m;
+}
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline void __threadfence() {}
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
