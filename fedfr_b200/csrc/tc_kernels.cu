@@ -109,6 +109,7 @@ struct LogitsParams {
   // MODE_PROB (forward that keeps the unnormalised probabilities): P_ij = exp2(s2 cos_ij - row_bound_i) -> bf16 scratch
   const float* row_bound;    // [n_rows] log2 units: an upper bound of every logit of the row minus a fixed headroom
   float* target_cos;         // [n_rows] plain cosine at the target column (the backward's fp32 fix-up needs it)
+  int exp;                   // timing experiments only (FEDFR_FWD_EXP, wrong results): 1 no ex2, 2 no P store
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -692,7 +693,7 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? norm_warps(MODE) * 32
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
             const float2 zz = __ffma2_rn(make_float2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), s2v, m2v);
-            g[q] = make_float2(fast_exp2(zz.x), fast_exp2(zz.y));
+            g[q] = (p.exp & 1) ? zz : make_float2(fast_exp2(zz.x), fast_exp2(zz.y));
           }
           if (tile_has_oob) {
 #pragma unroll
@@ -727,7 +728,7 @@ __global__ void __launch_bounds__(kLogitsThreads + (NORM ? norm_warps(MODE) * 32
             fence_proxy_async_smem();
             __syncwarp();
             const int cbg = p.class_base + cb;               // the scratch spans the whole shard
-            if (lane == 0 && cbg < p.ldg && rb < p.n_rb) {
+            if (lane == 0 && cbg < p.ldg && rb < p.n_rb && !(p.exp & 2)) {
               tma_store_2d(&tmap_g, gbuf, 0, ((cbg >> 6) * p.n_rb + rb) * BM + quad * 32);
               tma_store_commit();
             }
@@ -2503,6 +2504,8 @@ static int tc_normalize_fwd_enqueue(const float* w, const int64_t* index, const 
     p.n_rb = (int)((n_rows + BM - 1) / BM); p.n_ct = (int)((cc + bn - 1) / bn);
     p.s = s; p.m = m; p.margin_kind = margin_kind; p.part_max = part_max; p.part_sum = part_sum; p.target_logit = target_logit; p.accumulate_stats = k > 0; p.prefetch = g_prefetch[0];
     p.row_bound = row_bound; p.target_cos = target_cos; p.ldg = L.c_pad;
+    static const int fwd_exp = getenv("FEDFR_FWD_EXP") ? atoi(getenv("FEDFR_FWD_EXP")) : 0;
+    p.exp = fwd_exp;
     if (has_next) {
       p.norm_w = index ? w : w + n0 * emb; p.norm_index = index ? index + n0 : nullptr; p.norm_rows = chunk_len(n0);
       p.norm_out = wh + n0 * emb; p.norm_inv = inv_norm + n0;

@@ -182,7 +182,7 @@ class CudaOps:
         bt = x_hat.shape[0]
         w_hat = self._w_hat_buffer(n, emb)
         inv = self._persist("inv_norm", (n,), torch.float32)
-        n_part = N.lib.pfc_fwd_num_partials(bt, n, emb, self.path)
+        n_part = self._const("num_partials", bt, n, emb)
         part = self._persist("part", (2, n_part, bt), torch.float32)
         tz = self._persist("target_logit", (bt,), torch.float32)
         st = _stream(self.device)
@@ -202,8 +202,24 @@ class CudaOps:
         self.last_token += 1
         return w_hat, inv, stats
 
+    def _const(self, what, bt, cs, emb):
+        """Shape-only quantities of the library (slot counts, workspace sizes): asked once per shape, not once per step."""
+        key = ("const", what, bt, cs, emb, self.path)
+        v = self._ws.get(key)
+        if v is None:
+            if what == "num_partials":
+                v = N.lib.pfc_fwd_num_partials(bt, cs, emb, self.path)
+            elif what == "prob_ws":
+                v = N.lib.pfc_prob_workspace_bytes(bt, cs, emb)
+            elif what == "bwd_prob_ws":
+                v = N.lib.pfc_bwd_prob_workspace_bytes(bt, cs, emb)
+            else:
+                v = N.lib.pfc_bwd_workspace_bytes(bt, cs, emb, self.path)
+            self._ws[key] = v
+        return v
+
     def _prob_ws(self, bt, cs, emb):
-        nbytes = N.lib.pfc_prob_workspace_bytes(bt, cs, emb)
+        nbytes = self._const("prob_ws", bt, cs, emb)
         ws = self._buf("prob", nbytes + 1024)
         return ws, (-ws.data_ptr()) % 1024, nbytes
 
@@ -219,7 +235,7 @@ class CudaOps:
         """-> stats [Bt, 3] = (row max, sum-exp at that max, target logit) of this shard."""
         bt, emb = x_hat.shape
         cs = w_hat.shape[0]
-        n_part = N.lib.pfc_fwd_num_partials(bt, cs, emb, self.path)
+        n_part = self._const("num_partials", bt, cs, emb)
         part = self._persist("part", (2, n_part, bt), torch.float32)
         tz = self._persist("target_logit", (bt,), torch.float32)
         st = _stream(self.device)
@@ -260,14 +276,14 @@ class CudaOps:
         if self._prob is not None and self._prob[3:6] == (bt, cs, emb) and (token is None or token == self._prob[6]):   # its forward kept P
             pws, poff, pbytes = self._prob[:3]
             self._prob = None
-            nbytes = N.lib.pfc_bwd_prob_workspace_bytes(bt, cs, emb)
+            nbytes = self._const("bwd_prob_ws", bt, cs, emb)
             ws = self._buf("bwd_prob", nbytes + 1024)
             off = (-ws.data_ptr()) % 1024
             N.check(N.lib.pfc_bwd_prob(N.ptr(x_hat), N.ptr(w_hat), N.ptr(inv_norm), N.ptr(label), N.ptr(row_sum), bt, cs, emb, float(s), float(m),
                                        int(margin_kind), float(inv_total_batch), N.ptr(dx), N.ptr(dw), 1 if accumulate else 0, pws.data_ptr() + poff,
                                        pbytes, ws.data_ptr() + off, ws.numel() - off, _stream(self.device)), "pfc_bwd_prob")
             return dx
-        nbytes = N.lib.pfc_bwd_workspace_bytes(bt, cs, emb, self.path)
+        nbytes = self._const("bwd_ws", bt, cs, emb)
         ws = self._buf("bwd", nbytes + 1024)
         off = (-ws.data_ptr()) % 1024
         N.check(N.lib.pfc_bwd(N.ptr(x_hat), N.ptr(w_hat), N.ptr(inv_norm), N.ptr(label), N.ptr(row_max), N.ptr(row_sum), bt, cs, emb, float(s),
