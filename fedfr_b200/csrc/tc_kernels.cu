@@ -1166,8 +1166,14 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
 constexpr int kDwEpiWarps = 8;                 // two warps per TMEM lane quadrant, each takes half of the slice's columns
 constexpr int kDwThreads = (kDwEpiWarps + 2) * 32;
 
-template <int EMB, int STAGES, int CS>
-__global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+// P2 (E = 512 only, cluster of 4): the same kernel on cta_group::2 pairs.  Pair h = cluster ranks (2h, 2h+1) computes e-slice
+// h of TWO class tiles with one M = 256 MMA (CTA of parity c: tile 2g + c, and the N-half c of x_scaled), so a CTA fills 32 KB
+// per k-block instead of 48 and reads 8 KB of operands per MMA instead of 12 (section 5a of DESIGN.md); the partial dots
+// are exchanged with the CTA that owns the same class tile in the other pair (rank ^ 2).  Epilogue unchanged.
+// EW = epilogue warps: 8 (two column halves per lane quadrant) or 16 (four column groups: half the serial chain per warp --
+// tcgen05.ld, fma, st.shared, proxy fence, TMA store per 32-column group -- which is what bounds the kernel at small K).
+template <int EMB, int STAGES, int CS, bool P2 = false, int EW = kDwEpiWarps>
+__global__ void __launch_bounds__((EW + 2) * 32, 1) dw_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
                                                            const __grid_constant__ CUtensorMap tmap_wh, const __grid_constant__ CUtensorMap tmap_dw,
                                                            const DwParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -1175,51 +1181,60 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
   constexpr int EN = EMB < 256 ? EMB : 256;              // accumulator width = N of one MMA
   constexpr int NH = EMB / EN;                           // e-slices per class tile
   constexpr bool ES = NH == 2;                           // e-split cluster: both CTAs work on the same class tile
-  static_assert(!ES || CS == 2, "the e-split arrangement is a cluster of exactly two CTAs");
+  static_assert(!ES || (!P2 && CS == 2) || (P2 && CS == 4), "the e-split arrangement is a cluster of two CTAs (four with cta_group::2 pairs)");
+  static_assert(!P2 || ES, "pairs of pairs only for E = 512");
   constexpr int NBOX = EN / 64;                          // 64-wide boxes per e-slice
-  constexpr int CW = EN / 2;                             // columns per epilogue warp
+  constexpr int NCG = EW / 4;                            // column groups (epilogue warps per lane quadrant)
+  constexpr int CW = EN / NCG;                           // columns per epilogue warp
   constexpr int NG = CW / 32;                            // 32-column groups per epilogue warp (1, 2 or 4)
-  constexpr int kContrib = ES ? 4 : 2;                   // partial dots per class row: (cluster rank x) column half
+  constexpr int kContrib = (ES ? 2 : 1) * NCG;           // partial dots per class row: (cluster rank x) column group
+  static_assert(CW >= 32 && kContrib <= 8, "epilogue warp count");
   constexpr int kABytes = 2 * kBoxBytes;                 // 128 classes x 64 rows
-  constexpr int kBBytes = NBOX * kBoxBytes;              // EN x 64 rows
+  constexpr int kBBytes = P2 ? 2 * kBoxBytes : NBOX * kBoxBytes;      // EN x 64 rows (P2: this CTA's 128-e half of it)
   constexpr int kStageBytes = kABytes + kBBytes;
   constexpr int kWBox = 32 * 128;                        // w_hat box: 32 classes x 64 e bf16 = 4 KB = one fp32 staging box [32 x 32]
   constexpr int kWWarp = (NG + 1) / 2 * kWBox;           // per-warp w_hat columns (a warp with 32 columns still loads a 64-e box)
-  constexpr int kSBox = NG == 1 ? 2 : 0;                 // extra staging boxes for the warps that own a single w_hat box
+  constexpr bool kDeep = P2 && NG == 4;                  // a third staging box per warp: three output stores in flight instead of two
+  constexpr int kSBox = NG == 1 ? 2 : (kDeep ? 1 : 0);   // extra staging boxes (warps that own a single w_hat box; the deep pipeline)
   uint8_t* smem_w = smem + STAGES * kStageBytes;         // [8 warps] w_hat boxes, reused as output staging
-  uint8_t* smem_s = smem_w + kDwEpiWarps * kWWarp;       // [8 warps][kSBox] staging (EN = 64 only)
-  float* tpart = reinterpret_cast<float*>(smem_s + kDwEpiWarps * kSBox * kWBox);   // [2][kContrib][128] partial dots
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tpart + 2 * 4 * 128);
+  uint8_t* smem_s = smem_w + EW * kWWarp;                // [EW warps][kSBox] staging
+  float* tpart = reinterpret_cast<float*>(smem_s + EW * kSBox * kWBox);   // [2][kContrib][128] partial dots
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tpart + 2 * 8 * 128);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;               // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;          // [2]
-  uint64_t* wfull = bars + 2 * STAGES + 4;               // [8 warps]
-  uint64_t* tbar = bars + 2 * STAGES + 12;               // [2][4 quadrants] all partial dots of the quadrant's rows have landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 20);
+  uint64_t* wfull = bars + 2 * STAGES + 4;               // [EW warps]
+  uint64_t* tbar = bars + 2 * STAGES + 4 + EW;           // [2][4 quadrants] all partial dots of the quadrant's rows have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12 + EW);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kb = (p.n_rows + BK - 1) / BK;
   const uint32_t crank = CS > 1 ? cluster_ctarank() : 0;
   const int n_clusters = gridDim.x / CS, cid = blockIdx.x / CS;
   constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1);
-  constexpr int kProducerWarp = kDwEpiWarps, kMmaWarp = kDwEpiWarps + 1;
+  constexpr int kProducerWarp = EW, kMmaWarp = EW + 1;
   // ES:   item i -> class tile i * n_clusters + cid (both CTAs), e-slice = cluster rank.
   // else: item i -> class tile (i * n_clusters + cid) * CS + crank, the only e-slice.  Every CTA of a cluster runs the
   //       same number of items (tiles past n_ct are phantoms: TMA zero-fills their loads and clips their stores).
-  auto tile_of = [&](int i) { return ES ? i * n_clusters + cid : (i * n_clusters + cid) * CS + (int)crank; };
-  auto more = [&](int i) { return ES ? i * n_clusters + cid < p.n_ct : (i * n_clusters + cid) * CS < p.n_ct; };
-  const int hs = ES ? (int)crank : 0;
+  // P2:   item i -> class tiles 2 (i * n_clusters + cid) + parity; e-slice = pair index.
+  const int cpar = P2 ? (int)(crank & 1) : 0;
+  auto tile_of = [&](int i) { return P2 ? 2 * (i * n_clusters + cid) + cpar : (ES ? i * n_clusters + cid : (i * n_clusters + cid) * CS + (int)crank); };
+  auto more = [&](int i) { return P2 ? 2 * (i * n_clusters + cid) < p.n_ct : (ES ? i * n_clusters + cid < p.n_ct : (i * n_clusters + cid) * CS < p.n_ct); };
+  const int hs = P2 ? (int)(crank >> 1) : (ES ? (int)crank : 0);
+  const bool mma_leader = !P2 || cpar == 0;
+  const uint32_t leader_rank = crank & ~1u;
+  const uint16_t pair_mask = (uint16_t)(3u << (2 * hs));
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CS); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kDwEpiWarps); }
-    for (int i = 0; i < kDwEpiWarps; ++i) mbar_init(&wfull[i], 1);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], P2 ? 1 : CS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], P2 ? 2 * EW : EW); }
+    for (int i = 0; i < EW; ++i) mbar_init(&wfull[i], 1);
     for (int i = 0; i < 8; ++i) mbar_init(&tbar[i], kContrib);
     fence_barrier_init();
   }
   if (warp == kProducerWarp && lane == 0) { prefetch_tmap(&tmap_g); prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_wh); prefetch_tmap(&tmap_dw); }
-  if (warp == kMmaWarp) tmem_alloc<2 * EN>(tmem_slot);
+  if (warp == kMmaWarp) { if (P2) tmem_alloc_2cta<2 * EN>(tmem_slot); else tmem_alloc<2 * EN>(tmem_slot); }
   tc_fence_before();
   if (CS > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -1232,9 +1247,20 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
         const int ct = tile_of(i);
         if (crank == 0) sweep_pace(p.sweep, ct * BM);
         for (int kb = 0; kb < n_kb; ++kb) {
-          mbar_wait(&empty[ps.stage], ps.phase ^ 1);
+          mbar_wait_cluster(&empty[ps.stage], ps.phase ^ 1);
           uint8_t* sa = smem + ps.stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
+          if (P2) {                               // both CTAs of the pair credit the leader's barrier (dx2's producer)
+            const uint32_t full_leader = mapa_u32(smem_u32(&full[ps.stage]), leader_rank);
+            if (mma_leader) mbar_arrive_expect_tx(&full[ps.stage], 2 * kStageBytes);
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb)
+              tma_load_2d_2cta(sa + hb * kBoxBytes, &tmap_g, full_leader, 0, ((2 * ct + hb) * p.n_rb + (kb >> 1)) * BM + (kb & 1) * 64);
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) tma_load_2d_2cta(sb + nb * kBoxBytes, &tmap_x, full_leader, hs * EN + cpar * 128 + nb * 64, kb * BK);
+            ps.advance(STAGES);
+            continue;
+          }
           mbar_arrive_expect_tx(&full[ps.stage], kStageBytes);
           // G scratch blocks (2 ct, kb / 2) and (2 ct + 1, kb / 2): 64 rows x 64 classes each, contiguous 8 KB
           if (ES) {                               // this CTA fetches class half `crank` for both CTAs of the cluster
@@ -1261,20 +1287,20 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
       }
     }
   } else if (warp == kMmaWarp) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, EN, true, true);
+    if (lane == 0 && mma_leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(P2 ? 2 * BM : BM, EN, true, true);
       PipeState ps;
       long long t_we = 0, t_wf = 0, t_all = clock64();
       for (int it = 0; more(it); ++it) {
         const int acc = it & 1;
         long long c0 = clock64();
-        mbar_wait(&tmem_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+        mbar_wait_cluster(&tmem_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
         t_we += clock64() - c0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * EN;
         for (int kb = 0; kb < n_kb; ++kb) {
           c0 = clock64();
-          mbar_wait(&full[ps.stage], ps.phase);
+          mbar_wait_cluster(&full[ps.stage], ps.phase);
           t_wf += clock64() - c0;
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + ps.stage * kStageBytes);
@@ -1283,12 +1309,15 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint64_t da = make_desc_sw128(a_addr + kk * 2048, kBoxBytes, 1024);
             const uint64_t db = make_desc_sw128(b_addr + kk * 2048, kBoxBytes, 1024);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb | kk) != 0);
+            if (P2) umma_bf16_ss_2cta(d_tmem, da, db, idesc, (kb | kk) != 0);
+            else umma_bf16_ss(d_tmem, da, db, idesc, (kb | kk) != 0);
           }
-          if (CS == 1) umma_commit(&empty[ps.stage]); else umma_commit_mc(&empty[ps.stage], kMask);
+          if (P2) umma_commit_2cta(&empty[ps.stage], pair_mask);
+          else if (CS == 1) umma_commit(&empty[ps.stage]);
+          else umma_commit_mc(&empty[ps.stage], kMask);
           ps.advance(STAGES);
         }
-        umma_commit(&tmem_full[acc]);
+        if (P2) umma_commit_2cta(&tmem_full[acc], pair_mask); else umma_commit(&tmem_full[acc]);
       }
       if (p.dbg && blockIdx.x == 0) { p.dbg[0] = t_we; p.dbg[1] = t_wf; p.dbg[2] = clock64() - t_all; }
     }
@@ -1301,8 +1330,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
     uint8_t* wbuf = smem_w + warp * kWWarp;
     uint8_t* sbuf = smem_s + warp * kSBox * kWBox;
     uint64_t* wbar = &wfull[warp];
-    const uint32_t peer = crank ^ 1u;
-    const int contrib = (ES ? (int)crank * 2 : 0) + chalf;
+    const uint32_t peer = P2 ? crank ^ 2u : crank ^ 1u;    // the CTA holding the other e-slice of the same class tile
+    const int contrib = (ES ? hs * NCG : 0) + chalf;
+    const uint32_t tmem_leader_empty0 = mapa_u32(smem_u32(&tmem_empty[0]), leader_rank);
     const int e_warp = hs * EN + chalf * CW;              // first e column of this warp
     long long t_wfull = 0, t_ww = 0, t_ep = 0, t_p1 = 0, t_ex = 0, t_p2 = 0;
     auto issue_w = [&](int i) {                           // this warp's w_hat rows of item i (lane 0 only)
@@ -1371,7 +1401,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
       float t = 0.f;
       if (!(ex & 2)) {
         const int buf = it & 1;
-        float* slot = tpart + (buf * 4 + contrib) * 128 + quad * 32 + lane;
+        float* slot = tpart + (buf * 8 + contrib) * 128 + quad * 32 + lane;
         *slot = dot2.x + dot2.y;
         if (ES) st_cluster_f32(mapa_u32(smem_u32(slot), peer), dot2.x + dot2.y);
         __syncwarp();                                     // one release per warp covers the 32 lanes' stores (not 32 cluster fences)
@@ -1381,9 +1411,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
         }
         if (ES) mbar_wait_cluster(&tbar[buf * 4 + quad], (uint32_t)((it >> 1) & 1));
         else mbar_wait(&tbar[buf * 4 + quad], (uint32_t)((it >> 1) & 1));
-        const float* all = tpart + buf * 4 * 128 + quad * 32 + lane;
-        t = all[0] + all[128];                            // fixed order: every warp (and both CTAs) get the same bits
-        if (ES) t = (t + all[256]) + all[384];
+        const float* all = tpart + buf * 8 * 128 + quad * 32 + lane;
+        t = all[0];                                       // fixed order: every warp (and both CTAs) get the same bits
+#pragma unroll
+        for (int c = 1; c < kContrib; ++c) t += all[c * 128];
       }
       t_ex += clock64() - c0;
       const float c1 = ok ? -t * inv_n : 0.f;
@@ -1398,9 +1429,16 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
       {
         uint32_t va[32];
         auto out_group = [&](const uint32_t (&v)[32], int g) {
-          uint8_t* orow = NG == 1 ? sbuf + (it & 1) * kWBox : wbuf + (g & (kNW - 1)) * kWBox;
+          // kDeep: groups 0..3 -> boxes (extra, w_hat box 0, w_hat box 1, extra): the extra box was last used three groups ago,
+          // the w_hat boxes were reloaded (and read into registers) since their last store -- almost nothing to wait for
+          uint8_t* orow = NG == 1 ? sbuf + (it & 1) * kWBox : (kDeep ? ((g == 0 || g == 3) ? sbuf : wbuf + (g - 1) * kWBox) : wbuf + (g & (kNW - 1)) * kWBox);
           // the store issued two groups ago (same box) must have been read; stores are committed one group each
-          if (lane == 0) { if (NG == 1) tma_store_wait_read<1>(); else tma_store_wait_read<kNW - 1>(); }
+          if (lane == 0) {
+            if (NG == 1) tma_store_wait_read<1>();
+            else if (!kDeep) tma_store_wait_read<kNW - 1>();
+            else if (g == 0) tma_store_wait_read<0>();
+            else if (g == 3) tma_store_wait_read<2>();
+          }
           __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -1435,8 +1473,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&tmem_empty[acc]);
-        if (NG > 1) tma_store_wait_read<0>();             // the staging boxes are this warp's w_hat boxes: all reads done before the reload
+        if (mma_leader) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_cluster_addr_relaxed(tmem_leader_empty0 + acc * 8);
+        if (kDeep) tma_store_wait_read<1>();              // the w_hat boxes carried groups 1 and 2; group 3 (extra box) may still be read
+        else if (NG > 1) tma_store_wait_read<0>();        // the staging boxes are this warp's w_hat boxes: all reads done before the reload
         if (more(it + 1) && !(ex & 8)) issue_w(it + 1);
       }
       __syncwarp();
@@ -1447,7 +1487,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const __grid_constant
   }
   tc_fence_before();
   if (CS > 1) cluster_sync_all(); else __syncthreads();     // peers may still multicast into / arrive on this CTA
-  if (warp == kMmaWarp) tmem_dealloc<2 * EN>(tmem_base);
+  if (warp == kMmaWarp) { if (P2) tmem_dealloc_2cta<2 * EN>(tmem_base); else tmem_dealloc<2 * EN>(tmem_base); }
 }
 
 // ================================================================================================
@@ -2081,20 +2121,33 @@ static int launch_dx(const CUtensorMap& tg, const CUtensorMap& tw, const DxParam
   return launch_dx_cs<BN, 1>(tg, tw, p, grid, st);
 }
 
-template <int EMB, int CS>
+template <int EMB, int CS, bool P2 = false, int EW = kDwEpiWarps>
 static int launch_dw_cs(const CUtensorMap& tg, const CUtensorMap& tx, const CUtensorMap& twh, const CUtensorMap& tdw, const DwParams& p, int grid,
                         cudaStream_t st) {
   constexpr int EN = EMB < 256 ? EMB : 256;
-  constexpr int kStage = 2 * kBoxBytes + (EN / 64) * kBoxBytes;
-  constexpr int NG = EN / 64;                                    // 32-column groups per epilogue warp
-  constexpr int kEpi = kDwEpiWarps * ((NG + 1) / 2) * 4096 + (NG == 1 ? kDwEpiWarps * 2 * 4096 : 0);   // w_hat boxes (= staging) [+ staging]
-  constexpr int kFixed = 4096 /* partial dots */ + 1024 /* alignment */ + 512 /* barriers */;
+  constexpr int kStage = 2 * kBoxBytes + (P2 ? 2 : EN / 64) * kBoxBytes;
+  constexpr int NG = EN / (EW / 4) / 32;                         // 32-column groups per epilogue warp
+  constexpr int kEpi = EW * ((NG + 1) / 2) * 4096 + (NG == 1 ? EW * 2 * 4096 : ((P2 && NG == 4) ? EW * 4096 : 0));   // w_hat boxes (= staging) [+ staging]
+  constexpr int kFixed = 8192 /* partial dots */ + 1024 /* alignment */ + 512 /* barriers */;
   constexpr int STAGES = (232448 - kFixed - kEpi) / kStage > 8 ? 8 : (232448 - kFixed - kEpi) / kStage;
   static_assert(STAGES >= 2, "dw kernel smem budget");
   const size_t smem = (size_t)STAGES * kStage + kEpi + kFixed;
-  return launch_cluster_threads(dw_kernel<EMB, STAGES, CS>, kDwThreads, grid, CS, smem, st, tg, tx, twh, tdw, p);
+  return launch_cluster_threads(dw_kernel<EMB, STAGES, CS, P2, EW>, (EW + 2) * 32, grid, CS, smem, st, tg, tx, twh, tdw, p);
 }
 
+static int g_dw_p2 = getenv("FEDFR_DW_P2") ? atoi(getenv("FEDFR_DW_P2")) : 0;      // 1: the pair kernel on cta_group::2 pairs (clusters of 4) for E = 512
+// E = 512, cta_group::2 pairs: clusters of four CTAs, each taking two class tiles per item
+static int launch_dw_p2(const CUtensorMap& tg, const CUtensorMap& tx, const CUtensorMap& twh, const CUtensorMap& tdw, const DwParams& p, int n_ct,
+                        int sms, cudaStream_t st) {
+  const int n_groups = (n_ct + 1) / 2;
+  int clusters = sms / 4 * 9 / 10;                       // GPC packing of 4-CTA clusters leaves a few SMs unused
+  if (clusters > sms / 4) clusters = sms / 4;
+  if (clusters > n_groups) clusters = n_groups;
+  if (clusters < 1) clusters = 1;
+  return launch_dw_cs<512, 4, true>(tg, tx, twh, tdw, p, clusters * 4, st);
+}
+
+static int g_dw_ew = getenv("FEDFR_DW_EW") ? atoi(getenv("FEDFR_DW_EW")) : 8;      // epilogue warps of the E = 512 pair kernel (8 or 16)
 template <int EMB>
 static int launch_dw(const CUtensorMap& tg, const CUtensorMap& tx, const CUtensorMap& twh, const CUtensorMap& tdw, const DwParams& p, int n_ct,
                      int cs, int sms, cudaStream_t st) {
@@ -2108,6 +2161,7 @@ static int launch_dw(const CUtensorMap& tg, const CUtensorMap& tx, const CUtenso
   const int clusters = n_groups < max_clusters ? n_groups : max_clusters;
   const int grid = clusters * cs;
   if constexpr (EMB > 256) {
+    if (g_dw_ew == 16) return launch_dw_cs<EMB, 2, false, 16>(tg, tx, twh, tdw, p, grid, st);
     return launch_dw_cs<EMB, 2>(tg, tx, twh, tdw, p, grid, st);
   } else {
     if constexpr (EMB >= 128) {
@@ -2691,7 +2745,8 @@ static int tc_bwd_prob_enqueue(const void* w_hat, const float* inv_norm, const i
       qp.inv_norm = inv_norm; qp.w_hat = wh; qp.dw = dw; qp.accumulate = accumulate_dw; qp.dbg = g_dbg; qp.exp = dw_exp;
       rc = launch_dw4(tg_mn, tx_mn, qp, pl.sm_dw, sW);
     } else switch (emb) {
-      case 512: rc = launch_dw<512>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
+      case 512: rc = g_dw_p2 ? launch_dw_p2(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, pl.sm_dw, sW)
+                             : launch_dw<512>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
       case 256: rc = launch_dw<256>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
       case 128: rc = launch_dw<128>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
       default: rc = launch_dw<64>(tg_mn, tx_mn, twh_e, tdw_e, wp, wp.n_ct, g_dw_cluster, pl.sm_dw, sW); break;
@@ -2735,7 +2790,7 @@ int tc_bwd_prob(const void* x, const void* w_hat, const float* inv_norm, const i
   kb.add(4).add(x).add(w_hat).add(inv_norm).add(label).add(row_sum).add(dx).add(dw).add(workspace).add(prob_ws).add(n_rows).add(n_classes)
       .add(workspace_bytes).add(emb).add(accumulate_dw).add(s).add(m).add(margin_kind).add(inv_total_batch).add(g_logits_pair).add(g_dx_cluster)
       .add(g_dw_cluster).add(g_prob_dx_sms).add(g_prob_dw_rate).add(g_sweep_lead).add(g_prefetch[1]).add(g_prefetch[2]).add(g_dx_pair)
-      .add(range_flag_of_current_device()).add(g_dw4);
+      .add(range_flag_of_current_device()).add(g_dw4).add(g_dw_p2).add(g_dw_ew);
   if (kb.overflow) return enqueue(st);
   return run_cached_graph(kb, st, enqueue);
 }
