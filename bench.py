@@ -397,7 +397,9 @@ def run_fedavg(args):
             "roofline": {"bound": "hbm", "kernel": "fedavg_kernel (fedavg_weighted_sum call: table upload + one launch)",
                          "achieved": (len(mine) + 1) * n_elem * 4.0 / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": (len(mine) + 1) * n_elem * 4.0 / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
-                         "ms_per_launch": kernel_ms, "peak_source": peaks["source"] + " copy bandwidth"},
+                         "ms_per_launch": kernel_ms, "peak_source": peaks["source"] + " copy bandwidth",
+                         "note": "the peak is a COPY bandwidth (1 read : 1 write); this kernel reads K client buffers per buffer it writes, and an "
+                                 "HBM stream with no read/write turnarounds can exceed the copy figure by a few percent (frac > 1 is not an error)"},
             "cpu_baseline": cpu, "parity": parity,
             "extras": {"dict_of_tensors_call_ms": ms_dict, "dict_of_tensors_call_gbs": alg_bytes / (ms_dict * 1e-3) / 1e9,
                        "note": "same call on plain state_dicts (K x 477 tensors): bound by per-tensor Python work"}}

@@ -96,6 +96,12 @@ def _normalised_weights(weights: Sequence[float]) -> List[float]:
     return [w / tot for w in weights]          # Python doubles, server.py:27 / :37
 
 
+def _as_f32(ws: Sequence[float]) -> List[float]:
+    """Python doubles -> the fp32 values torch uses for ``python_float * fp32_tensor`` (round to nearest even), as floats."""
+    import numpy as np
+    return np.asarray(ws, dtype=np.float64).astype(np.float32).tolist()
+
+
 class _Tables:
     """Pinned host staging for the pointer table (reused across calls), with numpy views for bulk fills."""
 
@@ -185,8 +191,8 @@ def weighted_sum_clients(clients: List[List[torch.Tensor]], weights_f32: List[fl
     offsets = np.zeros(n_seg + 1, dtype=np.int64)
     np.cumsum((numels + 3) // 4 * 4, out=offsets[1:])
     flat_buf = torch.empty(max(int(offsets[-1]), 4), dtype=torch.float32, device=device)
-    offs = offsets.tolist()
-    outs = [flat_buf[offs[s]:offs[s] + int(numels[s])].view(ref[s].shape) for s in range(n_seg)]
+    offs, nums = offsets.tolist(), numels.tolist()
+    outs = _split_views(flat_buf, _split_plan([(offs[s], nums[s], tuple(ref[s].shape)) for s in range(n_seg)], flat_buf.numel()))
     _tables.out_np[:n_seg] = flat_buf.data_ptr() + 4 * offsets[:-1]
     _tables.len_np[:n_seg] = numels
     _tables.dtype_np[:n_seg] = codes
@@ -229,18 +235,46 @@ def _weighted_sum_flat(models, weights_f32, device, keep_views=True):
         src[1, :] = [m.flat_i64.data_ptr() for m in models]
     _tables.w_np[:k] = weights_f32
     _launch(n_seg, k, device)
-    views = _OUT_VIEWS.get(layout)
-    if views is None:           # (key, offset, numel, shape) in the output buffer, computed once per layout
-        views = [(key, (n_f_pad + off) if is_int else off, _numel(shape), shape) for (key, shape, is_int, off) in items]
-        _OUT_VIEWS[layout] = views
+    plan = _OUT_VIEWS.get(layout)
+    if plan is None:            # computed once per layout
+        plan = _split_plan([((n_f_pad + off) if is_int else off, _numel(shape), shape) for (_, shape, is_int, off) in items],
+                           flat_buf.numel())
+        _OUT_VIEWS[layout] = plan
     out = FlatStateDict()
     out.flat_f32, out.flat_i64, out.layout = flat_buf, None, None
-    for key, off, n, shape in views:
-        dict.__setitem__(out, key, flat_buf[off:off + n].view(shape))
+    for (key, _, _, _), view in zip(items, _split_views(flat_buf, plan)):
+        dict.__setitem__(out, key, view)
     return out, flat_buf
 
 
 _OUT_VIEWS = {}
+
+
+def _split_plan(spans, total):
+    """spans[i] = (offset, numel, shape) of disjoint views of a flat buffer of ``total`` elements -> (sizes, picks): the buffer
+    is cut ONCE by ``split_with_sizes(sizes)`` (one dispatcher call for all views, gaps become unused pieces) and view i is
+    piece ``picks[i][0]``, reshaped only when it is not 1-D.  The per-view slice + view pair of the obvious loop is what
+    bounded the FlatStateDict call on the host (477 tensors: 1.4 ms against a 1.07 ms kernel)."""
+    order = sorted(range(len(spans)), key=lambda i: (spans[i][0], spans[i][1]))
+    sizes, picks, pos = [], [None] * len(spans), 0
+    for i in order:
+        off, n, shape = spans[i]
+        if off < pos:
+            raise ValueError("overlapping views")
+        if off > pos:
+            sizes.append(off - pos)
+        picks[i] = (len(sizes), None if len(shape) == 1 else shape)
+        sizes.append(n)
+        pos = off + n
+    if total > pos:
+        sizes.append(total - pos)
+    return sizes, picks
+
+
+def _split_views(flat_buf, plan):
+    sizes, picks = plan
+    parts = flat_buf.split_with_sizes(sizes)
+    return [parts[j] if shape is None else parts[j].view(shape) for j, shape in picks]
 
 
 def _numel(shape):
@@ -284,7 +318,7 @@ def FedPavg(models: List[Dict[str, torch.Tensor]], weights: Sequence[float], dev
     dev = _device_of(models, device)
     if dev.index is None:
         dev = torch.device("cuda", torch.cuda.current_device())
-    wn = [float(torch.tensor(w, dtype=torch.float64).to(torch.float32)) for w in _normalised_weights(weights)]
+    wn = _as_f32(_normalised_weights(weights))
     if _all_flat(models, None):
         staged = [m if m.flat_f32.device == dev else _flat_to(m, dev) for m in models]
         out, _ = _weighted_sum_flat(staged, wn, dev)
@@ -305,7 +339,7 @@ def FedAvg_on_FC(pretrain_fc: torch.Tensor, models: List[torch.Tensor], weights:
     if not torch.cuda.is_available():
         raise RuntimeError("fedfr_b200.FedAvg_on_FC needs a CUDA device (sm_100); there is no CPU fallback")
     dev = _device_of([{"fc": m} for m in models], device)
-    wn = [float(torch.tensor(w, dtype=torch.float64).to(torch.float32)) for w in _normalised_weights(weights)]
+    wn = _as_f32(_normalised_weights(weights))
     group = [m.to(dev, non_blocking=True).contiguous() for m in models]
     aggr = weighted_sum_segments([group], wn, dev, keep_first_term=True)[0]
     if p == 1:
@@ -344,7 +378,7 @@ def FedPavg_sharded(local_models: List[Dict[str, torch.Tensor]], local_weights: 
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
     tot = float(tot.item())
-    wn = [float(torch.tensor(w / tot, dtype=torch.float64).to(torch.float32)) for w in local_weights]
+    wn = _as_f32([w / tot for w in local_weights])
     keys = list(local_models[0].keys())
     if _segments_fn is None:
         if dev.index is None:

@@ -142,15 +142,21 @@ def build_head(device, rank, world_size, batch_size, num_classes, sample_rate, e
 @contextlib.contextmanager
 def single_rank_group(backend):
     """The reference calls torch.distributed unconditionally (partial_fc.py:122-173): give it a real 1-rank group."""
-    import socket
     import torch.distributed as dist
     if dist.is_initialized():
         yield
         return
-    with socket.socket() as so:
-        so.bind(("127.0.0.1", 0))
-        port = so.getsockname()[1]
-    dist.init_process_group(backend, init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    if os.environ.get("TORCHELASTIC_USE_AGENT_STORE"):
+        # A torchrun worker (bench.py --impl reference --gpus N>1, rank 0): the inherited switch turns every tcp:// or env://
+        # rendezvous into a CLIENT of the agent's store, so a private 1-rank group on its own port would wait for a server
+        # that does not exist.  An in-process store needs neither a socket nor the environment.
+        dist.init_process_group(backend, store=dist.HashStore(), rank=0, world_size=1)
+    else:
+        import socket
+        with socket.socket() as so:
+            so.bind(("127.0.0.1", 0))
+            port = so.getsockname()[1]
+        dist.init_process_group(backend, init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
     try:
         yield
     finally:

@@ -14,8 +14,14 @@ def _run(env_extra):
                           capture_output=True, text=True, env=env, timeout=600)
 
 
+# what a torchrun worker inherits when --nproc-per-node > 1: the agent-store switch (turns every TCP rendezvous into a client
+# of the agent's store -- the reference's private 1-rank group must not depend on it) and one OpenMP thread per worker
+TORCHRUN_ENV = {"TORCHELASTIC_USE_AGENT_STORE": "True", "TORCHELASTIC_RESTART_COUNT": "0", "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": "1",
+                "LOCAL_RANK": "0", "OMP_NUM_THREADS": "1"}
+
+
 def test_reference_arm_prints_one_json_line():
-    r = _run({"RANK": "0", "WORLD_SIZE": "2"})
+    r = _run(dict(TORCHRUN_ENV, RANK="0", WORLD_SIZE="2"))
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -26,8 +32,9 @@ def test_reference_arm_prints_one_json_line():
     assert "1000000 classes" in d["cpu_baseline"]["sample"] and "full size" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "c3" in d["config"]["workload"] and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)          # rank 0 has the box to itself: OMP_NUM_THREADS=1 is overridden
 
 
 def test_reference_arm_other_ranks_are_silent():
-    r = _run({"RANK": "1", "WORLD_SIZE": "2"})
+    r = _run(dict(TORCHRUN_ENV, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
     assert r.returncode == 0 and r.stdout.strip() == ""

@@ -27,6 +27,8 @@ def main():
     B, E, s, m = 512, 512, 64.0, 0.4
     dev = torch.device("cuda:0")
     ops = CudaOps(dev)
+    if os.environ.get("SHAPE_FWD_CHUNKS"):            # forward class chunks (default 4), normaliser blocks per SM
+        N.lib.pfc_set_fwd_overlap(int(os.environ["SHAPE_FWD_CHUNKS"]), int(os.environ.get("SHAPE_NORM_BLOCKS", "2")))
     for W in worlds:
         bt, cs = B * W, classes // W
         torch.manual_seed(100)
