@@ -445,6 +445,27 @@ def test_cosface_dense_abi_under_emulation(libs):
     assert np.array_equal(c_np, want_c.numpy()) and np.array_equal(out, (want_c * 64.0).numpy())
 
 
+def test_arcface_dense_abi_under_emulation(libs):
+    """losses.ArcFace.forward on materialised logits (losses.py:38-45): acos_ over the matrix, + m on the target column of
+    the rows with a label, cos_, mul_(s) -- in place, one pass."""
+    lib = libs["rows_abi"]
+    g = torch.Generator().manual_seed(4)
+    cosine = torch.rand(23, 37, generator=g) * 1.998 - 0.999
+    cosine[0, 0], cosine[1, 1] = 1.0, -1.0                      # the ends of acos
+    label = torch.randint(0, 37, (23,), generator=g)
+    label[::5] = -1
+    label[0], label[1] = 0, 1
+    want = cosine.clone()
+    rows = torch.where(label != -1)[0]
+    want.acos_()
+    want[rows, label[rows]] += 0.5
+    want.cos_().mul_(64.0)
+    c_np = cosine.numpy().copy()
+    assert lib.pfc_arcface_dense(_p(c_np), _p(label.numpy()), C.c_int64(23), C.c_int64(37), C.c_float(64.0), C.c_float(0.5), None) == 0
+    np.testing.assert_allclose(c_np, want.numpy(), rtol=0, atol=64.0 * 4e-7)
+    assert lib.pfc_arcface_dense(_p(c_np), _p(label.numpy()), C.c_int64(0), C.c_int64(37), C.c_float(64.0), C.c_float(0.5), None) == 0
+
+
 @pytest.mark.parametrize("world,n_rows,n_part", [(1, 33, 5), (3, 70, 2), (2, 1100, 1)])
 def test_stats_abi_under_emulation(libs, world, n_rows, n_part):
     """pfc_merge_stats + pfc_finalize_stats == the reference's max / sum-exp / target all-reduces and loss
